@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the hot path (BASELINE.json: training sequences/sec, % of roofline, vs CPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one synthetic batch: item-row gather, recurrent scan, fused logits +
+softmax-CE, backward (incl. the embedding-gradient scatter-add), global-norm clip and Adagrad -- plus the gradient
+all-reduce when N > 1 (weak scaling: every rank owns B sequences).  Workload at N=1: configs[1] of BASELINE.json
+(Reddit-like: V=10k, GRU-128, T=50, B=256).  Rank 0 prints ONE JSON line.
+
+Timing: W warm-up steps, then K steps each bracketed by CUDA events on the launching stream, an L2 flush (a 256 MiB
+memset, outside the events) between steps, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training sequences/sec"
+DEFAULT_CONFIG = "cfg2_reddit_gru128"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_work(cfg, n_tokens):
+    """SURVEY §8(d) per-unit figures x the units one launch processes."""
+    G = {"simpleRNN": 1, "LSTM": 4, "GRU": 3}[cfg["cell"]]
+    H, V = cfg["H"], cfg["V"]
+    GH = G * H
+    return {
+        "gather_bytes": n_tokens * (4 + 2 * GH * 4),
+        "scatter_bytes": n_tokens * (4 + 3 * GH * 4),
+        "rnn_fwd_flops": n_tokens * 2 * G * H * H,
+        "rnn_bwd_flops": n_tokens * 4 * G * H * H,
+        "ce_fwd_flops": n_tokens * 2 * H * V,
+        "ce_bwd_flops": n_tokens * 4 * H * V,
+        "step_flops": n_tokens * (6 * G * H * H + 6 * H * V),
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(cfg, ids, tgt, seed):
+    """The oracle port (torch-CPU fp32 restatement of the Keras/Theano arithmetic) -- the CPU baseline."""
+    import torch
+    from oracle import keras_semantics as ks
+    from seq_recommendations_b200 import synthetic
+    ws = synthetic.make_weights(cfg["cell"], cfg["V"], cfg["H"], seed=seed)
+    ora = ks.Model(cfg["cell"], cfg["act"], ws, dtype=torch.float32)
+    ti, tt = torch.tensor(ids.astype(np.int64)), torch.tensor(tgt.astype(np.int64))
+    mask = ti >= 0
+
+    def step():
+        loss, _, _ = ora.train_step(ti, tt, mask, lr=0.01, epsilon=1e-8, clipnorm=1.0)
+        return float(loss)
+    return step
+
+
+def time_cpu(cfg, steps, warmup, budget_s=25.0, sample_b=None):
+    import torch
+    from seq_recommendations_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = sample_b or cfg["B"]
+    ids, tgt = synthetic.make_batch(cfg["V"], cfg["T"], B, seed=0)
+    step = cpu_oracle_step_fn(cfg, ids, tgt, seed=0)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    ms = float(np.median(times)) * 1e3
+    return dict(value=B / (ms / 1e3), unit="sequences/sec", cores=torch.get_num_threads(), kind="port",
+                sample="%d steps of fwd+bwd+clip+Adagrad on B=%d,T=%d (oracle/keras_semantics.py, torch-CPU fp32, "
+                       "median)" % (len(times), B, cfg["T"]), ms_per_step=ms)
+
+
+def run_reference(args, cfg, name):
+    """--impl reference: the reference's CPU path.  The reference itself (Python 2 + Keras 2.0.x + Theano) cannot run
+    in this image, so the oracle port stands in."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_cpu(cfg, max(1, args.steps), max(1, min(args.warmup, 2)), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "sequences/sec", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, **{k: cfg[k] for k in ("cell", "act", "V", "H", "T", "B")}},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "sequences/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dropout", type=float, default=0.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    from seq_recommendations_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[args.config])
+    if args.impl == "reference":
+        return run_reference(args, cfg, args.config)
+
+    import torch
+    from seq_recommendations_b200 import _lib, dist
+    from seq_recommendations_b200.engine import HotPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    comm = dist.init_from_env("nccl") if world > 1 else dist.Comm()
+    dev = torch.device("cuda", local)
+
+    V, H, T, B = cfg["V"], cfg["H"], cfg["T"], cfg["B"]
+    ws = synthetic.make_weights(cfg["cell"], V, H, seed=0)
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, comm=comm, seed=rank)
+    hot.set_optimizer("adagrad", lr=0.01, epsilon=1e-8, clipnorm=1.0)
+    hot.dropout_out = args.dropout
+    n_batches = 4
+    host = [synthetic.make_batch(V, T, B, seed=100 * rank + i) for i in range(n_batches)]
+    pinned = [(torch.from_numpy(i).pin_memory(), torch.from_numpy(t).pin_memory()) for i, t in host]
+    resident = [(i.to(dev), t.to(dev)) for i, t in pinned]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        comm.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for s in range(args.warmup):
+        hot.train_batch(*resident[s % n_batches])
+    sync_all()
+
+    # ---- timed: K steps, inputs resident in HBM
+    clocks = ClockSampler(local) if rank == 0 else None
+    _lib.launch_count(reset=True)
+    hot.prof = []
+    evs = []
+    sync_all()
+    t_wall = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = hot.train_batch(*resident[s % n_batches])
+        e1.record()
+        evs.append((e0, e1))
+    sync_all()
+    wall_s = time.perf_counter() - t_wall
+    launches = _lib.launch_count()
+    phases = hot.phase_times_ms()
+    hot.prof = None
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(t)
+    step_ms = float(t.item())
+    final_loss = float(loss.item())
+
+    # ---- e2e: same step through the public call with HOST buffers (pinned H2D of ids/targets + D2H of the loss)
+    for s in range(3):
+        float(hot.train_batch(*pinned[s % n_batches]).item())
+    sync_all()
+    e2e_t = []
+    for s in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        float(hot.train_batch(*pinned[s % n_batches]).item())
+        e2e_t.append(time.perf_counter() - t0)
+    sync_all()
+    e2e_ms = float(np.mean(e2e_t)) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    comm.all_reduce_max(t)
+    e2e_ms = float(t.item())
+    clk = clocks.stop() if clocks is not None else None
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    N = B * T
+    work = algorithmic_work(cfg, N)
+    per_step = {k: v / args.steps for k, v in phases.items()}
+    dom_ms = per_step.get("ce_bwd", 0.0)
+    achieved = work["ce_bwd_flops"] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    roofline = {
+        "kernel": "seqrec_ce_backward (logits recompute + dH + dW_out, %s)" % ("fp32 SIMT"),
+        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+        "ms_per_launch": dom_ms,
+        "others": {
+            "gather_gbs": work["gather_bytes"] / (per_step.get("gather", 1e9) * 1e-3) / 1e9,
+            "scatter_gbs": work["scatter_bytes"] / (per_step.get("scatter", 1e9) * 1e-3) / 1e9,
+            "hbm_peak_gbs": peaks["hbm"],
+            "ce_fwd_tflops": work["ce_fwd_flops"] / (per_step.get("ce_fwd", 1e9) * 1e-3) / 1e12,
+        },
+    }
+    cpu = None
+    if not args.no_cpu:
+        cpu = time_cpu(cfg, 8, 2, budget_s=25.0)
+    line = {
+        "metric": METRIC, "value": world * B / (step_ms * 1e-3), "unit": "sequences/sec", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "cell": cfg["cell"], "act": cfg["act"], "V": V, "H": H, "T": T,
+                   "B_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "256 MiB memset between timed steps (outside the events)", "dropout": args.dropout,
+                   "optimizer": "adagrad lr=0.01 eps=1e-8 clipnorm=1"},
+        "clocks": clk,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 2 * B * T * 4, "d2h_bytes_per_step": 4,
+                "api": "HotPath.train_batch(pinned host ids, targets) -> loss.item()"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "phases_ms": per_step,
+        "wall_s_timed_region": wall_s,
+        "final_loss": final_loss,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

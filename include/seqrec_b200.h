@@ -1,0 +1,143 @@
+/*
+ * seqrec_b200 -- C-ABI of the B200-native next-item training / scoring hot path.
+ *
+ * The reference (efikarra/seq-recommendations) has no FFI of its own: its hot path is everything Keras/Theano
+ * executes under `self.model.fit(...)` / `self.model.predict(...)` (model.py:181, model.py:195).  The entry points
+ * below are what a binding for that path would call; each cites the reference construct it replaces.  The Python
+ * host (`seq_recommendations_b200/engine.py`) binds them with ctypes -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); nothing is allocated here
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous
+ *   - return value: 0 on success, a negative cudaError_t on launch/config failure, -1000-x for argument errors
+ *   - token order is TIME-MAJOR: token n = t*B + b, ids/targets/mask are [T][B]; pad tokens have mask 0
+ *   - weights keep the Keras layouts: W_in (F, G*H), U (H, G*H), b (G*H), W_out (H, V), b_out (V), row-major fp32
+ *   - gate order along G*H:  LSTM i,f,c,o   GRU z,r,h   simpleRNN h
+ */
+#ifndef SEQREC_B200_H_
+#define SEQREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SEQREC_CELL_SIMPLE = 0, SEQREC_CELL_LSTM = 1, SEQREC_CELL_GRU = 2 };
+enum { SEQREC_ACT_RELU = 0, SEQREC_ACT_TANH = 1, SEQREC_ACT_LINEAR = 2 };
+
+/* library / device sanity: returns the compute capability major*10+minor of the current device, or <0 */
+int seqrec_device_cc(void);
+/* ABI version of this header */
+int seqrec_abi_version(void);
+/* number of kernels this library has launched since load (or since the last call with reset != 0) */
+int seqrec_launch_count(int reset);
+
+/* ---- batch format (preprocessor.py:67-94, model.py:335 Masking) ------------------------------------------------
+ * (B,T) batch-major ids/targets (pad = negative) -> time-major ids/targets/mask; counts valid tokens into
+ * n_valid[0] (int32, must be zeroed by the caller). */
+int seqrec_format_batch(const int32_t* ids_bt, const int32_t* tgt_bt, int32_t* ids_tb, int32_t* tgt_tb,
+                        uint8_t* mask_tb, int32_t* n_valid, int B, int T, void* stream);
+
+/* ---- K1: one-hot x input-kernel == row gather (model.py:360-364 LSTM on the masked one-hot input) ---------------
+ * xp[n,:] = (mask[n] ? in_scale[n]*W_in[ids[n],:] : 0) + b.   in_scale may be NULL (no y->z dropout). */
+int seqrec_gather_rows(const float* W_in, const float* b, const int32_t* ids, const uint8_t* mask,
+                       const float* in_scale, float* xp, int64_t n_tokens, int V, int GH, void* stream);
+
+/* ---- K7: dense one_hot^T . dxp of Theano == scatter-add ----------------------------------------------
+ * dW_in[ids[n],:] += in_scale[n]*dxp[n,:] for valid tokens, warp-aggregated atomics.  Rows touched for the first time
+ * are appended to rows[] (count in n_rows[0]) using the flag array touched[V]; dW_in and touched must be all-zero
+ * on entry for untouched rows (the row-sparse optimizer restores that invariant). */
+int seqrec_scatter_add_rows(const float* dxp, const int32_t* ids, const uint8_t* mask, const float* in_scale,
+                            float* dW_in, int32_t* touched, int32_t* rows, int32_t* n_rows, int64_t n_tokens,
+                            int V, int GH, void* stream);
+
+/* union row marking for data-parallel runs: claims every valid id of ids[] in touched[] / rows[] without adding */
+int seqrec_mark_rows(const int32_t* ids, const uint8_t* mask, int32_t* touched, int32_t* rows, int32_t* n_rows,
+                     int64_t n_tokens, int V, void* stream);
+
+/* ---- K2: dense-feature input projection (RNNBaseline with [onehot || xs], model.py:245-255) ----------------------
+ * C[M,N] (+)= A[M,K] . Bm[K,N] (+ bias[N]); plain fp32 SIMT GEMM for the small feature widths of that model. */
+int seqrec_gemm_nn(const float* A, const float* Bm, const float* bias, float* C, int M, int N, int K,
+                   int accumulate, void* stream);
+/* C[M,N] += A[K,M]^T . Bm[K,N]  (weight gradients: dW = X^T . dY), atomics over K-splits; C must be pre-zeroed */
+int seqrec_gemm_tn_atomic(const float* A, const float* Bm, float* C, int M, int N, int K, void* stream);
+
+/* ---- K3: recurrent scan forward (Theano K.rnn with mask; model.py:345-352) --------------------------------------
+ * xg: in = xp [T][B][G*H], out = post-activation gates (in place).  hout [T][B][H]; cst [T][B][H] (LSTM cell
+ * state; scratch for GRU backward).  Masked steps hold state and repeat the previous output. */
+int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8_t* mask, float* hout, float* cst,
+                       int T, int B, int H, void* stream);
+
+/* ---- K4: recurrent scan backward (Theano scan gradient) ----------------------------------------------------------
+ * dhout [T][B][H] = dLoss/dHout.  xg: in = saved gates, out = dxp (pre-activation gradients, in place).
+ * Ut = U^T (G*H, H).  For GRU, cst receives r*h_{t-1} (operand of dU's candidate block). */
+int seqrec_rnn_backward(int cell, int act, float* xg, const float* Ut, const uint8_t* mask, const float* hout,
+                        float* cst, const float* dhout, int T, int B, int H, void* stream);
+/* dU (H,G*H) += sum_t hprev_t^T . dxp_t (GRU candidate block uses cst = r*hprev);  db (G*H) += sum_n dxp[n,:].
+ * dU and db must be pre-zeroed. */
+int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,
+                           int T, int B, int H, void* stream);
+/* out (cols, rows) = in (rows, cols)^T */
+int seqrec_transpose(const float* in, float* out, int rows, int cols, void* stream);
+
+/* ---- K5: TimeDistributed(Dense) + softmax + categorical_crossentropy, never materialising (N,V)
+ *          (model.py:382-384, :397; experiments_methods.py:42) -----------------------------------------------------
+ * Per token: running max m and sum-exp s over the vocabulary and the target logit zy.  With V split over `splits`
+ * partial ranges (or GPUs) the partial (m,s) live in ws_m/ws_s [splits][N]; seqrec_ce_finalize merges them.
+ * hscale: optional inverted-dropout factors (N,H) applied to hout (z->y Dropout, model.py:371-372). */
+int seqrec_ce_forward(const float* hout, const float* hscale, const float* W_out, const float* b_out,
+                      const int32_t* tgt, float* ws_m, float* ws_s, float* zy, int64_t n_tokens, int H, int V,
+                      int v_begin, int v_end, int ldw, int splits, int use_tensor_cores, void* stream);
+/* merge partial stats; ce[n] = -log(clip(exp(zy-m)/s, 1e-7, 1-1e-7))*mask; py[n] = clipped prob (model.py:108-110);
+ * coef[n] = mask * [clip inactive] (to be scaled by 1/n_valid); loss_sum[0] = sum ce (deterministic single block) */
+int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
+                       float* s_out, float* ce, float* py, float* coef, float* loss_sum, int64_t n_tokens,
+                       int splits, void* stream);
+
+/* ---- K6: backward of K5 with recomputed logits ------------------------------------------------------------------
+ * dlogit[n,v] = (exp(z-m)/s - [v==tgt]) * coef[n] * inv_nvalid[0];
+ * dh (N,H) = dlogit . W_out^T (times hscale), dW_out (H,V) += hs^T . dlogit, db_out (V) += sum_n dlogit.
+ * dW_out / db_out must be pre-zeroed; dh is overwritten (or accumulated when accumulate_dh != 0). */
+int seqrec_ce_backward(const float* hout, const float* hscale, const float* W_out, const float* b_out,
+                       const int32_t* tgt, const float* m, const float* s, const float* coef,
+                       const float* inv_nvalid, float* dh, float* dW_out, float* db_out, int64_t n_tokens, int H,
+                       int V, int v_begin, int v_end, int ldw, int accumulate_dh, int use_tensor_cores,
+                       void* stream);
+
+/* ---- K9: scoring (model.py:194-195 predict; model.py:106-112 consumer) ------------------------------------------
+ * full probabilities, batch-major (B,T,V) float32, for catalogs small enough to materialise */
+int seqrec_predict_probs(const float* hout, const float* W_out, const float* b_out, const float* m, const float* s,
+                         float* probs_btv, int T, int B, int H, int V, void* stream);
+/* top-k item ids (and their probabilities) per token row; ties broken by the lower item id.  rows index hout. */
+int seqrec_topk(const float* hout, const float* W_out, const float* b_out, const float* m, const float* s,
+                int32_t* topk_ids, float* topk_p, int64_t n_rows, int H, int V, int k, void* stream);
+
+/* ---- K8: global-norm clip + Adagrad (experiments_methods.py:41) -------------------------------------------------
+ * sumsq[0] (double, pre-zeroed) += sum g^2 */
+int seqrec_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
+int seqrec_sumsq_rows(const float* g, const int32_t* rows, const int32_t* n_rows, int GH, int max_rows,
+                      double* sumsq, void* stream);
+/* scale = (norm >= clipnorm) ? clipnorm/norm : 1 (clipnorm <= 0: no clip); a += (g*scale)^2;
+ * p -= lr*g*scale/(sqrt(a)+eps) */
+int seqrec_adagrad(float* p, const float* g, float* a, int64_t n, float lr, float eps, float clipnorm,
+                   const double* sumsq, void* stream);
+/* row-sparse variant over the touched rows; also re-zeroes those rows of g and their touched flags */
+int seqrec_adagrad_rows(float* p, float* g, float* a, const int32_t* rows, const int32_t* n_rows, int32_t* touched,
+                        int GH, int max_rows, float lr, float eps, float clipnorm, const double* sumsq,
+                        void* stream);
+
+/* ---- Dropout (model.py:362-363, :371-372): inverted-dropout factors from a counter-based RNG ---------------------
+ * out[i] = (u_i >= rate) ? 1/(1-rate) : 0 */
+int seqrec_dropout_mask(float* out, int64_t n, float rate, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- bf16 hi/lo operand staging for the tensor-core logits kernels ----------------------------------------------
+ * src (rows, cols) fp32 (optionally times scale (rows, cols)) -> hi, lo bf16 with hi+lo ~= src to 16 mantissa bits.
+ * transpose != 0 writes (cols, rows).  ld_out = leading dimension (elements) of the outputs. */
+int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols,
+                      int64_t ld_out, int transpose, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQREC_B200_H_ */

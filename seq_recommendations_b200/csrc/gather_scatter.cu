@@ -1,0 +1,225 @@
+// K1 row gather, K7 warp-aggregated scatter-add, and the (B,T)->(T,B) batch formatter.
+//
+// Replaces the dense one-hot (N,V).(V,G*H) product Theano runs for `LSTM(...)(masked one-hot)` (model.py:360-364)
+// and the dense one_hot^T . dxp gradient.  Both are HBM-bound; the roofline figures in DESIGN.md are
+// N*(4 + 2*G*H*4) B for the gather and N*(4 + 3*G*H*4) B for the scatter-add.
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------------------------------------------
+// (B,T) -> (T,B) ids/targets/mask; pad = negative id.  Also counts valid tokens.
+__global__ void format_batch_kernel(const int32_t* __restrict__ ids_bt, const int32_t* __restrict__ tgt_bt,
+                                    int32_t* __restrict__ ids_tb, int32_t* __restrict__ tgt_tb,
+                                    uint8_t* __restrict__ mask_tb, int32_t* __restrict__ n_valid, int B, int T) {
+  __shared__ int32_t tile_i[32][33];
+  __shared__ int32_t tile_t[32][33];
+  const int b0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  int cnt = 0;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int b = b0 + r, t = t0 + threadIdx.x;
+    int32_t vi = -1, vt = -1;
+    if (b < B && t < T) {
+      vi = ids_bt[(int64_t)b * T + t];
+      vt = tgt_bt ? tgt_bt[(int64_t)b * T + t] : 0;
+    }
+    tile_i[r][threadIdx.x] = vi;
+    tile_t[r][threadIdx.x] = vt;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int t = t0 + r, b = b0 + threadIdx.x;
+    if (t < T && b < B) {
+      int32_t vi = tile_i[threadIdx.x][r];
+      int32_t vt = tile_t[threadIdx.x][r];
+      bool ok = vi >= 0;
+      ids_tb[(int64_t)t * B + b] = vi;
+      if (tgt_tb) tgt_tb[(int64_t)t * B + b] = ok ? vt : -1;
+      mask_tb[(int64_t)t * B + b] = ok ? 1 : 0;
+      cnt += ok ? 1 : 0;
+    }
+  }
+  cnt = (int)warp_sum((float)cnt);
+  if (threadIdx.x == 0 && cnt) atomicAdd(n_valid, cnt);
+}
+
+extern "C" int seqrec_format_batch(const int32_t* ids_bt, const int32_t* tgt_bt, int32_t* ids_tb, int32_t* tgt_tb,
+                                   uint8_t* mask_tb, int32_t* n_valid, int B, int T, void* stream) {
+  SEQREC_ARG(B > 0 && T > 0, 1);
+  dim3 grid(ceil_div(T, 32), ceil_div(B, 32)), block(32, 8);
+  format_batch_kernel<<<grid, block, 0, as_stream(stream)>>>(ids_bt, tgt_bt, ids_tb, tgt_tb, mask_tb, n_valid, B, T);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K1: xp[n,:] = (mask ? scale*W_in[id,:] : 0) + b.   One thread per float4 of the output, consecutive threads on
+// consecutive 16-byte chunks of one row (coalesced reads of the table row and coalesced streaming stores).
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ W, const float* __restrict__ bias, const int32_t* __restrict__ ids,
+                   const uint8_t* __restrict__ mask, const float* __restrict__ in_scale, float* __restrict__ xp,
+                   int64_t n_tokens, int GH) {
+  if (VEC4) {
+    const int chunks = GH >> 2;
+    const int64_t total = n_tokens * chunks;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t n = i / chunks;
+      const int c = (int)(i - n * chunks);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mask[n]) {
+        const int32_t id = ids[n];
+        v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)id * GH) + c);
+        if (in_scale) {
+          const float s = in_scale[n];
+          v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        }
+      }
+      if (bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      }
+      st_stream_f4(reinterpret_cast<float4*>(xp + n * GH) + c, v);
+    }
+  } else {
+    const int64_t total = n_tokens * GH;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t n = i / GH;
+      const int c = (int)(i - n * GH);
+      float v = 0.f;
+      if (mask[n]) {
+        v = __ldg(W + (int64_t)ids[n] * GH + c);
+        if (in_scale) v *= in_scale[n];
+      }
+      if (bias) v += __ldg(bias + c);
+      xp[i] = v;
+    }
+  }
+}
+
+extern "C" int seqrec_gather_rows(const float* W_in, const float* b, const int32_t* ids, const uint8_t* mask,
+                                  const float* in_scale, float* xp, int64_t n_tokens, int V, int GH, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && GH > 0, 1);
+  const bool vec = (GH % 4 == 0) && ((reinterpret_cast<uintptr_t>(W_in) | reinterpret_cast<uintptr_t>(xp) |
+                                      reinterpret_cast<uintptr_t>(b)) % 16 == 0);
+  const int64_t work = vec ? n_tokens * (GH / 4) : n_tokens * GH;
+  int blocks = (int)((work + 255) / 256);
+  const int cap = SEQREC_NUM_SMS * 16;  // grid-stride: 8 resident CTAs/SM x 2 waves
+  if (blocks > cap) blocks = cap;
+  if (vec)
+    gather_rows_kernel<true><<<blocks, 256, 0, as_stream(stream)>>>(W_in, b, ids, mask, in_scale, xp, n_tokens, GH);
+  else
+    gather_rows_kernel<false><<<blocks, 256, 0, as_stream(stream)>>>(W_in, b, ids, mask, in_scale, xp, n_tokens, GH);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K7: dW[id[n],:] += scale[n]*dxp[n,:].  One warp owns 32 consecutive tokens.  __match_any_sync groups the lanes
+// whose tokens hit the same table row; the group's rows are summed in registers by the whole warp and leave as
+// ONE vector reduction per 16-byte chunk (warp-aggregated atomics).  The group leader also claims the row in the
+// touched[] flag array and appends it to the row list that drives the row-sparse optimizer.
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const float* __restrict__ dxp, const int32_t* __restrict__ ids,
+                        const uint8_t* __restrict__ mask, const float* __restrict__ in_scale,
+                        float* __restrict__ dW, int32_t* __restrict__ touched, int32_t* __restrict__ rows,
+                        int32_t* __restrict__ n_rows, int64_t n_tokens, int GH) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (GH & 3) == 0;
+  for (int64_t base = warp_global * 32; base < n_tokens; base += n_warps * 32) {
+    const int64_t n = base + lane;
+    int32_t id = -1;
+    float sc = 1.0f;
+    if (n < n_tokens && mask[n]) {
+      id = ids[n];
+      if (in_scale) sc = in_scale[n];
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, id);
+    const bool leader = (id >= 0) && (lane == (__ffs(peers) - 1));
+    if (leader) {
+      if (atomicExch(touched + id, 1) == 0) {
+        const int slot = atomicAdd(n_rows, 1);
+        rows[slot] = id;
+      }
+    }
+    unsigned leaders = __ballot_sync(0xffffffffu, leader);
+    while (leaders) {
+      const int l = __ffs(leaders) - 1;
+      leaders &= leaders - 1;
+      const unsigned grp = __shfl_sync(0xffffffffu, peers, l);
+      const int32_t gid = __shfl_sync(0xffffffffu, id, l);
+      float* dst = dW + (int64_t)gid * GH;
+      // uniform trip counts: every lane runs every iteration so the shuffles below stay convergent
+      if (vec) {
+        const int chunks = GH >> 2;
+        for (int c0 = 0; c0 < chunks; c0 += 32) {
+          const int c = c0 + lane;
+          const bool on = c < chunks;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          unsigned g = grp;
+          while (g) {
+            const int m = __ffs(g) - 1;
+            g &= g - 1;
+            const float s = __shfl_sync(0xffffffffu, sc, m);
+            if (on) {
+              const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(dxp + (base + m) * GH) + c);
+              acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
+            }
+          }
+          if (on) red_add_f4(dst + 4 * c, acc);
+        }
+      } else {
+        for (int c0 = 0; c0 < GH; c0 += 32) {
+          const int c = c0 + lane;
+          const bool on = c < GH;
+          float acc = 0.f;
+          unsigned g = grp;
+          while (g) {
+            const int m = __ffs(g) - 1;
+            g &= g - 1;
+            const float s = __shfl_sync(0xffffffffu, sc, m);
+            if (on) acc += s * dxp[(base + m) * GH + c];
+          }
+          if (on) atomicAdd(dst + c, acc);
+        }
+      }
+    }
+  }
+}
+
+extern "C" int seqrec_scatter_add_rows(const float* dxp, const int32_t* ids, const uint8_t* mask,
+                                       const float* in_scale, float* dW_in, int32_t* touched, int32_t* rows,
+                                       int32_t* n_rows, int64_t n_tokens, int V, int GH, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && GH > 0, 1);
+  const int64_t warps = (n_tokens + 31) / 32;
+  int blocks = (int)((warps + 7) / 8);
+  const int cap = SEQREC_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  scatter_add_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dxp, ids, mask, in_scale, dW_in, touched, rows,
+                                                                 n_rows, n_tokens, GH);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Data-parallel helper: after a dense all-reduce of dW_in every rank must update the UNION of touched rows.
+__global__ void __launch_bounds__(256)
+mark_rows_kernel(const int32_t* __restrict__ ids, const uint8_t* __restrict__ mask, int32_t* __restrict__ touched,
+                 int32_t* __restrict__ rows, int32_t* __restrict__ n_rows, int64_t n_tokens) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < n_tokens; n += (int64_t)gridDim.x * blockDim.x) {
+    if (mask ? (mask[n] != 0) : (ids[n] >= 0)) {
+      const int32_t id = ids[n];
+      if (id >= 0 && atomicExch(touched + id, 1) == 0) rows[atomicAdd(n_rows, 1)] = id;
+    }
+  }
+}
+
+extern "C" int seqrec_mark_rows(const int32_t* ids, const uint8_t* mask, int32_t* touched, int32_t* rows,
+                                int32_t* n_rows, int64_t n_tokens, int V, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0, 1);
+  int blocks = (int)((n_tokens + 255) / 256);
+  if (blocks > SEQREC_NUM_SMS * 8) blocks = SEQREC_NUM_SMS * 8;
+  mark_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, mask, touched, rows, n_rows, n_tokens);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,225 @@
+// K8: global-norm clip + Adagrad, dense and row-sparse (experiments_methods.py:41:
+// Adagrad(lr, epsilon=1e-08, decay=0.0, clipnorm=1.)), plus the dropout-factor generator and the bf16 hi/lo splitter
+// that stages operands for the tensor-core logits kernels.  All HBM-bound elementwise passes.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = i0; i < n4; i += stride) {
+      const float4 v = __ldg(g4 + i);
+      acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    }
+    for (int64_t i = (n4 << 2) + i0; i < n; i += stride) acc += (double)(g[i] * g[i]);
+  } else {
+    for (int64_t i = i0; i < n; i += stride) acc += (double)(g[i] * g[i]);
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// one warp per touched row
+__global__ void __launch_bounds__(256)
+sumsq_rows_kernel(const float* __restrict__ g, const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows,
+                  int GH, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31;
+  const int nr = n_rows[0];
+  double acc = 0.0;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nr; w += (gridDim.x * blockDim.x) >> 5) {
+    const float* row = g + (size_t)rows[w] * GH;
+    for (int c = lane; c < GH; c += 32) acc += (double)(row[c] * row[c]);
+  }
+  acc = warp_sum_d(acc);
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0 && v != 0.0) atomicAdd(out, v);
+  }
+}
+
+__device__ __forceinline__ float clip_scale(const double* sumsq, float clipnorm) {
+  if (!(clipnorm > 0.f) || sumsq == nullptr) return 1.0f;
+  const float norm = (float)sqrt(sumsq[0]);
+  return (norm >= clipnorm) ? clipnorm / norm : 1.0f;  // Keras clip_norm: K.switch(n >= c, g*c/n, g)
+}
+
+__global__ void __launch_bounds__(256)
+adagrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ a, int64_t n, float lr,
+               float eps, float clipnorm, const double* __restrict__ sumsq) {
+  const float sc = clip_scale(sumsq, clipnorm);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gv = g[i] * sc;
+    const float av = a[i] + gv * gv;
+    a[i] = av;
+    p[i] = p[i] - lr * gv / (sqrtf(av) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adagrad_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ a,
+                    const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows,
+                    int32_t* __restrict__ touched, int GH, float lr, float eps, float clipnorm,
+                    const double* __restrict__ sumsq) {
+  const float sc = clip_scale(sumsq, clipnorm);
+  const int lane = threadIdx.x & 31;
+  const int nr = n_rows[0];
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nr; w += (gridDim.x * blockDim.x) >> 5) {
+    const int32_t row = rows[w];
+    const size_t off = (size_t)row * GH;
+    for (int c = lane; c < GH; c += 32) {
+      const float gv = g[off + c] * sc;
+      const float av = a[off + c] + gv * gv;
+      a[off + c] = av;
+      p[off + c] = p[off + c] - lr * gv / (sqrtf(av) + eps);
+      g[off + c] = 0.f;  // restore the all-zero invariant of the dense gradient buffer
+    }
+    if (lane == 0) touched[row] = 0;
+  }
+}
+
+static int grid_for(int64_t n, int per_block) {
+  int64_t b = (n + per_block - 1) / per_block;
+  const int cap = SEQREC_NUM_SMS * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+extern "C" int seqrec_sumsq(const float* g, int64_t n, double* sumsq, void* stream) {
+  SEQREC_ARG(n > 0, 1);
+  sumsq_kernel<<<grid_for(n, 256 * 8), 256, 0, as_stream(stream)>>>(g, n, sumsq);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int seqrec_sumsq_rows(const float* g, const int32_t* rows, const int32_t* n_rows, int GH, int max_rows,
+                                 double* sumsq, void* stream) {
+  SEQREC_ARG(GH > 0 && max_rows > 0, 1);
+  sumsq_rows_kernel<<<grid_for(max_rows, 8), 256, 0, as_stream(stream)>>>(g, rows, n_rows, GH, sumsq);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int seqrec_adagrad(float* p, const float* g, float* a, int64_t n, float lr, float eps, float clipnorm,
+                              const double* sumsq, void* stream) {
+  SEQREC_ARG(n > 0, 1);
+  adagrad_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(p, g, a, n, lr, eps, clipnorm, sumsq);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int seqrec_adagrad_rows(float* p, float* g, float* a, const int32_t* rows, const int32_t* n_rows,
+                                   int32_t* touched, int GH, int max_rows, float lr, float eps, float clipnorm,
+                                   const double* sumsq, void* stream) {
+  SEQREC_ARG(GH > 0 && max_rows > 0, 1);
+  adagrad_rows_kernel<<<grid_for(max_rows, 8), 256, 0, as_stream(stream)>>>(p, g, a, rows, n_rows, touched, GH, lr,
+                                                                            eps, clipnorm, sumsq);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dropout factors.  Theano's MRG31k3p stream cannot be reproduced, so only the distribution is kept:
+// out = 0 with probability `rate`, else 1/(1-rate).  Counter-based (splitmix64 of seed, offset+i): reproducible and
+// independent of the launch geometry.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(float* __restrict__ out, int64_t n, float rate, uint64_t seed, uint64_t offset) {
+  const float keep = 1.0f / (1.0f - rate);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = splitmix64(splitmix64(seed) ^ (offset + (uint64_t)i));
+    const float u = (float)(r >> 40) * (1.0f / 16777216.0f);
+    out[i] = (u >= rate) ? keep : 0.f;
+  }
+}
+
+extern "C" int seqrec_dropout_mask(float* out, int64_t n, float rate, uint64_t seed, uint64_t offset, void* stream) {
+  SEQREC_ARG(n > 0 && rate >= 0.f && rate < 1.f, 1);
+  dropout_mask_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(out, n, rate, seed, offset);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits between them.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, const float* __restrict__ scale, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, int64_t rows, int64_t cols, int64_t ld_out) {
+  const int64_t total = rows * cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols, c = i - r * cols;
+    float x = src[i];
+    if (scale) x *= scale[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi[r * ld_out + c] = h;
+    if (lo) lo[r * ld_out + c] = l;
+  }
+}
+
+// transposing variant through a 32x32 shared-memory tile: out is (cols, rows) with leading dimension ld_out
+__global__ void split_bf16_t_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t rows,
+                                    int64_t cols, int64_t ld_out) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    float x = 0.f;
+    if (r < rows && c < cols) {
+      x = src[r * cols + c];
+      if (scale) x *= scale[r * cols + c];
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float x = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[c * ld_out + r] = h;
+      if (lo) lo[c * ld_out + r] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+extern "C" int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, int64_t rows,
+                                 int64_t cols, int64_t ld_out, int transpose, void* stream) {
+  SEQREC_ARG(rows > 0 && cols > 0 && ld_out > 0, 1);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
+  if (!transpose) {
+    split_bf16_kernel<<<grid_for(rows * cols, 256 * 4), 256, 0, as_stream(stream)>>>(src, scale, h, l, rows, cols,
+                                                                                     ld_out);
+  } else {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    SEQREC_ARG(grid.y <= 65535, 2);
+    split_bf16_t_kernel<<<grid, block, 0, as_stream(stream)>>>(src, scale, h, l, rows, cols, ld_out);
+  }
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,496 @@
+"""Device-side orchestration of the hot path: one `HotPath` object owns the weights, gradients, optimizer state and
+work buffers in HBM and sequences the C-ABI kernels (include/seqrec_b200.h) on the current CUDA stream.
+
+What it replaces in the reference: everything Keras/Theano executes under `self.model.fit(...)`,
+`self.model.evaluate(...)` and `self.model.predict(...)` (model.py:181, :195, :198) for the recurrent models
+(model.py:241-258, :322-403) trained with Adagrad + clipnorm (experiments_methods.py:41-42).
+
+PyTorch is plumbing here (device memory, streams, NCCL); every arithmetic step of the path is a kernel of
+libseqrec_b200.so.  There is no CPU path: constructing a HotPath without CUDA or without the library raises.
+
+HBM layout (all fp32 unless noted; token n = t*B + b, time-major):
+  weights   W_in (F,G*H) | flat[U (H,G*H) | b (G*H) | W_out (H,V) | b_out (V)]         Keras layouts, row-major
+  grads     dW_in (F,G*H) zero-invariant + touched flags + row list | flat like the weights
+  accum     Adagrad accumulators, same shapes
+  per batch ids/tgt int32 [T][B], mask u8 [T][B], xg [T][B][G*H] (xp -> gates -> dxp in place),
+            hout [T][B][H], cst [T][B][H], dh [T][B][H], per-token stats m,s,zy,ce,py,coef [N], ws [splits][N]
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, CELL, call, ptr
+from .dist import Comm, embedding_grad_mode
+
+GATES = {"simpleRNN": 1, "LSTM": 4, "GRU": 3}
+NUM_SMS = 148
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class _Work:
+    """Per-(B,T) work buffers."""
+
+    def __init__(self, hp, B, T):
+        dev = hp.device
+        N = B * T
+        f32, i32 = torch.float32, torch.int32
+        self.B, self.T, self.N = B, T, N
+        self.ids_bt = torch.empty((B, T), dtype=i32, device=dev)
+        self.tgt_bt = torch.empty((B, T), dtype=i32, device=dev)
+        self.ids = torch.empty((T, B), dtype=i32, device=dev)
+        self.tgt = torch.empty((T, B), dtype=i32, device=dev)
+        self.mask = torch.empty((T, B), dtype=torch.uint8, device=dev)
+        self.n_valid_i = torch.zeros(1, dtype=i32, device=dev)
+        self.xg = torch.empty((T, B, hp.GH), dtype=f32, device=dev)
+        self.hout = torch.empty((T, B, hp.H), dtype=f32, device=dev)
+        self.cst = torch.empty((T, B, hp.H), dtype=f32, device=dev)
+        self.dh = torch.empty((T, B, hp.H), dtype=f32, device=dev)
+        self.splits = hp._ce_splits(N)
+        self.ws_m = torch.empty((self.splits, N), dtype=f32, device=dev)
+        self.ws_s = torch.empty((self.splits, N), dtype=f32, device=dev)
+        self.m = torch.empty(N, dtype=f32, device=dev)
+        self.s = torch.empty(N, dtype=f32, device=dev)
+        self.zy = torch.zeros(N, dtype=f32, device=dev)
+        self.ce = torch.empty(N, dtype=f32, device=dev)
+        self.py = torch.empty(N, dtype=f32, device=dev)
+        self.coef = torch.empty(N, dtype=f32, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=f32, device=dev)
+        self.hscale = None
+        self.in_scale = None
+        self.x_dense = None
+        # pinned staging for host batches
+        self.pin_ids = torch.empty((B, T), dtype=i32, pin_memory=True)
+        self.pin_tgt = torch.empty((B, T), dtype=i32, pin_memory=True)
+
+
+class HotPath:
+    def __init__(self, cell, act, in_dim, hidden, n_items, out_bias=False, input_kind="ids", weights=None,
+                 device=None, comm=None, seed=0):
+        if not torch.cuda.is_available():
+            raise _lib.SeqrecError("seq_recommendations_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        _lib.load()
+        if cell not in CELL:
+            raise ValueError("rnn_type must be one of %s" % sorted(CELL))
+        if act not in ACT:
+            raise ValueError("activation must be one of %s" % sorted(ACT))
+        if input_kind not in ("ids", "dense"):
+            raise ValueError(input_kind)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.cell, self.act = cell, act
+        self.G = GATES[cell]
+        self.F, self.H, self.V = int(in_dim), int(hidden), int(n_items)
+        self.GH = self.G * self.H
+        self.out_bias = bool(out_bias)
+        self.input_kind = input_kind
+        self.comm = comm if comm is not None else Comm()
+        self.dropout_in = 0.0
+        self.dropout_out = 0.0
+        self.seed = int(seed)
+        self._rng_offset = 0
+        self._work = {}
+        f32 = torch.float32
+        dev = self.device
+        # flat parameter / gradient / accumulator buffers: U | b | W_out | b_out (64-float aligned segments)
+        sizes = [self.H * self.GH, self.GH, self.H * self.V, self.V if self.out_bias else 0]
+        offs, o = [], 0
+        for s in sizes:
+            offs.append(o)
+            o += _align(s)
+        self._seg = list(zip(offs, sizes))
+        self.flat_p = torch.zeros(o, dtype=f32, device=dev)
+        self.flat_g = torch.zeros(o, dtype=f32, device=dev)
+        self.flat_a = torch.zeros(o, dtype=f32, device=dev)
+
+        def views(flat):
+            U = flat[offs[0]:offs[0] + sizes[0]].view(self.H, self.GH)
+            b = flat[offs[1]:offs[1] + sizes[1]]
+            Wo = flat[offs[2]:offs[2] + sizes[2]].view(self.H, self.V)
+            bo = flat[offs[3]:offs[3] + sizes[3]] if self.out_bias else None
+            return U, b, Wo, bo
+
+        self.U, self.b, self.W_out, self.b_out = views(self.flat_p)
+        self.dU, self.db, self.dW_out, self.db_out = views(self.flat_g)
+        self.W_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
+        self.dW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
+        self.aW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
+        self.Ut = torch.empty((self.GH, self.H), dtype=f32, device=dev)
+        self.touched = torch.zeros(self.F, dtype=torch.int32, device=dev)
+        self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
+        self.n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.inv_nvalid = torch.ones(1, dtype=f32, device=dev)
+        self.trainable = {"W_in": True, "U": True, "b": True, "W_out": True, "b_out": True}
+        self.opt = None
+        self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
+        if weights is not None:
+            self.set_weights(weights)
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _mark(self, name):
+        """Phase boundary for bench.py's per-kernel timing: a CUDA event on the launching stream."""
+        if self.prof is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self.prof.append((name, ev))
+
+    def phase_times_ms(self):
+        """Elapsed ms between consecutive marks, summed per phase name (call after a synchronize)."""
+        out = {}
+        for (name, ev), (_, nxt) in zip(self.prof[:-1], self.prof[1:]):
+            if name != "end":
+                out[name] = out.get(name, 0.0) + ev.elapsed_time(nxt)
+        return out
+
+    @property
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ce_splits(self, N):
+        tiles = (N + 63) // 64
+        v_tiles = (self.V + 63) // 64
+        s = max(1, min(v_tiles, math.ceil(2 * NUM_SMS / tiles)))
+        return s
+
+    def work(self, B, T):
+        key = (B, T)
+        w = self._work.get(key)
+        if w is None:
+            if len(self._work) > 4:
+                self._work.clear()
+            w = self._work[key] = _Work(self, B, T)
+        return w
+
+    def weight_list(self):
+        ws = [self.W_in, self.U, self.b, self.W_out]
+        if self.out_bias:
+            ws.append(self.b_out)
+        return ws
+
+    def get_weights(self):
+        """Keras `get_weights()` order: [W_in, U, b, W_out (, b_out)] as float32 numpy arrays."""
+        return [w.detach().cpu().numpy().copy() for w in self.weight_list()]
+
+    def set_weights(self, weights):
+        ws = self.weight_list()
+        if len(weights) != len(ws):
+            raise ValueError("expected %d weight arrays, got %d" % (len(ws), len(weights)))
+        for dst, src in zip(ws, weights):
+            src = np.asarray(src, dtype=np.float32)
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError("weight shape %s does not match %s" % (src.shape, tuple(dst.shape)))
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+
+    def reset_optimizer_state(self):
+        self.flat_a.zero_()
+        self.aW_in.zero_()
+
+    def set_optimizer(self, kind="adagrad", lr=0.01, epsilon=1e-8, clipnorm=0.0, decay=0.0):
+        if kind != "adagrad":
+            raise NotImplementedError("only Adagrad (the reference's optimizer, experiments_methods.py:41) is built")
+        if decay:
+            raise NotImplementedError("learning-rate decay is never used by the reference (decay=0.0)")
+        self.opt = dict(kind=kind, lr=float(lr), eps=float(epsilon), clipnorm=float(clipnorm or 0.0))
+        self.reset_optimizer_state()
+
+    # ------------------------------------------------------------------------------------------------ batch ingest
+    def _stage(self, w, ids, tgt, x_dense=None):
+        """Host (numpy / pinned torch) or device batch -> time-major device buffers.  ids (B,T) int32, pad < 0."""
+        st = self.stream
+
+        def to_dev(dst, pin, src):
+            if src is None:
+                return None
+            if isinstance(src, torch.Tensor):
+                if src.device.type == "cuda":
+                    dst.copy_(src, non_blocking=True)
+                else:
+                    dst.copy_(src, non_blocking=True)  # pinned source: async H2D
+            else:
+                pin.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)))
+                dst.copy_(pin, non_blocking=True)
+            return dst
+
+        w.n_valid_i.zero_()
+        w.x_dense = None
+        if x_dense is None:
+            to_dev(w.ids_bt, w.pin_ids, ids)
+            have_t = tgt is not None
+            if have_t:
+                to_dev(w.tgt_bt, w.pin_tgt, tgt)
+            call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
+                 ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, st)
+        else:
+            # dense-feature input (RNNBaseline): x_dense (B,T,F) float; mask = any(x != 0) (model.py:246)
+            xd = x_dense if isinstance(x_dense, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(x_dense, dtype=np.float32))
+            xd = xd.to(self.device, dtype=torch.float32, non_blocking=True)
+            w.x_dense = xd.permute(1, 0, 2).contiguous()
+            valid_bt = (xd != 0).any(dim=-1)
+            marker = torch.where(valid_bt, 0, -1).to(torch.int32)
+            w.ids_bt.copy_(marker)
+            have_t = tgt is not None
+            if have_t:
+                to_dev(w.tgt_bt, w.pin_tgt, tgt)
+            call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
+                 ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, st)
+
+    def _dropout(self, shape, rate):
+        t = torch.empty(shape, dtype=torch.float32, device=self.device)
+        n = t.numel()
+        call("seqrec_dropout_mask", ptr(t), n, float(rate), self.seed, self._rng_offset, self.stream)
+        self._rng_offset += n
+        return t
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _forward_hidden(self, w, training):
+        st = self.stream
+        w.in_scale = None
+        w.hscale = None
+        self._mark("gather")
+        if w.x_dense is None:
+            if training and self.dropout_in > 0:
+                w.in_scale = self._dropout((w.N,), self.dropout_in)
+            call("seqrec_gather_rows", ptr(self.W_in), ptr(self.b), ptr(w.ids), ptr(w.mask), ptr(w.in_scale),
+                 ptr(w.xg), w.N, self.F, self.GH, st)
+        else:
+            call("seqrec_gemm_nn", ptr(w.x_dense), ptr(self.W_in), ptr(self.b), ptr(w.xg), w.N, self.GH, self.F, 0, st)
+        self._mark("rnn_fwd")
+        call("seqrec_rnn_forward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(w.mask), ptr(w.hout),
+             ptr(w.cst), w.T, w.B, self.H, st)
+        self._mark("misc")
+        if training and self.dropout_out > 0:
+            w.hscale = self._dropout((w.N, self.H), self.dropout_out)
+
+    def _forward_ce(self, w, with_targets=True):
+        st = self.stream
+        self._mark("ce_fwd")
+        call("seqrec_ce_forward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
+             ptr(w.tgt) if with_targets else None, ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy), w.N, self.H, self.V, 0,
+             self.V, self.V, w.splits, 0, st)
+        call("seqrec_ce_finalize", ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
+             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, w.splits, st)
+        self._mark("misc")
+
+    # ------------------------------------------------------------------------------------------------ public steps
+    def loss_batch(self, ids, tgt, x_dense=None):
+        """Forward only: returns (loss_sum, n_valid) device tensors of THIS rank's batch (evaluate path)."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        self._stage(w, ids, tgt, x_dense)
+        self._forward_hidden(w, training=False)
+        self._forward_ce(w)
+        return w.loss_sum.clone(), w.n_valid_i.to(torch.float32)
+
+    def train_batch(self, ids, tgt, x_dense=None):
+        """One optimisation step on the global batch (this rank's shard).  Returns the global masked-mean loss as a
+        one-element device tensor (no host sync)."""
+        if self.opt is None:
+            raise _lib.SeqrecError("compile_model / set_optimizer must be called before training")
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        st = self.stream
+        comm = self.comm
+        self._mark("ingest")
+        self._stage(w, ids, tgt, x_dense)
+        n_valid = w.n_valid_i.to(torch.float32)
+        comm.all_reduce_sum(n_valid)
+        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        self._forward_hidden(w, training=True)
+        self._forward_ce(w)
+        loss_sum = w.loss_sum
+        comm.all_reduce_sum(loss_sum)
+        loss = loss_sum * self.inv_nvalid
+
+        # ---- backward
+        self.flat_g.zero_()
+        self._mark("ce_bwd")
+        call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt), ptr(w.m),
+             ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out), w.N, self.H,
+             self.V, 0, self.V, self.V, 0, 0, st)
+        self._mark("rnn_bwd")
+        call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),
+             ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        self._mark("rnn_wgrad")
+        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
+             w.T, w.B, self.H, st)
+        self._mark("allreduce")
+        comm.all_reduce_sum(self.flat_g)
+
+        # ---- input-kernel gradient
+        self._mark("scatter")
+        self.n_rows.zero_()
+        if w.x_dense is None:
+            if not comm.enabled:
+                call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
+                     ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
+            elif embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense":
+                call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
+                     ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
+                comm.all_reduce_sum(self.dW_in)
+                all_ids = comm.all_gather_cat(w.ids.view(-1))
+                call("seqrec_mark_rows", ptr(all_ids), None, ptr(self.touched), ptr(self.rows), ptr(self.n_rows),
+                     all_ids.numel(), self.F, st)
+            else:
+                all_ids = comm.all_gather_cat(w.ids.view(-1))
+                all_mask = comm.all_gather_cat(w.mask.view(-1))
+                all_dxp = comm.all_gather_cat(w.xg.view(w.N, self.GH))
+                all_scale = comm.all_gather_cat(w.in_scale) if w.in_scale is not None else None
+                call("seqrec_scatter_add_rows", ptr(all_dxp), ptr(all_ids), ptr(all_mask), ptr(all_scale),
+                     ptr(self.dW_in), ptr(self.touched), ptr(self.rows), ptr(self.n_rows), all_ids.numel(), self.F,
+                     self.GH, st)
+        else:
+            self.dW_in.zero_()
+            call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
+            comm.all_reduce_sum(self.dW_in)
+
+        # ---- global-norm clip + Adagrad
+        self._mark("optim")
+        self._apply_update(w)
+        self._mark("end")
+        return loss
+
+    def _segments(self):
+        names = ["U", "b", "W_out", "b_out"]
+        return [(n, o, s) for n, (o, s) in zip(names, self._seg) if s > 0]
+
+    def _apply_update(self, w):
+        st = self.stream
+        o = self.opt
+        self.sumsq.zero_()
+        segs = self._segments()
+        all_dense = all(self.trainable[n] for n, _, _ in segs)
+        max_rows = min(self.F, w.N * self.comm.world)
+        if o["clipnorm"] > 0:
+            if all_dense:
+                call("seqrec_sumsq", ptr(self.flat_g), self.flat_g.numel(), ptr(self.sumsq), st)
+            else:
+                for n, off, sz in segs:
+                    if self.trainable[n]:
+                        call("seqrec_sumsq", ptr(self.flat_g[off:off + sz]), sz, ptr(self.sumsq), st)
+            if self.trainable["W_in"]:
+                if w.x_dense is None:
+                    call("seqrec_sumsq_rows", ptr(self.dW_in), ptr(self.rows), ptr(self.n_rows), self.GH, max_rows,
+                         ptr(self.sumsq), st)
+                else:
+                    call("seqrec_sumsq", ptr(self.dW_in), self.dW_in.numel(), ptr(self.sumsq), st)
+        if all_dense:
+            call("seqrec_adagrad", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_a), self.flat_p.numel(), o["lr"],
+                 o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+        else:
+            for n, off, sz in segs:
+                if self.trainable[n]:
+                    call("seqrec_adagrad", ptr(self.flat_p[off:off + sz]), ptr(self.flat_g[off:off + sz]),
+                         ptr(self.flat_a[off:off + sz]), sz, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+        if w.x_dense is None:
+            if self.trainable["W_in"]:
+                # also re-zeroes the touched rows of dW_in and their flags (zero invariant of the dense buffer)
+                call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows),
+                     ptr(self.n_rows), ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"],
+                     ptr(self.sumsq), st)
+            else:
+                self.dW_in.zero_()
+                self.touched.zero_()
+        else:
+            if self.trainable["W_in"]:
+                call("seqrec_adagrad", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), self.W_in.numel(), o["lr"],
+                     o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+            self.dW_in.zero_()
+
+    # ------------------------------------------------------------------------------------------------ gradients only
+    def grad_batch(self, ids, tgt, x_dense=None):
+        """fwd + bwd WITHOUT the update (parity tests): returns loss and the raw (unclipped) gradients as numpy arrays
+        in weight-list order.  Leaves the dW_in zero-invariant intact."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        st = self.stream
+        saved_opt = self.opt
+        self._stage(w, ids, tgt, x_dense)
+        n_valid = w.n_valid_i.to(torch.float32)
+        self.comm.all_reduce_sum(n_valid)
+        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        self._forward_hidden(w, training=True)
+        self._forward_ce(w)
+        loss = (w.loss_sum * self.inv_nvalid).clone()
+        self.flat_g.zero_()
+        call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt), ptr(w.m),
+             ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out), w.N, self.H,
+             self.V, 0, self.V, self.V, 0, 0, st)
+        dh = w.dh.clone()
+        call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),
+             ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
+             w.T, w.B, self.H, st)
+        self.n_rows.zero_()
+        if w.x_dense is None:
+            call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
+                 ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
+        else:
+            self.dW_in.zero_()
+            call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
+        grads = [self.dW_in, self.dU, self.db, self.dW_out] + ([self.db_out] if self.out_bias else [])
+        out = [g.detach().cpu().numpy().copy() for g in grads]
+        rows = self.rows[: int(self.n_rows.item())].cpu().numpy().copy() if w.x_dense is None else None
+        self.dW_in.zero_()
+        self.touched.zero_()
+        self.opt = saved_opt
+        return float(loss.item()), out, dict(dh=dh.cpu().numpy(), rows=rows,
+                                             dxp=w.xg.detach().cpu().numpy().copy())
+
+    # ------------------------------------------------------------------------------------------------ scoring
+    def hidden_batch(self, ids, x_dense=None):
+        """(B,T,H) hidden outputs (z_to_z_output activations), inference phase."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        self._stage(w, ids, None, x_dense)
+        self._forward_hidden(w, training=False)
+        return w.hout.permute(1, 0, 2).contiguous()
+
+    def predict_batch(self, ids, x_dense=None):
+        """model.predict: (B,T,V) float32 softmax probabilities on the device."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        self._stage(w, ids, None, x_dense)
+        self._forward_hidden(w, training=False)
+        self._forward_ce(w, with_targets=False)
+        probs = torch.empty((w.B, w.T, self.V), dtype=torch.float32, device=self.device)
+        call("seqrec_predict_probs", ptr(w.hout), ptr(self.W_out), ptr(self.b_out), ptr(w.m), ptr(w.s), ptr(probs),
+             w.T, w.B, self.H, self.V, self.stream)
+        return probs
+
+    def target_prob_batch(self, ids, tgt, x_dense=None):
+        """p(true next item) per step, clipped to [1e-7, 1-1e-7] like model.py:108-110; (B,T) device tensor."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        self._stage(w, ids, tgt, x_dense)
+        self._forward_hidden(w, training=False)
+        self._forward_ce(w)
+        return w.py.view(w.T, w.B).t().contiguous()
+
+    def topk_batch(self, ids, k, last_step_only=True, x_dense=None):
+        """Top-k next items: (B,k) ids and probabilities for the last step, or (B,T,k) for every step."""
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        self._stage(w, ids, None, x_dense)
+        self._forward_hidden(w, training=False)
+        self._forward_ce(w, with_targets=False)
+        if last_step_only:
+            off = (w.T - 1) * w.B
+            hrows, m, s, n = w.hout[w.T - 1], w.m[off:off + w.B], w.s[off:off + w.B], w.B
+        else:
+            hrows, m, s, n = w.hout, w.m, w.s, w.N
+        out_i = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        out_p = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        call("seqrec_topk", ptr(hrows), ptr(self.W_out), ptr(self.b_out), ptr(m), ptr(s), ptr(out_i), ptr(out_p), n,
+             self.H, self.V, int(k), self.stream)
+        if last_step_only:
+            return out_i, out_p
+        return (out_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),
+                out_p.view(w.T, w.B, k).permute(1, 0, 2).contiguous())

@@ -1,0 +1,551 @@
+"""Drop-in mirror of the reference's model.py surface for the recurrent next-item models, backed by the B200 kernels.
+
+Same class names, constructor kwargs, method signatures and return conventions as /root/reference/model.py:170-403
+(`BaseRNNModel`, `RNNBaseline`, `RNNFullModel`, `ModelResults`, `ValLossHistoryCut`), so the reference's drivers
+(experiments_methods.py:19-50, :188-249) run against this module unchanged.  `self.model` plays the role of the Keras
+`Model` the reference reaches into (`fit`, `evaluate`, `predict`, `get_weights`, `get_layer`, `load_weights`, ...).
+
+Scope: the `y_to_z`-only RNNFullModel ("ytoz", experiments_server.py:106-114) and RNNBaseline, cells
+simpleRNN / LSTM (the reference's) and GRU (north-star).  The x_to_z / x_to_y / y_to_y branches of RNNFullModel and
+NoRecurrenceModel are §8(f) "next" rows and raise NotImplementedError.
+
+Additive (not in the reference): id-format batches ((N,T) / (N,T,1) integer arrays, pad < 0), `predict_target_prob`,
+`predict_topk`.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import callbacks as cb
+from . import optimizers
+from .engine import GATES, HotPath
+from .preprocessor import is_one_hot, to_id_batch
+
+_EPSILON = 1e-7
+
+
+class ModelResults():
+    def __init__(self, train_loss=None, val_loss=None, epoch=None):
+        self.val_loss = val_loss
+        self.train_loss = train_loss
+        self.epoch = epoch
+
+
+def compute_likelihood_cut(predictions, train_percent, orig_lengths=None, count_first_prob=False):
+    """utils.py:145-163 (per-sequence mean NLL with a within-sequence 70/30 cut)."""
+    assert train_percent <= 1.0, "ERROR: train_percent should be <= 1.0"
+    train_lls, val_lls = [], []
+    for i, pred in enumerate(predictions):
+        sort_pred = pred[:]
+        if not count_first_prob:
+            sort_pred = sort_pred[1:]
+        if orig_lengths is not None:
+            sort_pred = pred[-int(orig_lengths[i]):]
+        seq_length = len(sort_pred)
+        train_elems = int(np.ceil(train_percent * seq_length))
+        val_elems = int(np.floor((1.0 - train_percent) * seq_length))
+        if train_elems > 0:
+            train_lls.append(-np.sum(np.log(sort_pred[0:train_elems])) / train_elems)
+        if val_elems > 0:
+            val_lls.append(-np.sum(np.log(sort_pred[-val_elems:])) / val_elems)
+    return np.sum(train_lls) / len(train_lls), np.sum(val_lls) / len(val_lls)
+
+
+def compute_likelihood(predictions, count_first_prob=False):
+    """utils.py:166-178."""
+    lls = []
+    for pred in predictions:
+        sort_pred = pred[:]
+        if not count_first_prob:
+            sort_pred = sort_pred[1:]
+        sort_pred = np.clip(sort_pred, _EPSILON, 1.0 - _EPSILON)
+        if len(sort_pred) > 0:
+            lls.append(-np.sum(np.log(sort_pred)) / len(sort_pred))
+    return np.mean(lls)
+
+
+class ValLossHistoryCut(cb.Callback):
+    """model.py:94-117: per-epoch p(true next item) on the validation set and its within-sequence cut NLL.  Uses the
+    fused on-device target-probability scoring instead of materialising predict()'s (N,T,V) output."""
+
+    def __init__(self, val_data, orig_seqs_lengths):
+        cb.Callback.__init__(self)
+        self.val_data = val_data
+        self.orig_seqs_lengths = orig_seqs_lengths
+
+    def on_train_begin(self, logs=None):
+        self.val_lossses = []
+        if logs is not None and "my_loss" not in logs:
+            logs["my_loss"] = 0.0
+
+    def on_epoch_end(self, epoch, logs=None):
+        p = self.model.predict_target_prob(self.val_data[0], self.val_data[1])
+        _, val_neg_ll = compute_likelihood_cut(p, 0.7, orig_lengths=self.orig_seqs_lengths)
+        self.val_lossses.append(val_neg_ll)
+        if logs is not None:
+            logs["my_loss"] = val_neg_ll
+
+
+class BaseModel():
+    def __init__(self, n_classes, model_name="test_model"):
+        self.n_classes = n_classes
+        self.model_name = model_name
+        self.model = None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class _Layer(object):
+    """What `model.get_layer(name)` hands back: get_weights / set_weights / trainable."""
+
+    def __init__(self, net, name, weight_names):
+        self._net = net
+        self.name = name
+        self._weight_names = weight_names
+
+    def get_weights(self):
+        return [self._net._get(n) for n in self._weight_names]
+
+    def set_weights(self, weights):
+        if len(weights) != len(self._weight_names):
+            raise ValueError("layer %s expects %d weight arrays" % (self.name, len(self._weight_names)))
+        for n, w in zip(self._weight_names, weights):
+            self._net._set(n, w)
+
+    @property
+    def trainable(self):
+        return all(self._net.hot.trainable[n] for n in self._weight_names) if self._weight_names else True
+
+    @trainable.setter
+    def trainable(self, value):
+        for n in self._weight_names:
+            self._net.hot.trainable[n] = bool(value)
+
+
+class _Net(object):
+    """The object behind `BaseRNNModel.model`: the Keras-`Model` methods the reference calls, on top of HotPath."""
+
+    def __init__(self, hot, layers, rnn_bias=True, seed=None):
+        self.hot = hot
+        self.layers = layers
+        self.rnn_bias = rnn_bias
+        self.stop_training = False
+        self.metrics_names = ["loss"]
+        self.optimizer = None
+        self.loss = None
+        if not rnn_bias:
+            hot.trainable["b"] = False
+        for l in layers:
+            l._net = self
+
+    # ---- weights -------------------------------------------------------------------------------------------------
+    def _names(self):
+        names = ["W_in", "U"] + (["b"] if self.rnn_bias else []) + ["W_out"] + (["b_out"] if self.hot.out_bias else [])
+        return names
+
+    def _tensor(self, name):
+        return getattr(self.hot, name)
+
+    def _get(self, name):
+        return self._tensor(name).detach().cpu().numpy().copy()
+
+    def _set(self, name, value):
+        t = self._tensor(name)
+        v = np.asarray(value, dtype=np.float32)
+        if tuple(v.shape) != tuple(t.shape):
+            raise ValueError("weight %s: shape %s does not match %s" % (name, v.shape, tuple(t.shape)))
+        t.copy_(torch.from_numpy(np.ascontiguousarray(v)))
+
+    def get_weights(self):
+        return [self._get(n) for n in self._names()]
+
+    def set_weights(self, weights):
+        names = self._names()
+        if len(weights) != len(names):
+            raise ValueError("expected %d weight arrays, got %d" % (len(names), len(weights)))
+        for n, w in zip(names, weights):
+            self._set(n, w)
+
+    @property
+    def trainable_weights(self):
+        return [n for n in self._names() if self.hot.trainable[n]]
+
+    @property
+    def non_trainable_weights(self):
+        return [n for n in self._names() if not self.hot.trainable[n]]
+
+    def get_layer(self, name=None, index=None):
+        if index is not None:
+            return self.layers[index]
+        for l in self.layers:
+            if l.name == name:
+                return l
+        raise ValueError("No such layer: " + str(name))
+
+    def save_weights(self, filepath, overwrite=True):
+        """Weights-only checkpoint in `get_weights()` order.  h5 needs h5py (absent in this image) -- the flat
+        `weight{i}` layout of model.py:201-208 is written as .npz instead."""
+        ws = self.get_weights()
+        d = os.path.dirname(filepath)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        with open(filepath, "wb") as f:
+            np.savez(f, **{"weight%d" % i: w for i, w in enumerate(ws)})
+
+    def load_weights(self, filepath, by_name=False):
+        with np.load(filepath) as z:
+            self.set_weights([z["weight%d" % i] for i in range(len(z.files))])
+
+    # ---- compile -------------------------------------------------------------------------------------------------
+    def compile(self, loss="categorical_crossentropy", optimizer="adam", metrics=None):
+        if loss != "categorical_crossentropy":
+            raise NotImplementedError("only categorical_crossentropy (experiments_methods.py:42) is built")
+        self.loss = loss
+        self.optimizer = optimizers.resolve(optimizer)
+        self.metrics_names = ["loss"] + [m for m in (metrics or []) if isinstance(m, str)]
+        if not isinstance(self.optimizer, str):
+            o = self.optimizer
+            self.hot.set_optimizer("adagrad", lr=o.lr, epsilon=o.epsilon, clipnorm=getattr(o, "clipnorm", None) or 0.0,
+                                   decay=getattr(o, "decay", 0.0))
+
+    # ---- batches -------------------------------------------------------------------------------------------------
+    def _inputs(self, x):
+        """Reference inputs are an ndarray or a one-element list (experiments_methods.py:209-216: `[x]` for ytoz)."""
+        if isinstance(x, (list, tuple)):
+            if len(x) != 1:
+                raise NotImplementedError("history-feature inputs (x_to_z / x_to_y) are not built yet (SURVEY §8(f))")
+            x = x[0]
+        x = np.asarray(x)
+        if x.ndim == 3 and x.shape[2] > 1 and not (x.shape[2] == self.hot.F and is_one_hot(x)):
+            if x.shape[2] != self.hot.F:
+                raise ValueError("input feature width %d does not match the model's %d" % (x.shape[2], self.hot.F))
+            return None, np.ascontiguousarray(x, dtype=np.float32)      # dense-feature path (K2)
+        return to_id_batch(x), None                                       # gather path (K1)
+
+    def _slice(self, ids, xd, idx):
+        return (ids[idx] if ids is not None else None), (xd[idx] if xd is not None else None)
+
+    def _epoch_eval(self, ids, xd, tgt, batch_size):
+        """Keras test_loop: batch-size-weighted mean of per-batch masked-mean losses."""
+        n = len(tgt)
+        total = torch.zeros(1, dtype=torch.float64, device=self.hot.device)
+        for lo in range(0, n, batch_size):
+            hi = min(n, lo + batch_size)
+            i, d = self._slice(ids, xd, slice(lo, hi))
+            ls, nv = self.hot.loss_batch(i, tgt[lo:hi], d)
+            if self.hot.comm.enabled:
+                self.hot.comm.all_reduce_sum(ls)
+                self.hot.comm.all_reduce_sum(nv)
+            total += (ls / nv).double() * (hi - lo)
+        return float(total.item()) / n
+
+    # ---- Keras Model methods ------------------------------------------------------------------------------------
+    def fit(self, x, y, validation_data=None, epochs=10, batch_size=100, verbose=1, callbacks=None, shuffle=True):
+        if isinstance(self.optimizer, str) or self.optimizer is None:
+            raise NotImplementedError("training needs an Adagrad optimizer object (experiments_methods.py:41); got %r"
+                                      % (self.optimizer,))
+        ids, xd = self._inputs(x)
+        tgt = to_id_batch(y)
+        n = len(tgt)
+        val = None
+        if validation_data is not None:
+            vi, vd = self._inputs(validation_data[0])
+            val = (vi, vd, to_id_batch(validation_data[1]))
+        history = cb.History()
+        cbs = [history] + list(callbacks or [])
+        for c in cbs:
+            c.set_model(self)
+            c.set_params({"epochs": epochs, "batch_size": batch_size, "samples": n, "verbose": verbose})
+        self.stop_training = False
+        logs0 = {}
+        for c in cbs:
+            c.on_train_begin(logs0)
+        index = np.arange(n)
+        for epoch in range(epochs):
+            for c in cbs:
+                c.on_epoch_begin(epoch)
+            if shuffle:
+                np.random.shuffle(index)
+            acc = torch.zeros(1, dtype=torch.float64, device=self.hot.device)
+            for lo in range(0, n, batch_size):
+                sel = index[lo:lo + batch_size]
+                i, d = self._slice(ids, xd, sel)
+                loss = self.hot.train_batch(i, tgt[sel], d)
+                acc += loss.double() * len(sel)
+            logs = {"loss": float(acc.item()) / n}
+            for m in self.metrics_names[1:]:
+                logs[m] = logs["loss"]
+            if val is not None:
+                logs["val_loss"] = self._epoch_eval(val[0], val[1], val[2], batch_size)
+                for m in self.metrics_names[1:]:
+                    logs["val_" + m] = logs["val_loss"]
+            for c in cbs:
+                c.on_epoch_end(epoch, logs)
+            if verbose:
+                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in sorted(logs.items())))
+            if self.stop_training:
+                break
+        for c in cbs:
+            c.on_train_end()
+        return history
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None, validation_data=None,
+                      validation_steps=None):
+        history = cb.History()
+        cbs = [history] + list(callbacks or [])
+        for c in cbs:
+            c.set_model(self)
+        self.stop_training = False
+        for c in cbs:
+            c.on_train_begin({})
+        for epoch in range(epochs):
+            acc, cnt = 0.0, 0
+            for _ in range(steps_per_epoch):
+                x, y = next(generator)
+                ids, xd = self._inputs(x)
+                tgt = to_id_batch(y)
+                loss = self.hot.train_batch(ids, tgt, xd)
+                acc += float(loss.item()) * len(tgt)
+                cnt += len(tgt)
+            logs = {"loss": acc / max(cnt, 1)}
+            if validation_data is not None:
+                vacc, vcnt = 0.0, 0
+                for _ in range(validation_steps or 1):
+                    vx, vy = next(validation_data) if hasattr(validation_data, "__next__") else validation_data
+                    vi, vd = self._inputs(vx)
+                    vt = to_id_batch(vy)
+                    vacc += self._epoch_eval(vi, vd, vt, len(vt)) * len(vt)
+                    vcnt += len(vt)
+                logs["val_loss"] = vacc / max(vcnt, 1)
+            for c in cbs:
+                c.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for c in cbs:
+            c.on_train_end()
+        return history
+
+    def train_on_batch(self, x, y):
+        """Keras `Model.train_on_batch`: one optimisation step on one host batch; returns the scalar loss (host)."""
+        ids, xd = self._inputs(x)
+        return float(self.hot.train_batch(ids, to_id_batch(y), xd).item())
+
+    def evaluate(self, x, y, batch_size=32, verbose=0):
+        ids, xd = self._inputs(x)
+        tgt = to_id_batch(y)
+        loss = self._epoch_eval(ids, xd, tgt, batch_size)
+        # the loss is registered again as a metric (model.py:177), so it comes back once per metrics_names entry
+        return [loss] * len(self.metrics_names) if len(self.metrics_names) > 1 else loss
+
+    def predict(self, x, batch_size=32, verbose=0):
+        ids, xd = self._inputs(x)
+        n = len(ids) if ids is not None else len(xd)
+        out = []
+        for lo in range(0, n, batch_size):
+            i, d = self._slice(ids, xd, slice(lo, min(n, lo + batch_size)))
+            out.append(self.hot.predict_batch(i, d).cpu().numpy())
+        return np.concatenate(out, axis=0)
+
+    # ---- additive scoring API --------------------------------------------------------------------------------------
+    def predict_target_prob(self, x, y, batch_size=1024):
+        """(N,T) p(true next item), clipped to [1e-7, 1-1e-7]; pads give 1e-7 (model.py:108-110 semantics)."""
+        ids, xd = self._inputs(x)
+        tgt = to_id_batch(y)
+        out = []
+        for lo in range(0, len(tgt), batch_size):
+            hi = min(len(tgt), lo + batch_size)
+            i, d = self._slice(ids, xd, slice(lo, hi))
+            out.append(self.hot.target_prob_batch(i, tgt[lo:hi], d).cpu().numpy())
+        return np.concatenate(out, axis=0)
+
+    def predict_topk(self, x, k=20, last_step_only=True, batch_size=1024):
+        """Top-k next-item ids (int32) and probabilities; ties broken by the lower item id."""
+        ids, xd = self._inputs(x)
+        n = len(ids) if ids is not None else len(xd)
+        oi, op = [], []
+        for lo in range(0, n, batch_size):
+            i, d = self._slice(ids, xd, slice(lo, min(n, lo + batch_size)))
+            a, b = self.hot.topk_batch(i, k, last_step_only=last_step_only, x_dense=d)
+            oi.append(a.cpu().numpy())
+            op.append(b.cpu().numpy())
+        return np.concatenate(oi, axis=0), np.concatenate(op, axis=0)
+
+    def hidden_states(self, x, batch_size=1024):
+        ids, xd = self._inputs(x)
+        n = len(ids) if ids is not None else len(xd)
+        out = []
+        for lo in range(0, n, batch_size):
+            i, d = self._slice(ids, xd, slice(lo, min(n, lo + batch_size)))
+            out.append(self.hot.hidden_batch(i, d).cpu().numpy())
+        return np.concatenate(out, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class BaseRNNModel(BaseModel):
+    """model.py:170-238."""
+
+    def __init__(self, n_classes, model_name="test_model", rnn_type='simpleRNN'):
+        BaseModel.__init__(self, n_classes, model_name)
+        self.rnn_type = rnn_type
+
+    def compile_model(self, loss='categorical_crossentropy', metrics=[], optimizer='adam'):
+        self.model.compile(loss=loss, optimizer=optimizer, metrics=[loss] + metrics)
+
+    def fit_model(self, x_train, y_train, validation_data=None, n_epochs=10, batch_size=100, verbose=1,
+                  callbacks=None):
+        return self.model.fit(x_train, y_train, validation_data=validation_data, epochs=n_epochs,
+                              batch_size=batch_size, verbose=verbose, callbacks=callbacks)
+
+    def fit_generator(self, train_gen, steps_per_epoch, validation_steps, epochs, verbose, callbacks,
+                      validation_data):
+        return self.model.fit_generator(train_gen, validation_data=validation_data, callbacks=callbacks,
+                                        steps_per_epoch=steps_per_epoch, validation_steps=validation_steps,
+                                        epochs=epochs, verbose=verbose)
+
+    def predict(self, x_test, batch_size=10, verbose=1):
+        return self.model.predict(x_test, batch_size=batch_size, verbose=verbose)
+
+    def evaluate(self, x_test, y_test, batch_size=10, verbose=0):
+        scores = self.model.evaluate(x_test, y_test, verbose=verbose, batch_size=batch_size)
+        return self.model.metrics_names, scores
+
+    def save_model_weights(self, directory):
+        if not os.path.exists(directory):
+            os.makedirs(directory)
+        self.model.save_weights(directory + self.model_name + ".npz")
+
+    def load_model_weights(self, filepath):
+        self.model.load_weights(filepath, by_name=False)
+
+    def get_layer_weights(self, layer):
+        if isinstance(layer, str):
+            return self.model.get_layer(layer).get_weights()
+        else:
+            return self.model.layers[layer].get_weights()
+
+    def set_layer_weights_trainable(self, name, trainable=True):
+        self.model.get_layer(name).trainable = trainable
+
+    def set_layer_weights(self, name, weights):
+        self.model.get_layer(name).set_weights(weights)
+
+    def get_model_weights(self):
+        return self.model.trainable_weights, self.model.non_trainable_weights
+
+    def get_activations(self, layer, inputs, input_layers):
+        """Inference-phase output of a named layer (model.py:235-238).  Built for the recurrent layer (hidden states)
+        and the final softmax; `inputs` is the list the reference passes (one array per input layer)."""
+        rnn_names = [l.name for l in self.model.layers if l._weight_names[:1] == ["W_in"]]
+        if layer in rnn_names:
+            return self.model.hidden_states(inputs)
+        if layer == self.model.layers[-1].name:
+            return self.model.predict(inputs)
+        raise NotImplementedError("get_activations is built for the recurrent layer and the output layer only")
+
+    # additive
+    def predict_target_prob(self, x_test, y_test, batch_size=1024):
+        return self.model.predict_target_prob(x_test, y_test, batch_size=batch_size)
+
+    def predict_topk(self, x_test, k=20, last_step_only=True, batch_size=1024):
+        return self.model.predict_topk(x_test, k=k, last_step_only=last_step_only, batch_size=batch_size)
+
+
+def _glorot_uniform(rng, shape):
+    limit = np.sqrt(6.0 / (shape[0] + shape[1]))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+def _glorot_normal(rng, shape):
+    return (rng.standard_normal(size=shape) * np.sqrt(2.0 / (shape[0] + shape[1]))).astype(np.float32)
+
+
+def _orthogonal(rng, n):
+    q, r = np.linalg.qr(rng.standard_normal(size=(n, n)))
+    return (q * np.sign(np.diag(r))).astype(np.float32)
+
+
+def _init_weights(cell, F, H, V, out_bias, kernel_init="glorot_uniform", seed=None):
+    """Keras-2.0.x defaults: glorot_uniform kernels (glorot_normal for the ytoz LSTM, model.py:351), orthogonal
+    recurrent kernel per gate block, zero biases with unit_forget_bias."""
+    rng = np.random.default_rng(seed)
+    G = GATES[cell]
+    kin = _glorot_normal if kernel_init == "glorot_normal" else _glorot_uniform
+    W_in = kin(rng, (F, G * H))
+    U = np.concatenate([_orthogonal(rng, H) for _ in range(G)], axis=1)
+    b = np.zeros(G * H, dtype=np.float32)
+    if cell == "LSTM":
+        b[H:2 * H] = 1.0
+    ws = [W_in, U, b, _glorot_uniform(rng, (H, V))]
+    if out_bias:
+        ws.append(np.zeros(V, dtype=np.float32))
+    return ws
+
+
+class RNNBaseline(BaseRNNModel):
+    """model.py:241-258: Input(T,F) -> Masking -> SimpleRNN/LSTM(z_dim) -> Dropout -> TimeDistributed(Dense(V, softmax,
+    WITH bias))."""
+
+    def __init__(self, timesteps, features, n_classes, model_name="baseline_model", rnn_type='simpleRNN',
+                 out_activation="softmax", z_activation="relu", z_dim=20, z_to_y_drop=0.0, seed=None, comm=None):
+        BaseRNNModel.__init__(self, n_classes, model_name=model_name, rnn_type=rnn_type)
+        if out_activation != "softmax":
+            raise NotImplementedError("only the softmax output of the reference's experiments is built")
+        self.timesteps = timesteps
+        hot = HotPath(rnn_type, z_activation, features, z_dim, n_classes, out_bias=True, comm=comm,
+                      weights=_init_weights(rnn_type, features, z_dim, n_classes, True, seed=seed),
+                      seed=0 if seed is None else seed)
+        hot.dropout_out = float(z_to_y_drop)
+        rnn_name = "rnn" if rnn_type == "simpleRNN" else ("lstm" if rnn_type == "LSTM" else "gru")
+        layers = [_Layer(None, "myinput", []), _Layer(None, "mask", []), _Layer(None, rnn_name, ["W_in", "U", "b"]),
+                  _Layer(None, "dropout_1", []), _Layer(None, "output", ["W_out", "b_out"])]
+        self.model = _Net(hot, layers)
+
+
+class NoRecurrenceModel(BaseRNNModel):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("NoRecurrenceModel (model.py:264-319) has no recurrence and is outside the hot path; "
+                                  "it is a SURVEY §8(f) 'next' row")
+
+
+class RNNFullModel(BaseRNNModel):
+    """model.py:322-403, `y_to_z`-only variant: Input(T,V) one-hot -> Masking -> Dropout(y_to_z_dropout) ->
+    SimpleRNN/LSTM/GRU(z_dim, activation=z_to_z_activation) -> Dropout(z_to_y_dropout) -> TimeDistributed(Dense(V,
+    linear, use_bias=toy_bias)) -> softmax."""
+
+    def __init__(self, timesteps, x_dim, y_dim, z_dim=20, model_name="y_to_y_model", rnn_type='simpleRNN',
+                 z_to_z_activation="relu",
+                 y_to_y_activation="linear", xz_to_y_activation="linear", y_to_y_w_initializer=None,
+                 out_activation="softmax",
+                 ytoy_bias=False, toy_bias=False, z_bias=True, y_to_y_regularizer=None, toy_regularizer=None,
+                 y_to_z=True,
+                 y_to_z_initializer="glorot_normal",
+                 y_to_y=True, x_to_y=True, x_to_z=False, z_to_y_dropout=0.0, diag_b=True, y_to_z_dropout=0.0,
+                 z_to_z_dropout=0.0, seed=None, comm=None):
+        BaseRNNModel.__init__(self, y_dim, model_name=model_name, rnn_type=rnn_type)
+        if not (x_to_z or y_to_z):
+            raise ValueError("ERROR: the model needs an input into z's! either x or y should be added.")
+        if y_to_y or x_to_y or x_to_z or not y_to_z:
+            raise NotImplementedError(
+                "only the y_to_z recurrent path (y_to_z=True, y_to_y=False, x_to_y=False, x_to_z=False; "
+                "experiments_server.py:106-114) is built; the history-feature / skip branches are SURVEY §8(f) rows")
+        if out_activation != "softmax" or xz_to_y_activation != "linear":
+            raise NotImplementedError("only linear -> softmax outputs (the reference's experiments) are built")
+        if toy_regularizer is not None:
+            raise NotImplementedError("kernel regularisers are only used by non-hot-path branches")
+        if z_to_z_dropout:
+            raise NotImplementedError("recurrent_dropout is 0 in every reference experiment (experiments_server.py)")
+        self.timesteps = timesteps
+        kinit = y_to_z_initializer if rnn_type == "LSTM" else "glorot_uniform"
+        ws = _init_weights(rnn_type, y_dim, z_dim, y_dim, bool(toy_bias), kernel_init=kinit, seed=seed)
+        hot = HotPath(rnn_type, z_to_z_activation, y_dim, z_dim, y_dim, out_bias=bool(toy_bias), weights=ws, comm=comm,
+                      seed=0 if seed is None else seed)
+        hot.dropout_in = float(y_to_z_dropout)
+        hot.dropout_out = float(z_to_y_dropout)
+        rnn_w = ["W_in", "U"] + (["b"] if z_bias else [])
+        out_w = ["W_out"] + (["b_out"] if toy_bias else [])
+        layers = [_Layer(None, "y_input", []), _Layer(None, "mask1", []), _Layer(None, "dropout_1", []),
+                  _Layer(None, "z_to_z_output", rnn_w), _Layer(None, "dropout_2", []),
+                  _Layer(None, "to_y_output", out_w), _Layer(None, "activation_1", [])]
+        self.model = _Net(hot, layers, rnn_bias=bool(z_bias))
+        if not z_bias:
+            hot.b.zero_()

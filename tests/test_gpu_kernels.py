@@ -1,0 +1,253 @@
+"""Kernel-level parity of the CUDA path (called through the C-ABI) against the CPU oracle.  Run with -m gpu on a B200.
+
+Tolerances: gathers and top-k ids bit-exact; everything floating point within 1e-4 relative (north_star) -- measured
+against the float64 oracle, so the budget covers fp32 rounding of both sides."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import keras_semantics as ks
+from seq_recommendations_b200 import synthetic
+from seq_recommendations_b200._lib import call, ptr
+
+from gpu_util import as_t, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("V,GH,N", [(17, 400, 5000), (1000, 384, 1280), (50, 7, 33), (10000, 384, 12800)])
+def test_gather_rows_bit_exact(V, GH, N):
+    rng = np.random.default_rng(0)
+    W = torch.tensor(rng.standard_normal((V, GH)).astype(np.float32))
+    b = torch.tensor(rng.standard_normal(GH).astype(np.float32))
+    ids = torch.tensor(rng.integers(0, V, size=N).astype(np.int32))
+    mask = torch.tensor((rng.random(N) > 0.2).astype(np.uint8))
+    ids = torch.where(mask.bool(), ids, torch.full_like(ids, -1))
+    out = torch.empty((N, GH), dtype=torch.float32, device="cuda")
+    call("seqrec_gather_rows", ptr(W.cuda()), ptr(b.cuda()), ptr(ids.cuda()), ptr(mask.cuda()), None, ptr(out), N, V,
+         GH, stream())
+    ref = ks.input_projection(W, b, ids=ids.long(), mask=mask.bool())
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_format_batch_transposes_and_counts():
+    ids, tgt = synthetic.make_batch(500, 37, 45, seed=5)
+    d = lambda *s, dt=torch.int32: torch.empty(s, dtype=dt, device="cuda")
+    ids_tb, tgt_tb, mask_tb, nv = d(37, 45), d(37, 45), d(37, 45, dt=torch.uint8), torch.zeros(1, dtype=torch.int32, device="cuda")
+    call("seqrec_format_batch", ptr(torch.tensor(ids).cuda()), ptr(torch.tensor(tgt).cuda()), ptr(ids_tb), ptr(tgt_tb),
+         ptr(mask_tb), ptr(nv), 45, 37, stream())
+    assert np.array_equal(ids_tb.cpu().numpy(), ids.T) and np.array_equal(tgt_tb.cpu().numpy(), tgt.T)
+    assert np.array_equal(mask_tb.cpu().numpy().astype(bool), (ids >= 0).T) and int(nv.item()) == int((ids >= 0).sum())
+
+
+@pytest.mark.parametrize("V,GH,N", [(40, 384, 4000), (7, 13, 999), (100000, 64, 2048)])
+def test_scatter_add_rows_with_heavy_duplicates(V, GH, N):
+    rng = np.random.default_rng(1)
+    ids_np = synthetic.zipf_items(rng, V, N)
+    mask_np = rng.random(N) > 0.1
+    dxp = rng.standard_normal((N, GH)).astype(np.float32)
+    dW = torch.zeros((V, GH), dtype=torch.float32, device="cuda")
+    touched = torch.zeros(V, dtype=torch.int32, device="cuda")
+    rows = torch.empty(V, dtype=torch.int32, device="cuda")
+    n_rows = torch.zeros(1, dtype=torch.int32, device="cuda")
+    call("seqrec_scatter_add_rows", ptr(torch.tensor(dxp).cuda()), ptr(torch.tensor(ids_np).cuda()),
+         ptr(torch.tensor(mask_np.astype(np.uint8)).cuda()), None, ptr(dW), ptr(touched), ptr(rows), ptr(n_rows), N, V,
+         GH, stream())
+    ref = np.zeros((V, GH), dtype=np.float64)
+    np.add.at(ref, ids_np[mask_np], dxp[mask_np].astype(np.float64))
+    assert rel_err(dW.cpu().numpy(), ref) < 1e-6
+    got_rows = np.sort(rows[: int(n_rows.item())].cpu().numpy())
+    assert np.array_equal(got_rows, np.unique(ids_np[mask_np]))          # each touched row listed exactly once
+    assert np.array_equal(np.nonzero(touched.cpu().numpy())[0], got_rows)
+
+
+SHAPES = [  # (V, H, T, B)
+    (17, 100, 9, 5), (60, 6, 7, 3), (45, 5, 6, 2), (300, 32, 12, 150), (128, 128, 5, 300), (90, 64, 4, 700),
+    (64, 256, 3, 9),
+]
+
+
+@pytest.mark.parametrize("cell,act", [("simpleRNN", "relu"), ("LSTM", "relu"), ("LSTM", "tanh"), ("GRU", "tanh"),
+                                      ("GRU", "relu")])
+@pytest.mark.parametrize("V,H,T,B", SHAPES)
+def test_hidden_states_match_oracle(cell, act, V, H, T, B):
+    hot, ora, _ = make_pair(cell, act, V, H, seed=3, bias_scale=0.1)
+    ids, _ = synthetic.make_batch(V, T, B, seed=4, min_len=1)
+    ids[0, T // 2] = -1                                   # a masked step in the middle of a row
+    got = hot.hidden_batch(ids).cpu().numpy()
+    ref = ora.hidden_states(ids=as_t(ids), mask=as_t(ids) >= 0).numpy()
+    assert np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+    assert np.all(got[ids < 0][..., :] == got[ids < 0][..., :])      # finite
+    first_pad = ids[:, 0] < 0
+    assert np.all(got[first_pad, 0] == 0)                  # pre-pad outputs are exactly zero
+
+
+@pytest.mark.parametrize("cell,act", [("simpleRNN", "relu"), ("LSTM", "relu"), ("LSTM", "tanh"), ("GRU", "tanh")])
+@pytest.mark.parametrize("V,H,T,B", SHAPES)
+@pytest.mark.parametrize("out_bias", [False, True])
+def test_loss_and_gradients_match_oracle(cell, act, V, H, T, B, out_bias):
+    hot, ora, _ = make_pair(cell, act, V, H, seed=5, out_bias=out_bias, bias_scale=0.1)
+    ids, tgt = synthetic.make_batch(V, T, B, seed=6, min_len=1)
+    ids[0, T // 2] = -1
+    tgt[0, T // 2] = -1
+    loss, grads, extra = hot.grad_batch(ids, tgt)
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+    assert abs(loss - float(rl)) <= TOL * abs(float(rl))
+    for name, g, r in zip(["W_in", "U", "b", "W_out", "b_out"], grads, rg):
+        assert rel_err(g, r.numpy()) <= TOL, (name, rel_err(g, r.numpy()))
+    used = np.unique(ids[ids >= 0])
+    assert np.array_equal(np.sort(extra["rows"]), used)
+    assert float(hot.dW_in.abs().max().item()) == 0.0 and int(hot.touched.sum().item()) == 0   # zero invariant restored
+
+
+def test_clip_saturated_tokens_give_loss_but_no_gradient():
+    V, H, T, B = 50, 8, 4, 3
+    hot, ora, ws = make_pair("GRU", "tanh", V, H, seed=8)
+    ws[3] = ws[3] * 400.0                                   # huge logits: some targets fall below p = 1e-7
+    hot.set_weights(ws)
+    ora = ks.Model("GRU", "tanh", ws, dtype=torch.float64)
+    ids, tgt = synthetic.make_batch(V, T, B, seed=9, all_valid=True)
+    loss, grads, _ = hot.grad_batch(ids, tgt)
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+    _, _, py = ora.loss(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+    assert int((py <= ks.EPS32).sum()) > 0
+    assert abs(loss - float(rl)) <= 1e-3 * abs(float(rl))
+    for g, r in zip(grads, rg):
+        assert rel_err(g, r.numpy()) <= 2e-3 or np.linalg.norm(r.numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("cell,act,V,H,T,B,bias", [("GRU", "tanh", 300, 32, 12, 40, False),
+                                                   ("LSTM", "relu", 17, 100, 20, 100, False),
+                                                   ("simpleRNN", "relu", 80, 16, 6, 10, True),
+                                                   ("LSTM", "tanh", 1000, 64, 10, 160, True)])
+def test_training_steps_match_oracle(cell, act, V, H, T, B, bias):
+    """fwd + bwd + global-norm clip + Adagrad, three consecutive steps (accumulators carry over)."""
+    hot, ora, _ = make_pair(cell, act, V, H, seed=10, out_bias=bias)
+    hot.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
+    for step in range(3):
+        ids, tgt = synthetic.make_batch(V, T, B, seed=20 + step, min_len=1)
+        loss = float(hot.train_batch(ids, tgt).item())
+        rl, _, norm = ora.train_step(as_t(ids), as_t(tgt), as_t(ids) >= 0, lr=0.05, epsilon=1e-8, clipnorm=1.0)
+        assert abs(loss - float(rl)) <= TOL * abs(float(rl)), (step, loss, float(rl))
+    for name, w, r in zip(["W_in", "U", "b", "W_out", "b_out"], hot.get_weights(), ora.numpy_weights()):
+        assert rel_err(w, r) <= TOL, (name, rel_err(w, r))
+    assert rel_err(hot.aW_in.cpu().numpy(), ora.accum[0].numpy()) <= 1e-3
+    assert float(hot.dW_in.abs().max().item()) == 0.0
+
+
+def test_clipnorm_threshold_both_sides():
+    V, H, T, B = 40, 8, 5, 6
+    for clip in (1e-3, 1e3):                                # always clipping / never clipping
+        hot, ora, _ = make_pair("GRU", "tanh", V, H, seed=12)
+        hot.set_optimizer("adagrad", lr=0.1, epsilon=1e-8, clipnorm=clip)
+        ids, tgt = synthetic.make_batch(V, T, B, seed=13)
+        hot.train_batch(ids, tgt)
+        ora.train_step(as_t(ids), as_t(tgt), as_t(ids) >= 0, lr=0.1, epsilon=1e-8, clipnorm=clip)
+        for w, r in zip(hot.get_weights(), ora.numpy_weights()):
+            assert rel_err(w, r) <= TOL
+
+
+def test_frozen_layer_is_excluded_from_norm_and_update():
+    V, H, T, B = 40, 8, 5, 6
+    hot, ora, ws = make_pair("LSTM", "relu", V, H, seed=14)
+    hot.set_optimizer("adagrad", lr=0.1, epsilon=1e-8, clipnorm=0.05)
+    hot.trainable["W_out"] = False
+    ids, tgt = synthetic.make_batch(V, T, B, seed=15)
+    hot.train_batch(ids, tgt)
+    ora.train_step(as_t(ids), as_t(tgt), as_t(ids) >= 0, lr=0.1, epsilon=1e-8, clipnorm=0.05,
+                   trainable=[True, True, True, False])
+    got = hot.get_weights()
+    assert np.array_equal(got[3], ws[3])
+    for w, r in zip(got, ora.numpy_weights()):
+        assert rel_err(w, r) <= TOL
+
+
+@pytest.mark.parametrize("V,H,T,B,bias", [(17, 100, 9, 5, False), (1000, 64, 7, 33, True), (130, 32, 4, 70, False)])
+def test_predict_probabilities_and_target_prob(V, H, T, B, bias):
+    hot, ora, _ = make_pair("LSTM", "relu", V, H, seed=16, out_bias=bias, bias_scale=0.2)
+    ids, tgt = synthetic.make_batch(V, T, B, seed=17, min_len=1)
+    probs = hot.predict_batch(ids).cpu().numpy()
+    ref = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)
+    assert probs.shape == (B, T, V) and probs.dtype == np.float32
+    assert np.abs(probs - ref.numpy()).max() <= TOL
+    assert np.abs(probs.sum(-1) - 1).max() < 1e-5
+    py = hot.target_prob_batch(ids, tgt).cpu().numpy()
+    rpy = ks.target_prob(ref, as_t(tgt), as_t(ids) >= 0).numpy()
+    assert np.abs(py - rpy).max() <= TOL
+    assert np.all(py[ids < 0] == np.float32(ks.EPS32))
+
+
+@pytest.mark.parametrize("V,H,T,B,k", [(300, 32, 12, 24, 5), (5000, 64, 6, 70, 20), (64, 16, 5, 3, 64), (17, 100, 8, 9, 3)])
+def test_topk_ids_bit_exact(V, H, T, B, k):
+    hot, ora, _ = make_pair("GRU", "tanh", V, H, seed=18)
+    ids, _ = synthetic.make_batch(V, T, B, seed=19, min_len=1)
+    ref = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)
+    ti, tp = hot.topk_batch(ids, k, last_step_only=True)
+    want = ks.topk_items(ref[:, -1], k)
+    got = ti.cpu().numpy()
+    # items whose oracle probabilities differ by less than fp32 noise may legitimately swap; everything else is exact
+    refp = np.take_along_axis(ref[:, -1].numpy(), want.astype(np.int64), axis=1)
+    gap = np.abs(np.diff(refp, axis=1)).min(initial=1.0) if k > 1 else 1.0
+    if gap > 1e-6:
+        assert np.array_equal(got, want)
+    else:
+        assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1))
+    assert np.abs(tp.cpu().numpy() - np.take_along_axis(ref[:, -1].numpy(), got.astype(np.int64), axis=1)).max() <= TOL
+    ai, ap = hot.topk_batch(ids, min(k, 8), last_step_only=False)
+    assert ai.shape == (B, T, min(k, 8))
+    # pad steps score a zero hidden state: without an output bias every logit ties and the k lowest ids win
+    pad = ids < 0
+    if pad.any():
+        assert np.array_equal(ai.cpu().numpy()[pad][0], np.arange(min(k, 8)))
+
+
+def test_dropout_factors_distribution_and_training_effect():
+    n, rate = 1 << 20, 0.3
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    call("seqrec_dropout_mask", ptr(out), n, rate, 123, 0, stream())
+    vals = torch.unique(out).cpu().numpy()
+    assert np.allclose(np.sort(vals), [0.0, 1.0 / 0.7])
+    assert abs(float((out == 0).float().mean().item()) - rate) < 5e-3
+    out2 = torch.empty(n, dtype=torch.float32, device="cuda")
+    call("seqrec_dropout_mask", ptr(out2), n, rate, 123, 0, stream())
+    assert torch.equal(out, out2)                                         # counter-based: reproducible
+    # training with z->y dropout: gradient equals the oracle's when it is given the same factors
+    V, H, T, B = 60, 16, 5, 8
+    hot, ora, _ = make_pair("GRU", "tanh", V, H, seed=21)
+    hot.dropout_out = 0.3
+    ids, tgt = synthetic.make_batch(V, T, B, seed=22)
+    loss, grads, _ = hot.grad_batch(ids, tgt)
+    w = hot.work(B, T)
+    scale = w.hscale.view(T, B, H).permute(1, 0, 2).cpu().double()
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0, out_scale=scale)
+    assert abs(loss - float(rl)) <= TOL * abs(float(rl))
+    for g, r in zip(grads, rg):
+        assert rel_err(g, r.numpy()) <= TOL
+
+
+def test_dense_feature_inputs_match_oracle():
+    """RNNBaseline with [onehot || xs] features: K2 GEMM input projection instead of the gather."""
+    from seq_recommendations_b200.engine import HotPath
+    rng = np.random.default_rng(23)
+    V, F, H, T, B = 12, 24, 16, 6, 10
+    ws = synthetic.make_weights("LSTM", V, H, seed=24, out_bias=True, F=F)
+    x = (rng.random((B, T, F)) < 0.3).astype(np.float32) * rng.random((B, T, F)).astype(np.float32)
+    x[:, :2] = 0.0
+    x[0, 4] = 0.0
+    tgt = rng.integers(0, V, size=(B, T)).astype(np.int32)
+    mask = (x != 0).any(-1)
+    tgt[~mask] = -1
+    hot = HotPath("LSTM", "relu", F, H, V, out_bias=True, weights=ws)
+    ora = ks.Model("LSTM", "relu", ws, dtype=torch.float64)
+    loss, grads, _ = hot.grad_batch(None, tgt, x_dense=x)
+    rl, rg = ora.grads(None, as_t(tgt), torch.tensor(mask), x_dense=torch.tensor(x, dtype=torch.float64))
+    assert abs(loss - float(rl)) <= TOL * abs(float(rl))
+    for g, r in zip(grads, rg):
+        assert rel_err(g, r.numpy()) <= TOL

@@ -1,0 +1,185 @@
+"""End-to-end parity through the reference-facing surface (model.py mirror): fit_model / evaluate / predict / weights,
+driven exactly the way experiments_methods.py:19-50 drives the reference.  Run with -m gpu on a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import keras_semantics as ks
+from seq_recommendations_b200 import callbacks as cb
+from seq_recommendations_b200 import model as M
+from seq_recommendations_b200 import preprocessor as pp
+from seq_recommendations_b200.optimizers import Adagrad
+
+from gpu_util import as_t, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def mc_data(n=120, T=20):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mc_sequences.npz"))
+    seqs = [g["flat"][g["offs"][i]:g["offs"][i + 1]].tolist() for i in range(n)]
+    V = 17
+    vocab = dict(zip(range(V), range(V)))
+    xs = [[[0] * V for _ in s] for s in seqs]
+    p = pp.FullModelPreprocessor(vocab=vocab, pad_value=0., seq_length=T)
+    x, y, _ = p.transform_data(seqs, xs=xs)
+    return x, y, V, seqs
+
+
+def oracle_fit(ora, x_ids, y_ids, epochs, batch_size, lr, seed, val=None):
+    """Keras fit loop restated on the oracle."""
+    np.random.seed(seed)
+    n = len(x_ids)
+    index = np.arange(n)
+    hist = {"loss": [], "val_loss": []}
+    for _ in range(epochs):
+        np.random.shuffle(index)
+        tot = 0.0
+        for lo in range(0, n, batch_size):
+            sel = index[lo:lo + batch_size]
+            i, t = as_t(x_ids[sel]), as_t(y_ids[sel])
+            l, _, _ = ora.train_step(i, t, i >= 0, lr=lr, epsilon=1e-8, clipnorm=1.0)
+            tot += float(l) * len(sel)
+        hist["loss"].append(tot / n)
+        if val is not None:
+            hist["val_loss"].append(oracle_eval(ora, val[0], val[1], batch_size))
+    return hist
+
+
+def oracle_eval(ora, x_ids, y_ids, batch_size):
+    tot = 0.0
+    for lo in range(0, len(x_ids), batch_size):
+        i, t = as_t(x_ids[lo:lo + batch_size]), as_t(y_ids[lo:lo + batch_size])
+        with torch.no_grad():
+            l, _, _ = ora.loss(i, t, i >= 0)
+        tot += float(l) * len(i)
+    return tot / len(x_ids)
+
+
+@pytest.mark.parametrize("rnn_type,act", [("LSTM", "relu"), ("GRU", "tanh"), ("simpleRNN", "relu")])
+def test_fit_evaluate_predict_like_run_model(rnn_type, act):
+    x, y, V, _ = mc_data()
+    xv, yv = x[100:], y[100:]
+    x, y = x[:100], y[:100]
+    model = M.RNNFullModel(timesteps=x.shape[1], x_dim=V, y_dim=V, z_dim=24, model_name="ytoz", rnn_type=rnn_type,
+                           z_to_z_activation=act, y_to_z=True, y_to_y=False, x_to_y=False, x_to_z=False, seed=3)
+    assert model.n_classes == V and model.rnn_type == rnn_type
+    ws = model.model.get_weights()
+    G = {"LSTM": 4, "GRU": 3, "simpleRNN": 1}[rnn_type]
+    assert [w.shape for w in ws] == [(V, G * 24), (24, G * 24), (G * 24,), (24, V)]
+    ora = ks.Model(rnn_type, act, ws, dtype=torch.float64)
+    model.compile_model(loss="categorical_crossentropy", metrics=[], optimizer=Adagrad(lr=0.05, epsilon=1e-08,
+                                                                                        decay=0.0, clipnorm=1.))
+    np.random.seed(11)
+    hist = model.fit_model([x], y, validation_data=([xv], yv), n_epochs=3, batch_size=32, verbose=0)
+    ref = oracle_fit(ora, pp.to_id_batch(x), pp.to_id_batch(y), 3, 32, 0.05, 11,
+                     val=(pp.to_id_batch(xv), pp.to_id_batch(yv)))
+    assert np.allclose(hist.history["loss"], ref["loss"], rtol=TOL)
+    assert np.allclose(hist.history["val_loss"], ref["val_loss"], rtol=TOL)
+    assert hist.history["categorical_crossentropy"] == hist.history["loss"]
+    for w, r in zip(model.model.get_weights(), ora.numpy_weights()):
+        assert rel_err(w, r) <= TOL
+    names, scores = model.evaluate([xv], yv, batch_size=7)
+    assert names == ["loss", "categorical_crossentropy"] and len(scores) == 2 and scores[0] == scores[1]
+    assert abs(scores[0] - oracle_eval(ora, pp.to_id_batch(xv), pp.to_id_batch(yv), 7)) <= TOL * scores[0]
+    probs = model.predict([xv], batch_size=10, verbose=0)
+    i = as_t(pp.to_id_batch(xv))
+    rp = ora.predict_proba(ids=i, mask=i >= 0).numpy()
+    assert probs.shape == rp.shape and probs.dtype == np.float32 and np.abs(probs - rp).max() <= TOL
+    # id-format batches give the same numbers as the dense one-hot batches
+    probs_ids = model.predict(pp.to_id_batch(xv), batch_size=10, verbose=0)
+    assert np.array_equal(probs, probs_ids)
+    # the reference's scoring consumer (model.py:106-112) on the fused target-prob path
+    py = model.predict_target_prob([xv], yv)
+    want = np.clip(np.max(rp * yv, axis=2), ks.EPS32, ks.ONE_MINUS_EPS32)
+    assert np.abs(py - want).max() <= TOL
+
+
+def test_callbacks_early_stopping_checkpoint_and_val_cut(tmp_path):
+    x, y, V, seqs = mc_data(60, 12)
+    model = M.RNNFullModel(timesteps=12, x_dim=V, y_dim=V, z_dim=8, model_name="m", rnn_type="LSTM", y_to_z=True,
+                           y_to_y=False, x_to_y=False, x_to_z=False, seed=5)
+    model.compile_model(optimizer=Adagrad(lr=0.0, epsilon=1e-08, decay=0.0, clipnorm=1.))   # lr 0: loss cannot improve
+    lengths = np.minimum([len(s) - 1 for s in seqs], 12)
+    keep = lengths > 0
+    val_hist = M.ValLossHistoryCut(([x[keep]], y[keep]), lengths[keep])
+    ckpt = cb.ModelCheckpoint(str(tmp_path / "w.{epoch:02d}-{val_loss:.2f}.npz"), monitor="val_loss",
+                              save_weights_only=True, save_best_only=True)
+    stop = cb.EarlyStopping(monitor="val_loss", min_delta=0, patience=2, verbose=0, mode="auto")
+    hist = model.fit_model([x], y, validation_data=([x], y), n_epochs=50, batch_size=16, verbose=0,
+                           callbacks=[val_hist, ckpt, stop])
+    assert len(hist.history["loss"]) == 4                     # epoch 0 best, then patience 2 (+1 Keras off-by-one)
+    assert len(val_hist.val_lossses) == 4 and np.isfinite(val_hist.val_lossses).all()
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].startswith("w.00-")
+    before = model.model.get_weights()
+    model.load_model_weights(str(tmp_path / files[0]))
+    for a, b in zip(before, model.model.get_weights()):
+        assert np.array_equal(a, b)
+
+
+def test_weight_surface_layers_and_freezing(tmp_path):
+    V = 9
+    model = M.RNNFullModel(timesteps=5, x_dim=V, y_dim=V, z_dim=6, model_name="ws", rnn_type="LSTM", y_to_z=True,
+                           y_to_y=False, x_to_y=False, x_to_z=False, toy_bias=False, seed=1)
+    rnn = model.get_layer_weights("z_to_z_output")
+    assert [w.shape for w in rnn] == [(V, 24), (6, 24), (24,)] and np.all(rnn[2][6:12] == 1.0)   # unit_forget_bias
+    assert [w.shape for w in model.get_layer_weights("to_y_output")] == [(6, V)]
+    assert [w.shape for w in model.get_layer_weights(3)] == [(V, 24), (6, 24), (24,)]
+    new = [np.full_like(w, 0.5) for w in rnn]
+    model.set_layer_weights("z_to_z_output", new)
+    assert np.all(model.get_layer_weights("z_to_z_output")[0] == 0.5)
+    model.set_layer_weights_trainable("to_y_output", trainable=False)
+    tr, ntr = model.get_model_weights()
+    assert ntr == ["W_out"] and "W_out" not in tr
+    model.save_model_weights(str(tmp_path) + "/")
+    other = M.RNNFullModel(timesteps=5, x_dim=V, y_dim=V, z_dim=6, model_name="o", rnn_type="LSTM", y_to_z=True,
+                           y_to_y=False, x_to_y=False, x_to_z=False, seed=2)
+    other.load_model_weights(str(tmp_path) + "/ws.npz")
+    for a, b in zip(model.model.get_weights(), other.model.get_weights()):
+        assert np.array_equal(a, b)
+    acts = model.get_activations("z_to_z_output", [np.eye(V)[None, [1, 2, 3, 4, 0]]], ["y_input"])
+    assert acts.shape == (1, 5, 6)
+
+
+def test_baseline_model_with_history_features():
+    """RNNBaseline (model.py:241-258): [onehot || xs] features through the K2 projection, logits with bias."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "batch_format.npz"))
+    xb, yb = g["xb_xs"], g["yb_xs"]
+    model = M.RNNBaseline(timesteps=xb.shape[1], features=xb.shape[2], n_classes=4, rnn_type="LSTM", z_dim=5, seed=7)
+    ws = model.model.get_weights()
+    assert [w.shape for w in ws] == [(8, 20), (5, 20), (20,), (5, 4), (4,)]
+    ora = ks.Model("LSTM", "relu", ws, dtype=torch.float64)
+    model.compile_model(optimizer=Adagrad(lr=0.1, epsilon=1e-08, decay=0.0, clipnorm=1.))
+    hist = model.fit_model(xb, yb, n_epochs=2, batch_size=5, verbose=0)
+    t = as_t(pp.to_id_batch(yb))
+    xd = torch.tensor(xb, dtype=torch.float64)
+    want = []
+    for _ in range(2):
+        l, _, _ = ora.train_step(None, t, ks.derive_mask(xd), lr=0.1, epsilon=1e-8, clipnorm=1.0, x_dense=xd)
+        want.append(float(l))
+    assert np.allclose(hist.history["loss"], want, rtol=TOL)
+    for w, r in zip(model.model.get_weights(), ora.numpy_weights()):
+        assert rel_err(w, r) <= TOL
+    # plain one-hot features take the gather path and agree with the dense path's oracle too
+    xp_, yp_ = g["xb_plain"], g["yb_plain"]
+    m2 = M.RNNBaseline(timesteps=xp_.shape[1], features=4, n_classes=4, rnn_type="simpleRNN", z_dim=3, seed=8)
+    o2 = ks.Model("simpleRNN", "relu", m2.model.get_weights(), dtype=torch.float64)
+    p = m2.predict(xp_, batch_size=2, verbose=0)
+    xd = torch.tensor(xp_, dtype=torch.float64)
+    assert np.abs(p - o2.predict_proba(x_dense=xd, mask=ks.derive_mask(xd)).numpy()).max() <= TOL
+
+
+def test_unsupported_branches_raise():
+    with pytest.raises(NotImplementedError):
+        M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4)             # reference defaults: y_to_y / x_to_y branches
+    with pytest.raises(NotImplementedError):
+        M.NoRecurrenceModel(5, 4, 4)
+    m = M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4, y_to_z=True, y_to_y=False, x_to_y=False, x_to_z=False)
+    m.compile_model()                                              # 'adam' string is accepted at compile time ...
+    with pytest.raises(NotImplementedError):
+        m.fit_model(np.zeros((2, 5, 4)), np.zeros((2, 5, 4)), verbose=0)   # ... but the reference never trains with it
