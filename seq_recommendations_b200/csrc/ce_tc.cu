@@ -1,0 +1,848 @@
+// K5 / K6 on the 5th-generation tensor cores: fused logits GEMM + online-softmax statistics (forward) and the
+// recompute-based backward (dH and dW_out), never materialising the (N,V) logits.
+// Reference constructs replaced: TimeDistributed(Dense(V)) + softmax + categorical_crossentropy and Theano's
+// autodiff of them (model.py:382-384, :397; experiments_methods.py:42).
+//
+// sm_100a design
+//   * operands are bf16, K-major, staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into shared memory
+//   * tcgen05.mma (kind::f16, M=128) issued by ONE elected thread, fp32 accumulators in TMEM
+//   * "fp32 mode" = 3-pass split products  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  with hi = bf16(x), lo = bf16(x - hi)
+//     (16 mantissa bits per operand, ~2^-16 relative per product -- inside the 1e-4 budget of north_star);
+//     "bf16 mode" issues the hi.hi product only
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
+//     (tcgen05.ld 32x32b: one thread owns one token row -> row-wise softmax statistics need no shuffles)
+//   * the logits tile never leaves the SM: forward keeps a running (max, sum-exp) per row; backward turns the tile
+//     into dlogit = (p - onehot)*coef in registers, writes it as a bf16 hi/lo K-major operand into shared memory and
+//     feeds it straight back to the tensor core (dH += dS.W^T  /  dW += H^T.dS).
+//
+// Tiles: 128 tokens x 128 items; K (= hidden, padded to 64) is walked in 64-element blocks (one 128-byte swizzle row).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // tokens per tile (UMMA M)
+constexpr int BN = 128;          // items per tile  (UMMA N of the logits GEMM)
+constexpr int KBLK = 64;         // bf16 elements per 128-byte swizzled row
+constexpr int TILE_B = 128 * 128;  // bytes of one [128 rows x 64 bf16] operand block
+constexpr int TC_THREADS = 192;  // 6 warps
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ---- host: TMA descriptors --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 matrix (rows, cols) with leading dimension ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
+// Out-of-bounds elements are filled with zeros by the TMA unit.
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1030;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return -1031;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {KBLK, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1032;
+}
+
+// ---- device helpers ---------------------------------------------------------------------------------------------
+struct Pipe {  // ring of NS stages
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int ns) {
+    if (++stage == ns) { stage = 0; phase ^= 1; }
+  }
+};
+
+// one 64-wide K block of the split product: acc (+)= a_hi.b_hi [+ a_hi.b_lo + a_lo.b_hi]
+template <bool X3>
+__device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           uint32_t idesc, bool first) {
+  const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), db_hi = ptx::umma_desc_k_sw128(b_hi);
+  const uint64_t da_lo = ptx::umma_desc_k_sw128(a_lo), db_lo = ptx::umma_desc_k_sw128(b_lo);
+#pragma unroll
+  for (int k = 0; k < KBLK / 16; ++k) {
+    const int e = k * 16;
+    if (X3) {
+      // small cross terms first, the dominant hi.hi product last
+      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_lo, e), idesc,
+                     (first && k == 0) ? 0u : 1u);
+      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_lo, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
+      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
+    } else {
+      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc,
+                     (first && k == 0) ? 0u : 1u);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);  // .x = lo_elem (low 16 bits)
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// byte offset of element (row, col) inside a K-major 128-byte-swizzled operand whose 64-column blocks of `rows`
+// rows are laid one after another (block stride = rows*128 bytes)
+__device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
+  const int blk = col >> 6, c = col & 63;
+  return (uint32_t)(blk * rows * 128 + row * 128 + ((((c >> 3) ^ (row & 7)) << 4) | ((c & 7) << 1)));
+}
+
+// ================================================================================================================
+// forward: per-row running (max, sum-exp) of logits = A . Bt^T over this CTA's item tiles
+//   A  = hout (optionally x dropout factors), [N, Hk] bf16 hi/lo     (tmA_*,  box 64 x 128)
+//   Bt = W_out^T,                            [V, Hk] bf16 hi/lo     (tmB_*,  box 64 x 128)
+// grid = (token tiles, splits).  smem: A resident (KB blocks), Bt streamed in 64-wide K blocks through NS stages.
+template <int KB, int NS, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                     const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
+                     int64_t n_tokens, int v_begin, int v_end, int tiles_per_split) {
+  constexpr int NP = X3 ? 2 : 1;  // operand parts (hi, lo)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                                  // [NP][KB][TILE_B]
+  const uint32_t sB = sA + NP * KB * TILE_B;                 // [NS][NP][TILE_B]
+  const uint32_t sBar = sB + NS * NP * TILE_B;               // barriers
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, tmem_slot = bar_a + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BM;
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int vt0 = blockIdx.y * tiles_per_split;
+  const int vt1 = min(n_vtiles, vt0 + tiles_per_split);
+  const int n_tiles = max(0, vt1 - vt0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    ptx::mbar_init(bar_a, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0 && n_tiles > 0) {
+      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi);
+      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+        if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+      }
+      Pipe p;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int v0 = v_begin + (vt0 + t) * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          p.advance(NS);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0 && n_tiles > 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      ptx::mbar_wait(bar_a, 0);
+      ptx::tc_fence_after_sync();
+      Pipe p;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
+          ptx::umma_commit(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        ptx::umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int64_t n = (int64_t)row0 + row;
+    float m = -INFINITY, s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const int v0 = v_begin + (vt0 + t) * BN;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+      const bool ragged = v0 + BN > v_end;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        }
+        float z[32];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int v = v0 + c * 32 + j;
+          float x = __uint_as_float(r[j]);
+          if (b_out) x += (v < v_end) ? __ldg(b_out + v) : 0.f;
+          if (ragged && v >= v_end) x = -INFINITY;
+          z[j] = x;
+          cmax = fmaxf(cmax, x);
+        }
+        if (cmax > -INFINITY) {
+          const float mn = fmaxf(m, cmax);
+          const float nb = -mn * LOG2E;
+          float add = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) add += exp2f(fmaf(z[j], LOG2E, nb));
+          s = s * exp2f(fmaf(m, LOG2E, nb)) + add;
+          m = mn;
+        }
+      }
+    }
+    if (n < n_tokens && n_tiles > 0) {
+      ws_m[(int64_t)blockIdx.y * n_tokens + n] = m;
+      ws_s[(int64_t)blockIdx.y * n_tokens + n] = s;
+    } else if (n < n_tokens) {
+      ws_m[(int64_t)blockIdx.y * n_tokens + n] = -INFINITY;
+      ws_s[(int64_t)blockIdx.y * n_tokens + n] = 0.f;
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// per-row softmax terms shared by the two backward kernels
+struct RowTerms {
+  float nb;      // -m * log2(e)
+  float inv_s;   // 1 / s
+  float cf;      // coef * inv_nvalid (0 for masked / clip-saturated tokens)
+  int32_t tg;    // target item (or -1)
+};
+
+// dlogit for 32 consecutive items of one row, from the raw fp32 accumulator chunk
+__device__ __forceinline__ void dlogit_chunk(const uint32_t (&r)[32], const RowTerms& rt, int vcol0, int v_end,
+                                             float (&d)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float p = exp2f(fmaf(__uint_as_float(r[j]), LOG2E, rt.nb)) * rt.inv_s;
+    d[j] = (vcol0 + j < v_end) ? p * rt.cf : 0.f;
+  }
+  const int tj = rt.tg - vcol0;
+  if (tj >= 0 && tj < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == tj) d[j] -= rt.cf;
+  }
+}
+
+// ================================================================================================================
+// backward, token-stationary: dh[n,:] = sum_v dlogit[n,v] * W_out[:,v]
+//   per item tile:  S = A.Bt^T (TMEM, double buffered) -> epilogue writes dS (bf16 hi/lo, K-major over items) to
+//   shared memory -> dH (TMEM, persistent accumulator) += dS . W^T with W = W_out [Hk, Vp] bf16 hi/lo (box 64 x Hk)
+// grid = token tiles.  Needs Hk <= 128 (shared-memory budget; larger hidden sizes use the SIMT backward).
+template <int KB, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                         const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
+                         const float* __restrict__ srow, const float* __restrict__ coef,
+                         const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
+                         float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end, int accumulate) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int NS = 2;
+  constexpr int HK = KB * KBLK;
+  constexpr int NJ = BN / KBLK;                             // 64-item blocks per tile (K blocks of the dH GEMM)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                                  // [NP][KB][TILE_B]        hout tile (resident)
+  const uint32_t sD = sA + NP * KB * TILE_B;                 // [NP][NJ][TILE_B]        dS tile
+  const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]        Bt / W blocks
+  const uint32_t sBar = sB + NS * NP * TILE_B;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_dfull = bar_a + 8,
+                 bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8, tmem_slot = bar_hfull + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BM;
+  const int n_tiles = (v_end - v_begin + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_dfull, 4);
+    ptx::mbar_init(bar_dempty, 1);
+    ptx::mbar_init(bar_hfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_dh = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    // stage order must equal the MMA warp's consumption order: Bt(0), then per tile i: Bt(i+1), W(i)
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmW_hi);
+      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+        if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+      }
+      Pipe p;
+      auto load_bt = [&](int t) {
+        const int v0 = v_begin + t * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          p.advance(NS);
+        }
+      };
+      auto load_w = [&](int t) {
+        const int v0 = v_begin + t * BN;
+        for (int j = 0; j < NJ; ++j) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmW_hi, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmW_lo, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
+          p.advance(NS);
+        }
+      };
+      load_bt(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) load_bt(t + 1);
+        load_w(t);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(BM, HK);
+      ptx::mbar_wait(bar_a, 0);
+      ptx::tc_fence_after_sync();
+      Pipe p;
+      auto issue_s = [&](int t) {
+        const int buf = t & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc_s, kb == 0);
+          ptx::umma_commit(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        ptx::umma_commit(bar_tfull + 8 * buf);
+      };
+      issue_s(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) issue_s(t + 1);
+        ptx::mbar_wait(bar_dfull, t & 1);          // dS(t) is in shared memory
+        ptx::tc_fence_after_sync();
+        for (int j = 0; j < NJ; ++j) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(tmem_dh, sD + j * TILE_B, sD + (NJ + j) * TILE_B, b, b + TILE_B, idesc_h, t == 0 && j == 0);
+          ptx::umma_commit(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        ptx::umma_commit(bar_dempty);               // dS buffer may be overwritten
+      }
+      ptx::umma_commit(bar_hfull);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int64_t n = (int64_t)row0 + row;
+    RowTerms rt;
+    {
+      const bool ok = n < n_tokens;
+      const float cf = ok ? coef[n] * inv_nvalid[0] : 0.f;
+      rt.cf = cf;
+      rt.nb = (ok && cf != 0.f) ? -mrow[n] * LOG2E : 0.f;
+      rt.inv_s = (ok && cf != 0.f) ? 1.0f / srow[n] : 0.f;
+      rt.tg = (ok && cf != 0.f) ? tgt[n] : -1;
+    }
+    uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const int v0 = v_begin + t * BN;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        }
+        float d[32];
+        dlogit_chunk(r, rt, v0 + c * 32, v_end, d);
+        if (c == 0) ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);   // previous tile's dH MMAs are done with the buffer
+        // 32 consecutive items = 4 sixteen-byte chunks of this row, hi and lo parts
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = d[g * 8 + 2 * e], x1 = d[g * 8 + 2 * e + 1];
+            const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
+            if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
+          }
+          const uint32_t off = sw128_offset(row, c * 32 + g * 8, BM);
+          *reinterpret_cast<uint4*>(sD_gen + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (X3) *reinterpret_cast<uint4*>(sD_gen + NJ * TILE_B + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_dfull);
+    }
+    // final: dH accumulator -> global (fp32), optionally times the dropout factors
+    ptx::mbar_wait(bar_hfull, 0);
+    ptx::tc_fence_after_sync();
+#pragma unroll 1
+    for (int c = 0; c < HK / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_dh + ((uint32_t)(q * 32) << 16) + c * 32, r);
+      ptx::tmem_ld_wait();
+      if (n < n_tokens) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int h = c * 32 + j;
+          if (h < H) {
+            float x = __uint_as_float(r[j]);
+            if (hscale) x *= hscale[n * H + h];
+            if (accumulate) x += dh[n * H + h];
+            dh[n * H + h] = x;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================================
+// backward, item-stationary: dW_out[:, v] += sum_n hs[n,:] * dlogit[n,v]
+//   Bt tile resident.  Per token tile:  S = A.Bt^T -> epilogue writes dS TRANSPOSED (rows = items, K = tokens) ->
+//   dW (TMEM [Hk x 128 items]) += Ht . dS^T with Ht = hs^T [Hk, Np] bf16 hi/lo (box 64 tokens x Hk).
+// grid = (item tiles, token splits); the fp32 result leaves through vector reductions into a pre-zeroed dW_out.
+template <int KB, bool X3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo,
+                         const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
+                         const float* __restrict__ srow, const float* __restrict__ coef,
+                         const float* __restrict__ inv_nvalid, float* __restrict__ dW, int64_t n_tokens, int H,
+                         int v_begin, int v_end, int ldw, int tiles_per_split) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int NS = 2;
+  constexpr int HK = KB * KBLK;
+  constexpr int NJ = BM / KBLK;                             // 64-token blocks per tile (K blocks of the dW GEMM)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBt = base;                                 // [NP][KB][TILE_B]       W_out^T tile (resident)
+  const uint32_t sD = sBt + NP * KB * TILE_B;                // [NP][NJ][TILE_B]       dS^T tile
+  const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]       A / Ht blocks
+  const uint32_t sBar = sB + NS * NP * TILE_B;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_dfull = bar_a + 8,
+                 bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8, tmem_slot = bar_hfull + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v0 = v_begin + blockIdx.x * BN;
+  const int64_t tok_tiles = (n_tokens + BM - 1) / BM;
+  const int64_t tt0 = (int64_t)blockIdx.y * tiles_per_split;
+  const int n_tiles = (int)max((int64_t)0, min(tok_tiles, tt0 + tiles_per_split) - tt0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_dfull, 4);
+    ptx::mbar_init(bar_dempty, 1);
+    ptx::mbar_init(bar_hfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_dw = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0 && n_tiles > 0) {
+      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmT_hi);
+      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
+        if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
+      }
+      Pipe p;
+      auto load_a = [&](int t) {
+        const int r0 = (int)((tt0 + t) * BM);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmA_hi, bar_full + 8 * p.stage, kb * KBLK, r0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmA_lo, bar_full + 8 * p.stage, kb * KBLK, r0);
+          p.advance(NS);
+        }
+      };
+      auto load_t = [&](int t) {
+        const int r0 = (int)((tt0 + t) * BM);
+        for (int j = 0; j < NJ; ++j) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmT_hi, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmT_lo, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
+          p.advance(NS);
+        }
+      };
+      load_a(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) load_a(t + 1);
+        load_t(t);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0 && n_tiles > 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16(HK, BN);   // M = hidden, N = items, K = tokens
+      ptx::mbar_wait(bar_a, 0);
+      ptx::tc_fence_after_sync();
+      Pipe p;
+      auto issue_s = [&](int t) {
+        const int buf = t & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(d, a, a + TILE_B, sBt + kb * TILE_B, sBt + (KB + kb) * TILE_B, idesc_s, kb == 0);
+          ptx::umma_commit(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        ptx::umma_commit(bar_tfull + 8 * buf);
+      };
+      issue_s(0);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) issue_s(t + 1);
+        ptx::mbar_wait(bar_dfull, t & 1);
+        ptx::tc_fence_after_sync();
+        for (int j = 0; j < NJ; ++j) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a = sB + p.stage * NP * TILE_B;     // Ht block: rows = hidden, K = 64 tokens
+          mma_kblock<X3>(tmem_dw, a, a + TILE_B, sD + j * TILE_B, sD + (NJ + j) * TILE_B, idesc_w, t == 0 && j == 0);
+          ptx::umma_commit(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        ptx::umma_commit(bar_dempty);
+      }
+      ptx::umma_commit(bar_hfull);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
+    const float inv = inv_nvalid[0];
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const int64_t n = (tt0 + t) * BM + row;
+      RowTerms rt;
+      {
+        const bool ok = n < n_tokens;
+        const float cf = ok ? coef[n] * inv : 0.f;
+        rt.cf = cf;
+        rt.nb = (ok && cf != 0.f) ? -mrow[n] * LOG2E : 0.f;
+        rt.inv_s = (ok && cf != 0.f) ? 1.0f / srow[n] : 0.f;
+        rt.tg = (ok && cf != 0.f) ? tgt[n] : -1;
+      }
+      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+        }
+        float d[32];
+        dlogit_chunk(r, rt, v0 + c * 32, v_end, d);
+        if (c == 0) ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);
+        // transposed store: operand row = item (c*32+j), K index = this thread's token row
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(d[j]);
+          const uint32_t off = sw128_offset(c * 32 + j, row, BN);
+          *reinterpret_cast<__nv_bfloat16*>(sD_gen + off) = hv;
+          if (X3)
+            *reinterpret_cast<__nv_bfloat16*>(sD_gen + NJ * TILE_B + off) =
+                __float2bfloat16_rn(d[j] - __bfloat162float(hv));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_dfull);
+    }
+    if (n_tiles > 0) {
+      // final: dW accumulator rows = hidden unit, columns = items of this tile -> reductions into dW_out (H, ldw)
+      ptx::mbar_wait(bar_hfull, 0);
+      ptx::tc_fence_after_sync();
+      const int h = row;
+      const bool vec_ok = (ldw & 3) == 0 && (v_begin & 3) == 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_dw + ((uint32_t)(q * 32) << 16) + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (h < H && h < HK) {
+          float* dst = dW + (size_t)h * ldw + v0 + c * 32;
+          const int valid = min(32, v_end - (v0 + c * 32));
+          if (vec_ok && valid == 32) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              red_add_f4(dst + 4 * g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                                  __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < valid) atomicAdd(dst + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// exact fp32 target logit: zy[n] = sum_h hs[n,h] * W_out[h, tgt[n]] (+ b_out[tgt[n]]); one warp per token
+__global__ void __launch_bounds__(256)
+target_logit_kernel(const float* __restrict__ hout, const float* __restrict__ hscale,
+                    const float* __restrict__ W_out, const float* __restrict__ b_out,
+                    const int32_t* __restrict__ tgt, float* __restrict__ zy, int64_t n_tokens, int H, int ldw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_tokens) return;
+  const int32_t t = tgt[n];
+  if (t < 0) return;
+  float acc = 0.f;
+  for (int h = lane; h < H; h += 32) {
+    float x = hout[n * H + h];
+    if (hscale) x *= hscale[n * H + h];
+    acc = fmaf(x, __ldg(W_out + (size_t)h * ldw + t), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) zy[n] = acc + (b_out ? b_out[t] : 0.f);
+}
+
+template <int KB, int NS, bool X3>
+int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+               const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end, int splits,
+               cudaStream_t st) {
+  constexpr int NP = X3 ? 2 : 1;
+  const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NS * NP * TILE_B + 256;
+  auto k = ce_tc_forward_kernel<KB, NS, X3>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  const int n_vtiles = ceil_div(v_end - v_begin, BN);
+  const int tps = ceil_div(n_vtiles, splits);
+  dim3 grid(ceil_div(n_tokens, BM), splits);
+  k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, tps);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
+                                   const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && H > 0 && ldw > 0, 1);
+  target_logit_kernel<<<ceil_div(n_tokens * 32, 256), 256, 0, as_stream(stream)>>>(hout, hscale, W_out, b_out, tgt, zy,
+                                                                                  n_tokens, H, ldw);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi,
+                                    const uint16_t* Bt_lo, const float* b_out, float* ws_m, float* ws_s,
+                                    int64_t n_tokens, int Hk, int V, int v_begin, int v_end, int splits, int x3,
+                                    void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V && splits >= 1, 1);
+  SEQREC_ARG(Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256, 2);
+  SEQREC_ARG(A_hi && Bt_hi && (!x3 || (A_lo && Bt_lo)), 3);
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  if ((rc = make_tmap(&a_hi, A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&b_hi, Bt_hi, V, Hk, Hk, BN))) return rc;
+  if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
+  cudaStream_t st = as_stream(stream);
+#define FWD(KB, NS)                                                                                                 \
+  return x3 ? launch_fwd<KB, NS, true>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, splits, \
+                                       st)                                                                          \
+            : launch_fwd<KB, NS, false>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end,        \
+                                        splits, st)
+  switch (Hk / KBLK) {
+    case 1: FWD(1, 4);
+    case 2: FWD(2, 4);
+    case 3: FWD(3, 3);
+    default: FWD(4, 3);
+  }
+#undef FWD
+}
+
+extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Ht_hi,
+                                     const uint16_t* Ht_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                                     const uint16_t* W_hi, const uint16_t* W_lo, const int32_t* tgt, const float* m,
+                                     const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
+                                     float* dh, float* dW_out, int64_t n_tokens, int H, int Hk, int V, int Vp,
+                                     int64_t Np, int v_begin, int v_end, int ldw, int accumulate_dh, int x3,
+                                     void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
+  SEQREC_ARG((Hk == 64 || Hk == 128) && H <= Hk, 2);
+  SEQREC_ARG(Vp >= V && Vp % 8 == 0 && Np >= n_tokens && Np % 8 == 0 && ldw >= v_end, 3);
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, t_hi, t_lo;
+  int rc;
+  if ((rc = make_tmap(&a_hi, A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&b_hi, Bt_hi, V, Hk, Hk, BN))) return rc;
+  if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
+  const int NP = x3 ? 2 : 1;
+  const int KB = Hk / KBLK;
+  const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)2 * NP * TILE_B + 256;
+  if (dh) {
+    if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, Hk))) return rc;
+    if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, Hk))) return rc;
+#define DH(KBV, X3V)                                                                                          \
+  {                                                                                                           \
+    auto k = ce_tc_backward_dh_kernel<KBV, X3V>;                                                              \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e != cudaSuccess) return -(int)e;                                                                     \
+    k<<<ceil_div(n_tokens, BM), TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef,  \
+                                                        inv_nvalid, hscale, dh, n_tokens, H, v_begin, v_end,  \
+                                                        accumulate_dh);                                       \
+  }
+    if (KB == 1) { if (x3) DH(1, true) else DH(1, false) }
+    else         { if (x3) DH(2, true) else DH(2, false) }
+#undef DH
+    SEQREC_CHECK_LAUNCH();
+  }
+  if (dW_out) {
+    if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, Hk))) return rc;
+    if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, Hk))) return rc;
+    const int v_tiles = ceil_div(v_end - v_begin, BN);
+    const int64_t tok_tiles = (n_tokens + BM - 1) / BM;
+    int splits = SEQREC_NUM_SMS / v_tiles;                    // keep the grid within one wave of 148 CTAs
+    if (splits < 1) splits = 1;
+    if (splits > tok_tiles) splits = (int)tok_tiles;
+    const int tps = ceil_div(tok_tiles, splits);
+    splits = ceil_div(tok_tiles, tps);
+    dim3 grid(v_tiles, splits);
+#define DW(KBV, X3V)                                                                                          \
+  {                                                                                                           \
+    auto k = ce_tc_backward_dw_kernel<KBV, X3V>;                                                              \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e != cudaSuccess) return -(int)e;                                                                     \
+    k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,        \
+                                      dW_out, n_tokens, H, v_begin, v_end, ldw, tps);                         \
+  }
+    if (KB == 1) { if (x3) DW(1, true) else DW(1, false) }
+    else         { if (x3) DW(2, true) else DW(2, false) }
+#undef DW
+    SEQREC_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -31,8 +31,8 @@ def test_gather_rows_bit_exact(V, GH, N):
     mask = torch.tensor((rng.random(N) > 0.2).astype(np.uint8))
     ids = torch.where(mask.bool(), ids, torch.full_like(ids, -1))
     out = torch.empty((N, GH), dtype=torch.float32, device="cuda")
-    call("seqrec_gather_rows", ptr(W.cuda()), ptr(b.cuda()), ptr(ids.cuda()), ptr(mask.cuda()), None, ptr(out), N, V,
-         GH, stream())
+    dW, db_, dids, dmask = W.cuda(), b.cuda(), ids.cuda(), mask.cuda()     # keep the device copies alive
+    call("seqrec_gather_rows", ptr(dW), ptr(db_), ptr(dids), ptr(dmask), None, ptr(out), N, V, GH, stream())
     ref = ks.input_projection(W, b, ids=ids.long(), mask=mask.bool())
     assert torch.equal(out.cpu(), ref)
 
@@ -41,8 +41,8 @@ def test_format_batch_transposes_and_counts():
     ids, tgt = synthetic.make_batch(500, 37, 45, seed=5)
     d = lambda *s, dt=torch.int32: torch.empty(s, dtype=dt, device="cuda")
     ids_tb, tgt_tb, mask_tb, nv = d(37, 45), d(37, 45), d(37, 45, dt=torch.uint8), torch.zeros(1, dtype=torch.int32, device="cuda")
-    call("seqrec_format_batch", ptr(torch.tensor(ids).cuda()), ptr(torch.tensor(tgt).cuda()), ptr(ids_tb), ptr(tgt_tb),
-         ptr(mask_tb), ptr(nv), 45, 37, stream())
+    dids, dtgt = torch.tensor(ids).cuda(), torch.tensor(tgt).cuda()
+    call("seqrec_format_batch", ptr(dids), ptr(dtgt), ptr(ids_tb), ptr(tgt_tb), ptr(mask_tb), ptr(nv), 45, 37, stream())
     assert np.array_equal(ids_tb.cpu().numpy(), ids.T) and np.array_equal(tgt_tb.cpu().numpy(), tgt.T)
     assert np.array_equal(mask_tb.cpu().numpy().astype(bool), (ids >= 0).T) and int(nv.item()) == int((ids >= 0).sum())
 
@@ -57,9 +57,10 @@ def test_scatter_add_rows_with_heavy_duplicates(V, GH, N):
     touched = torch.zeros(V, dtype=torch.int32, device="cuda")
     rows = torch.empty(V, dtype=torch.int32, device="cuda")
     n_rows = torch.zeros(1, dtype=torch.int32, device="cuda")
-    call("seqrec_scatter_add_rows", ptr(torch.tensor(dxp).cuda()), ptr(torch.tensor(ids_np).cuda()),
-         ptr(torch.tensor(mask_np.astype(np.uint8)).cuda()), None, ptr(dW), ptr(touched), ptr(rows), ptr(n_rows), N, V,
-         GH, stream())
+    ddxp, dids = torch.tensor(dxp).cuda(), torch.tensor(ids_np).cuda()
+    dmask = torch.tensor(mask_np.astype(np.uint8)).cuda()
+    call("seqrec_scatter_add_rows", ptr(ddxp), ptr(dids), ptr(dmask), None, ptr(dW), ptr(touched), ptr(rows),
+         ptr(n_rows), N, V, GH, stream())
     ref = np.zeros((V, GH), dtype=np.float64)
     np.add.at(ref, ids_np[mask_np], dxp[mask_np].astype(np.float64))
     assert rel_err(dW.cpu().numpy(), ref) < 1e-6
