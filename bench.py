@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--tc", default="x3", choices=["x3", "bf16", "off"], help="logits GEMM mode (x3 = fp32-grade)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -196,7 +197,7 @@ def main():
 
     V, H, T, B = cfg["V"], cfg["H"], cfg["T"], cfg["B"]
     ws = synthetic.make_weights(cfg["cell"], V, H, seed=0)
-    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, comm=comm, seed=rank)
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, comm=comm, seed=rank, tc=args.tc)
     hot.set_optimizer("adagrad", lr=0.01, epsilon=1e-8, clipnorm=1.0)
     hot.dropout_out = args.dropout
     n_batches = 4
@@ -266,7 +267,10 @@ def main():
     dom_ms = per_step.get("ce_bwd", 0.0)
     achieved = work["ce_bwd_flops"] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     roofline = {
-        "kernel": "seqrec_ce_backward (logits recompute + dH + dW_out, %s)" % ("fp32 SIMT"),
+        "kernel": "seqrec_ce_%sbackward (logits recompute + dH + dW_out, %s)" % (
+            ("tc_", "tcgen05 bf16 %s, fp32 accumulate in TMEM" % ("3-pass hi/lo split" if hot.tc_x3 else "single pass"))
+            if hot.work(B, T).tc["bwd"] else ("", "fp32 SIMT")),
+        "mma_flops_issued": work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 6 / 4 if hot.work(B, T).tc["bwd"] else 1.5),
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
         "ms_per_launch": dom_ms,
@@ -283,7 +287,10 @@ def main():
     line = {
         "metric": METRIC, "value": world * B / (step_ms * 1e-3), "unit": "sequences/sec", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"x3": "f32 (bf16x3 split tensor-core GEMMs, fp32 accumulate; fp32 SIMT elsewhere)",
+                  "bf16": "bf16 logits GEMMs, fp32 accumulate; fp32 elsewhere", "off": "f32"}[hot.tc_mode],
+        "data": "synthetic",
         "config": {"workload": args.config, "cell": cfg["cell"], "act": cfg["act"], "V": V, "H": H, "T": T,
                    "B_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "256 MiB memset between timed steps (outside the events)", "dropout": args.dropout,

@@ -105,6 +105,27 @@ int seqrec_ce_backward(const float* hout, const float* hscale, const float* W_ou
                        int V, int v_begin, int v_end, int ldw, int accumulate_dh, int use_tensor_cores,
                        void* stream);
 
+/* ---- K5/K6 on the tcgen05 tensor cores (csrc/ce_tc.cu) ----------------------------------------------------------
+ * Operands are bf16 hi/lo pairs staged by seqrec_split_bf16 (lo pointers may be NULL when x3 == 0 = single-pass bf16):
+ *   A  = hs            (N, Hk)   hs = hout (x dropout factors), Hk = H padded to a multiple of 64 with zeros
+ *   Ht = hs^T          (Hk, Np)  Np = N padded to a multiple of 8
+ *   Bt = W_out^T       (V, Hk)
+ *   W  = W_out         (Hk, Vp)  Vp = V padded to a multiple of 8
+ * x3 != 0 selects the 3-pass split product (fp32-grade, ~2^-16 relative); forward supports Hk <= 256, backward
+ * Hk <= 128 and no output bias.  ws_m / ws_s as in seqrec_ce_forward; the target logit comes from
+ * seqrec_target_logit (exact fp32 dot product). */
+int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                         const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int Hk, int V, int v_begin,
+                         int v_end, int splits, int x3, void* stream);
+int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Ht_hi, const uint16_t* Ht_lo,
+                          const uint16_t* Bt_hi, const uint16_t* Bt_lo, const uint16_t* W_hi, const uint16_t* W_lo,
+                          const int32_t* tgt, const float* m, const float* s, const float* coef,
+                          const float* inv_nvalid, const float* hscale, float* dh, float* dW_out, int64_t n_tokens,
+                          int H, int Hk, int V, int Vp, int64_t Np, int v_begin, int v_end, int ldw,
+                          int accumulate_dh, int x3, void* stream);
+int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
+                        const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream);
+
 /* ---- K9: scoring (model.py:194-195 predict; model.py:106-112 consumer) ------------------------------------------
  * full probabilities, batch-major (B,T,V) float32, for catalogs small enough to materialise */
 int seqrec_predict_probs(const float* hout, const float* W_out, const float* b_out, const float* m, const float* s,

@@ -263,6 +263,11 @@ struct RowTerms {
 // dlogit for 32 consecutive items of one row, from the raw fp32 accumulator chunk
 __device__ __forceinline__ void dlogit_chunk(const uint32_t (&r)[32], const RowTerms& rt, int vcol0, int v_end,
                                              float (&d)[32]) {
+  if (rt.cf == 0.f) {  // masked or clip-saturated token: no gradient (and no inf*0 from an unscaled exp)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[j] = 0.f;
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float p = exp2f(fmaf(__uint_as_float(r[j]), LOG2E, rt.nb)) * rt.inv_s;
@@ -568,7 +573,7 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const int r0 = (int)((tt0 + t) * BM);
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // box = 128 rows (rows >= Hk are zero)
           const uint32_t dst = sB + p.stage * NP * TILE_B;
           ptx::tma_load_2d(dst, &tmT_hi, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
           if (X3) ptx::tma_load_2d(dst + TILE_B, &tmT_lo, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
@@ -585,7 +590,7 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0 && n_tiles > 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
-      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16(HK, BN);   // M = hidden, N = items, K = tokens
+      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16(128, BN);  // M = hidden (padded to 128), N = items, K = tokens
       ptx::mbar_wait(bar_a, 0);
       ptx::tc_fence_after_sync();
       Pipe p;
@@ -821,8 +826,8 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
     SEQREC_CHECK_LAUNCH();
   }
   if (dW_out) {
-    if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, Hk))) return rc;
-    if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, Hk))) return rc;
+    if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
+    if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     const int v_tiles = ceil_div(v_end - v_begin, BN);
     const int64_t tok_tiles = (n_tokens + BM - 1) / BM;
     int splits = SEQREC_NUM_SMS / v_tiles;                    // keep the grid within one wave of 148 CTAs

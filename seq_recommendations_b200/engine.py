@@ -17,6 +17,7 @@ HBM layout (all fp32 unless noted; token n = t*B + b, time-major):
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,20 @@ class _Work:
         self.hscale = None
         self.in_scale = None
         self.x_dense = None
+        # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
+        self.tc = hp._tc_plan(N)
+        if self.tc["fwd"]:
+            bf = torch.bfloat16
+            self.Np = (N + 7) // 8 * 8
+            self.A_hi = torch.zeros((N, hp.Hk), dtype=bf, device=dev)
+            self.A_lo = torch.zeros((N, hp.Hk), dtype=bf, device=dev) if hp.tc_x3 else None
+            if self.tc["bwd"]:
+                self.Ht_hi = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev)
+                self.Ht_lo = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev) if hp.tc_x3 else None
+            if self.tc["splits"] > self.splits:
+                self.splits = self.tc["splits"]
+                self.ws_m = torch.empty((self.splits, N), dtype=f32, device=dev)
+                self.ws_s = torch.empty((self.splits, N), dtype=f32, device=dev)
         # pinned staging for host batches
         self.pin_ids = torch.empty((B, T), dtype=i32, pin_memory=True)
         self.pin_tgt = torch.empty((B, T), dtype=i32, pin_memory=True)
@@ -71,7 +86,7 @@ class _Work:
 
 class HotPath:
     def __init__(self, cell, act, in_dim, hidden, n_items, out_bias=False, input_kind="ids", weights=None,
-                 device=None, comm=None, seed=0):
+                 device=None, comm=None, seed=0, tc="x3"):
         if not torch.cuda.is_available():
             raise _lib.SeqrecError("seq_recommendations_b200 needs a CUDA device (sm_100a); there is no CPU path")
         _lib.load()
@@ -128,6 +143,17 @@ class HotPath:
         self.trainable = {"W_in": True, "U": True, "b": True, "W_out": True, "b_out": True}
         self.opt = None
         self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
+        # tensor-core logits path: 'x3' = 3-pass bf16 split products (fp32-grade, the default), 'bf16' = single pass,
+        # 'off' = exact-fp32 SIMT kernels.  SEQREC_TC overrides.  Small / odd problems always take the SIMT kernels.
+        self.tc_mode = os.environ.get("SEQREC_TC", tc)
+        if self.tc_mode not in ("x3", "bf16", "off"):
+            raise ValueError("tc must be 'x3', 'bf16' or 'off'")
+        self.tc_x3 = self.tc_mode == "x3"
+        self.Hk = (self.H + 63) // 64 * 64
+        self.Vp = (self.V + 7) // 8 * 8
+        self._w_version = 0
+        self._split_version = -1
+        self.Bt_hi = self.Bt_lo = self.Wb_hi = self.Wb_lo = None
         if weights is not None:
             self.set_weights(weights)
 
@@ -157,6 +183,33 @@ class HotPath:
         s = max(1, min(v_tiles, math.ceil(2 * NUM_SMS / tiles)))
         return s
 
+    def _tc_plan(self, N):
+        """Which logits kernels serve a batch of N tokens."""
+        fwd = (self.tc_mode != "off" and self.Hk <= 256 and self.V >= 256 and N >= 128)
+        bwd = fwd and self.Hk <= 128 and not self.out_bias
+        tiles = (N + 127) // 128
+        v_tiles = (self.V + 127) // 128
+        splits = max(1, min(v_tiles, NUM_SMS // tiles)) if tiles <= NUM_SMS else 1
+        return dict(fwd=fwd, bwd=bwd, splits=splits)
+
+    def _stage_weight_operands(self):
+        """bf16 hi/lo copies of W_out (as W and as W^T), refreshed whenever the weights changed."""
+        if self._split_version == self._w_version:
+            return
+        bf = torch.bfloat16
+        if self.Bt_hi is None:
+            self.Bt_hi = torch.zeros((self.V, self.Hk), dtype=bf, device=self.device)
+            self.Wb_hi = torch.zeros((self.Hk, self.Vp), dtype=bf, device=self.device)
+            if self.tc_x3:
+                self.Bt_lo = torch.zeros((self.V, self.Hk), dtype=bf, device=self.device)
+                self.Wb_lo = torch.zeros((self.Hk, self.Vp), dtype=bf, device=self.device)
+        st = self.stream
+        call("seqrec_split_bf16", ptr(self.W_out), None, ptr(self.Bt_hi), ptr(self.Bt_lo), self.H, self.V, self.Hk, 1,
+             st)
+        call("seqrec_split_bf16", ptr(self.W_out), None, ptr(self.Wb_hi), ptr(self.Wb_lo), self.H, self.V, self.Vp, 0,
+             st)
+        self._split_version = self._w_version
+
     def work(self, B, T):
         key = (B, T)
         w = self._work.get(key)
@@ -185,6 +238,7 @@ class HotPath:
             if tuple(src.shape) != tuple(dst.shape):
                 raise ValueError("weight shape %s does not match %s" % (src.shape, tuple(dst.shape)))
             dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+        self._w_version += 1
 
     def reset_optimizer_state(self):
         self.flat_a.zero_()
@@ -267,15 +321,44 @@ class HotPath:
         if training and self.dropout_out > 0:
             w.hscale = self._dropout((w.N, self.H), self.dropout_out)
 
-    def _forward_ce(self, w, with_targets=True):
+    def _forward_ce(self, w, with_targets=True, training=False):
         st = self.stream
-        self._mark("ce_fwd")
-        call("seqrec_ce_forward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
-             ptr(w.tgt) if with_targets else None, ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy), w.N, self.H, self.V, 0,
-             self.V, self.V, w.splits, 0, st)
+        if w.tc["fwd"]:
+            self._mark("stage_operands")
+            self._stage_weight_operands()
+            call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), w.N, self.H, self.Hk, 0,
+                 st)
+            if training and w.tc["bwd"]:
+                call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.Ht_hi), ptr(w.Ht_lo), w.N, self.H, w.Np,
+                     1, st)
+            self._mark("ce_fwd")
+            if with_targets:
+                call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
+                     ptr(w.zy), w.N, self.H, self.V, st)
+            call("seqrec_ce_tc_forward", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out),
+                 ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, w.tc["splits"], 1 if self.tc_x3 else 0, st)
+            n_splits = w.tc["splits"]
+        else:
+            self._mark("ce_fwd")
+            n_splits = self._ce_splits(w.N)
+            call("seqrec_ce_forward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
+                 ptr(w.tgt) if with_targets else None, ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy), w.N, self.H, self.V, 0,
+                 self.V, self.V, n_splits, 0, st)
         call("seqrec_ce_finalize", ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
-             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, w.splits, st)
+             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, st)
         self._mark("misc")
+
+    def _backward_ce(self, w):
+        st = self.stream
+        if w.tc["bwd"]:
+            call("seqrec_ce_tc_backward", ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), ptr(self.Bt_hi),
+                 ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(w.tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
+                 ptr(self.inv_nvalid), ptr(w.hscale), ptr(w.dh), ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
+                 self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, st)
+        else:
+            call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
+                 ptr(w.m), ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out),
+                 w.N, self.H, self.V, 0, self.V, self.V, 0, 0, st)
 
     # ------------------------------------------------------------------------------------------------ public steps
     def loss_batch(self, ids, tgt, x_dense=None):
@@ -302,7 +385,7 @@ class HotPath:
         comm.all_reduce_sum(n_valid)
         torch.reciprocal(n_valid, out=self.inv_nvalid)
         self._forward_hidden(w, training=True)
-        self._forward_ce(w)
+        self._forward_ce(w, training=True)
         loss_sum = w.loss_sum
         comm.all_reduce_sum(loss_sum)
         loss = loss_sum * self.inv_nvalid
@@ -310,9 +393,7 @@ class HotPath:
         # ---- backward
         self.flat_g.zero_()
         self._mark("ce_bwd")
-        call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt), ptr(w.m),
-             ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out), w.N, self.H,
-             self.V, 0, self.V, self.V, 0, 0, st)
+        self._backward_ce(w)
         self._mark("rnn_bwd")
         call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
         call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),
@@ -353,6 +434,7 @@ class HotPath:
         # ---- global-norm clip + Adagrad
         self._mark("optim")
         self._apply_update(w)
+        self._w_version += 1
         self._mark("end")
         return loss
 
@@ -416,12 +498,10 @@ class HotPath:
         self.comm.all_reduce_sum(n_valid)
         torch.reciprocal(n_valid, out=self.inv_nvalid)
         self._forward_hidden(w, training=True)
-        self._forward_ce(w)
+        self._forward_ce(w, training=True)
         loss = (w.loss_sum * self.inv_nvalid).clone()
         self.flat_g.zero_()
-        call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt), ptr(w.m),
-             ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out), w.N, self.H,
-             self.V, 0, self.V, self.V, 0, 0, st)
+        self._backward_ce(w)
         dh = w.dh.clone()
         call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
         call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),

@@ -155,6 +155,7 @@ class _Net(object):
         if tuple(v.shape) != tuple(t.shape):
             raise ValueError("weight %s: shape %s does not match %s" % (name, v.shape, tuple(t.shape)))
         t.copy_(torch.from_numpy(np.ascontiguousarray(v)))
+        self.hot._w_version += 1
 
     def get_weights(self):
         return [self._get(n) for n in self._names()]
