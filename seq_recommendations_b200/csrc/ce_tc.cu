@@ -9,8 +9,9 @@
 //   * "fp32 mode" = 3-pass split products  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  with hi = bf16(x), lo = bf16(x - hi)
 //     (16 mantissa bits per operand, ~2^-16 relative per product -- inside the 1e-4 budget of north_star);
 //     "bf16 mode" issues the hi.hi product only
-//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
-//     (tcgen05.ld 32x32b: one thread owns one token row -> row-wise softmax statistics need no shuffles)
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue: two warps per
+//     TMEM lane quadrant, each owning one 64-column half of the tile (tcgen05.ld 32x32b: one thread owns one token
+//     row -> row-wise softmax statistics need no shuffles; the two halves are merged like two vocabulary splits)
 //   * the logits tile never leaves the SM: forward keeps a running (max, sum-exp) per row; backward turns the tile
 //     into dlogit = (p - onehot)*coef in registers, writes it as a bf16 hi/lo K-major operand into shared memory and
 //     feeds it straight back to the tensor core (dH += dS.W^T  /  dW += H^T.dS).
@@ -25,7 +26,8 @@ constexpr int BM = 128;          // tokens per tile (UMMA M)
 constexpr int BN = 128;          // items per tile  (UMMA N of the logits GEMM)
 constexpr int KBLK = 64;         // bf16 elements per 128-byte swizzled row
 constexpr int TILE_B = 128 * 128;  // bytes of one [128 rows x 64 bf16] operand block
-constexpr int TC_THREADS = 192;  // 6 warps
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int N_EPI_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- host: TMA descriptors --------------------------------------------------------------------------------------
@@ -104,12 +106,85 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
   return (uint32_t)(blk * rows * 128 + row * 128 + ((((c >> 3) ^ (row & 7)) << 4) | ((c & 7) << 1)));
 }
 
+// ---- epilogue helpers (each epilogue warp owns 32 rows x 64 columns of a 128 x 128 logits tile) -------------------
+// load the warp's 64 accumulator columns (two 32-column tcgen05.ld in flight, one wait)
+__device__ __forceinline__ void load_half_tile(uint32_t taddr, float (&z)[64]) {
+  uint32_t r0[32], r1[32];
+  ptx::tmem_ld_32x32(taddr, r0);
+  ptx::tmem_ld_32x32(taddr + 32, r1);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { z[j] = __uint_as_float(r0[j]); z[32 + j] = __uint_as_float(r1[j]); }
+}
+
+// per-row softmax terms of the backward kernels.  Rows without gradient (pad, clip-saturated) get nb = -inf,
+// scale = 0: exp2(z*log2e - inf) = 0 exactly, so no branch and no inf*0.
+struct RowTerms {
+  float nb;      // -m * log2(e)
+  float scale;   // coef * inv_nvalid / s
+  float cf;      // coef * inv_nvalid
+  int32_t tg;    // target item (or -1)
+};
+__device__ __forceinline__ RowTerms load_row_terms(int64_t n, int64_t n_tokens, const float* __restrict__ mrow,
+                                                   const float* __restrict__ srow, const float* __restrict__ coef,
+                                                   const int32_t* __restrict__ tgt, float inv) {
+  RowTerms rt;
+  rt.nb = -INFINITY; rt.scale = 0.f; rt.cf = 0.f; rt.tg = -1;
+  if (n < n_tokens) {
+    const float cf = coef[n] * inv;
+    if (cf != 0.f) {
+      rt.cf = cf;
+      rt.nb = -mrow[n] * LOG2E;
+      rt.scale = cf / srow[n];
+      rt.tg = tgt[n];
+    }
+  }
+  return rt;
+}
+
+// z (raw logits of 64 consecutive items starting at item vcol0) -> dlogit in place
+__device__ __forceinline__ void dlogit_half_tile(float (&z)[64], const RowTerms& rt, int vcol0, int v_end) {
+#pragma unroll
+  for (int j = 0; j < 64; ++j) z[j] = ptx::ex2_approx(fmaf(z[j], LOG2E, rt.nb)) * rt.scale;
+  if (vcol0 + 64 > v_end) {  // ragged last tile (warp-uniform): items beyond the vocabulary carry no gradient
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (vcol0 + j >= v_end) z[j] = 0.f;
+  }
+  const int tj = rt.tg - vcol0;
+  if (tj >= 0 && tj < 64) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (j == tj) z[j] -= rt.cf;
+  }
+}
+
+// write this thread's row of 64 dlogits as bf16 hi (and lo) into the swizzled operand block `blk` (rows of 128 B)
+template <bool X3>
+__device__ __forceinline__ void store_dlogit_row(uint8_t* sD_gen, const float (&d)[64], int row, int blk,
+                                                 int lo_offset_bytes) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = d[g * 8 + 2 * e], x1 = d[g * 8 + 2 * e + 1];
+      const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
+      if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
+    }
+    const uint32_t off = (uint32_t)(blk * TILE_B + row * 128 + ((g ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(sD_gen + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (X3) *reinterpret_cast<uint4*>(sD_gen + lo_offset_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ================================================================================================================
 // forward: per-row running (max, sum-exp) of logits = A . Bt^T over this CTA's item tiles
 //   A  = hout (optionally x dropout factors), [N, Hk] bf16 hi/lo     (tmA_*,  box 64 x 128)
 //   Bt = W_out^T,                            [V, Hk] bf16 hi/lo     (tmB_*,  box 64 x 128)
 // grid = (token tiles, splits).  smem: A resident (KB blocks), Bt streamed in 64-wide K blocks through NS stages.
-template <int KB, int NS, bool X3>
+template <int KB, int NS, bool X3, bool BIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -132,7 +207,7 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
     ptx::fence_barrier_init();
   }
@@ -194,54 +269,55 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;            // which 64-column half of the tile this warp owns
     const int row = q * 32 + lane;
     const int64_t n = (int64_t)row0 + row;
     float m = -INFINITY, s = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int v0 = v_begin + (vt0 + t) * BN;
+      const int vc0 = v_begin + (vt0 + t) * BN + half * 64;      // first item of this warp's columns
       ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-      const bool ragged = v0 + BN > v_end;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == BN / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-        }
-        float z[32];
-        float cmax = -INFINITY;
+      float z[64];
+      load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();               // accumulator read: hand the TMEM buffer back to the MMA warp
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      if (BIAS || vc0 + 64 > v_end) {            // warp-uniform slow path: output bias and the ragged last tile
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int v = v0 + c * 32 + j;
-          float x = __uint_as_float(r[j]);
-          if (b_out) x += (v < v_end) ? __ldg(b_out + v) : 0.f;
-          if (ragged && v >= v_end) x = -INFINITY;
-          z[j] = x;
-          cmax = fmaxf(cmax, x);
-        }
-        if (cmax > -INFINITY) {
-          const float mn = fmaxf(m, cmax);
-          const float nb = -mn * LOG2E;
-          float add = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) add += exp2f(fmaf(z[j], LOG2E, nb));
-          s = s * exp2f(fmaf(m, LOG2E, nb)) + add;
-          m = mn;
+        for (int j = 0; j < 64; ++j) {
+          const int v = vc0 + j;
+          if (v < v_end) { if (BIAS) z[j] += __ldg(b_out + v); }
+          else z[j] = -INFINITY;
         }
       }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        mx[0] = fmaxf(mx[0], z[j]); mx[1] = fmaxf(mx[1], z[j + 1]);
+        mx[2] = fmaxf(mx[2], z[j + 2]); mx[3] = fmaxf(mx[3], z[j + 3]);
+      }
+      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (cmax > -INFINITY) {
+        const float mn = fmaxf(m, cmax);
+        const float nb = -mn * LOG2E;
+        float add[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          add[0] += ptx::ex2_approx(fmaf(z[j], LOG2E, nb));
+          add[1] += ptx::ex2_approx(fmaf(z[j + 1], LOG2E, nb));
+          add[2] += ptx::ex2_approx(fmaf(z[j + 2], LOG2E, nb));
+          add[3] += ptx::ex2_approx(fmaf(z[j + 3], LOG2E, nb));
+        }
+        s = s * ptx::ex2_approx(fmaf(m, LOG2E, nb)) + ((add[0] + add[1]) + (add[2] + add[3]));
+        m = mn;
+      }
     }
-    if (n < n_tokens && n_tiles > 0) {
-      ws_m[(int64_t)blockIdx.y * n_tokens + n] = m;
-      ws_s[(int64_t)blockIdx.y * n_tokens + n] = s;
-    } else if (n < n_tokens) {
-      ws_m[(int64_t)blockIdx.y * n_tokens + n] = -INFINITY;
-      ws_s[(int64_t)blockIdx.y * n_tokens + n] = 0.f;
+    // each (split, half) pair is one partial of the vocabulary reduction merged by seqrec_ce_finalize
+    if (n < n_tokens) {
+      const int64_t slot = ((int64_t)blockIdx.y * 2 + half) * n_tokens + n;
+      ws_m[slot] = m;
+      ws_s[slot] = s;
     }
   }
   ptx::tc_fence_before_sync();
@@ -249,35 +325,6 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   if (warp == 1) {
     __syncwarp();
     ptx::tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// per-row softmax terms shared by the two backward kernels
-struct RowTerms {
-  float nb;      // -m * log2(e)
-  float inv_s;   // 1 / s
-  float cf;      // coef * inv_nvalid (0 for masked / clip-saturated tokens)
-  int32_t tg;    // target item (or -1)
-};
-
-// dlogit for 32 consecutive items of one row, from the raw fp32 accumulator chunk
-__device__ __forceinline__ void dlogit_chunk(const uint32_t (&r)[32], const RowTerms& rt, int vcol0, int v_end,
-                                             float (&d)[32]) {
-  if (rt.cf == 0.f) {  // masked or clip-saturated token: no gradient (and no inf*0 from an unscaled exp)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) d[j] = 0.f;
-    return;
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float p = exp2f(fmaf(__uint_as_float(r[j]), LOG2E, rt.nb)) * rt.inv_s;
-    d[j] = (vcol0 + j < v_end) ? p * rt.cf : 0.f;
-  }
-  const int tj = rt.tg - vcol0;
-  if (tj >= 0 && tj < 32) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j == tj) d[j] -= rt.cf;
   }
 }
 
@@ -314,9 +361,9 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
-    ptx::mbar_init(bar_dfull, 4);
+    ptx::mbar_init(bar_dfull, N_EPI_WARPS);
     ptx::mbar_init(bar_dempty, 1);
     ptx::mbar_init(bar_hfull, 1);
     ptx::fence_barrier_init();
@@ -414,69 +461,41 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int64_t n = (int64_t)row0 + row;
-    RowTerms rt;
-    {
-      const bool ok = n < n_tokens;
-      const float cf = ok ? coef[n] * inv_nvalid[0] : 0.f;
-      rt.cf = cf;
-      rt.nb = (ok && cf != 0.f) ? -mrow[n] * LOG2E : 0.f;
-      rt.inv_s = (ok && cf != 0.f) ? 1.0f / srow[n] : 0.f;
-      rt.tg = (ok && cf != 0.f) ? tgt[n] : -1;
-    }
+    const RowTerms rt = load_row_terms(n, n_tokens, mrow, srow, coef, tgt, inv_nvalid[0]);
     uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int v0 = v_begin + t * BN;
+      const int vc0 = v_begin + t * BN + half * 64;
       ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-        }
-        float d[32];
-        dlogit_chunk(r, rt, v0 + c * 32, v_end, d);
-        if (c == 0) ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);   // previous tile's dH MMAs are done with the buffer
-        // 32 consecutive items = 4 sixteen-byte chunks of this row, hi and lo parts
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x0 = d[g * 8 + 2 * e], x1 = d[g * 8 + 2 * e + 1];
-            const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
-            hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
-            if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
-          }
-          const uint32_t off = sw128_offset(row, c * 32 + g * 8, BM);
-          *reinterpret_cast<uint4*>(sD_gen + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (X3) *reinterpret_cast<uint4*>(sD_gen + NJ * TILE_B + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
-      ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      float z[64];
+      load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      dlogit_half_tile(z, rt, vc0, v_end);
+      ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);     // previous tile's dH MMAs are done with the dS buffer
+      store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);
+      ptx::fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dfull);
     }
-    // final: dH accumulator -> global (fp32), optionally times the dropout factors
+    // final: dH accumulator -> global (fp32), optionally times the dropout factors; this warp owns HK/2 columns
     ptx::mbar_wait(bar_hfull, 0);
     ptx::tc_fence_after_sync();
 #pragma unroll 1
-    for (int c = 0; c < HK / 32; ++c) {
+    for (int c = 0; c < HK / 64; ++c) {
+      const int h0 = half * (HK / 2) + c * 32;
       uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_dh + ((uint32_t)(q * 32) << 16) + c * 32, r);
+      ptx::tmem_ld_32x32(tmem_dh + ((uint32_t)(q * 32) << 16) + h0, r);
       ptx::tmem_ld_wait();
       if (n < n_tokens) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int h = c * 32 + j;
+          const int h = h0 + j;
           if (h < H) {
             float x = __uint_as_float(r[j]);
             if (hscale) x *= hscale[n * H + h];
@@ -497,8 +516,9 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
 // ================================================================================================================
 // backward, item-stationary: dW_out[:, v] += sum_n hs[n,:] * dlogit[n,v]
-//   Bt tile resident.  Per token tile:  S = A.Bt^T -> epilogue writes dS TRANSPOSED (rows = items, K = tokens) ->
-//   dW (TMEM [Hk x 128 items]) += Ht . dS^T with Ht = hs^T [Hk, Np] bf16 hi/lo (box 64 tokens x Hk).
+//   Bt tile resident.  Per token tile:  S = A.Bt^T -> epilogue writes dS row-wise (rows = tokens, like the dH kernel) ->
+//   dW (TMEM [128 x 128 items]) += Ht . dS with Ht = hs^T [Hk, Np] bf16 hi/lo (K-major, box 64 tokens x 128 rows) and
+//   dS read back as an MN-major B operand (K = tokens runs down the rows).
 // grid = (item tiles, token splits); the fp32 result leaves through vector reductions into a pre-zeroed dW_out.
 template <int KB, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -530,9 +550,9 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
-    ptx::mbar_init(bar_dfull, 4);
+    ptx::mbar_init(bar_dfull, N_EPI_WARPS);
     ptx::mbar_init(bar_dempty, 1);
     ptx::mbar_init(bar_hfull, 1);
     ptx::fence_barrier_init();
@@ -590,7 +610,9 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0 && n_tiles > 0) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
-      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16(128, BN);  // M = hidden (padded to 128), N = items, K = tokens
+      // dW GEMM: M = hidden (padded to 128), N = items, K = tokens.  A = Ht block (K-major, from TMA); B = dS exactly
+      // as the epilogue wrote it (rows = tokens = K, 64 items per 128-byte row) read as an MN-major operand.
+      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_bmn(128, BN);
       ptx::mbar_wait(bar_a, 0);
       ptx::tc_fence_after_sync();
       Pipe p;
@@ -618,7 +640,22 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
           ptx::tc_fence_after_sync();
           const uint32_t a = sB + p.stage * NP * TILE_B;     // Ht block: rows = hidden, K = 64 tokens
-          mma_kblock<X3>(tmem_dw, a, a + TILE_B, sD + j * TILE_B, sD + (NJ + j) * TILE_B, idesc_w, t == 0 && j == 0);
+          const uint64_t da_hi = ptx::umma_desc_k_sw128(a), da_lo = ptx::umma_desc_k_sw128(a + TILE_B);
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k) {
+            // 16 tokens = 16 rows of 128 B further down the dS image; its two 64-item blocks are TILE_B apart (LBO)
+            const uint32_t boff = (uint32_t)(j * KBLK + k * 16) * 128;
+            const uint64_t db_hi = ptx::umma_desc_mn_sw128(sD + boff, TILE_B);
+            const uint64_t db_lo = ptx::umma_desc_mn_sw128(sD + NJ * TILE_B + boff, TILE_B);
+            const uint32_t first = (t == 0 && j == 0 && k == 0) ? 0u : 1u;
+            if (X3) {
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, first);
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_lo, k * 16), db_hi, idesc_w, 1u);
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, 1u);
+            } else {
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, first);
+            }
+          }
           ptx::umma_commit(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
@@ -629,66 +666,45 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
     const float inv = inv_nvalid[0];
+    const int vc0 = v0 + half * 64;
+    RowTerms rt_next = load_row_terms(tt0 * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
-      const int64_t n = (tt0 + t) * BM + row;
-      RowTerms rt;
-      {
-        const bool ok = n < n_tokens;
-        const float cf = ok ? coef[n] * inv : 0.f;
-        rt.cf = cf;
-        rt.nb = (ok && cf != 0.f) ? -mrow[n] * LOG2E : 0.f;
-        rt.inv_s = (ok && cf != 0.f) ? 1.0f / srow[n] : 0.f;
-        rt.tg = (ok && cf != 0.f) ? tgt[n] : -1;
-      }
+      const RowTerms rt = rt_next;
+      if (t + 1 < n_tiles)                        // prefetch the next tile's row terms behind this tile's math
+        rt_next = load_row_terms((tt0 + t + 1) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
       ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-        }
-        float d[32];
-        dlogit_chunk(r, rt, v0 + c * 32, v_end, d);
-        if (c == 0) ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);
-        // transposed store: operand row = item (c*32+j), K index = this thread's token row
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const __nv_bfloat16 hv = __float2bfloat16_rn(d[j]);
-          const uint32_t off = sw128_offset(c * 32 + j, row, BN);
-          *reinterpret_cast<__nv_bfloat16*>(sD_gen + off) = hv;
-          if (X3)
-            *reinterpret_cast<__nv_bfloat16*>(sD_gen + NJ * TILE_B + off) =
-                __float2bfloat16_rn(d[j] - __bfloat162float(hv));
-        }
-      }
+      float z[64];
+      load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      dlogit_half_tile(z, rt, vc0, v_end);
+      ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);
+      store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);   // rows = tokens; consumed MN-major by the dW GEMM
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dfull);
     }
     if (n_tiles > 0) {
-      // final: dW accumulator rows = hidden unit, columns = items of this tile -> reductions into dW_out (H, ldw)
+      // final: dW accumulator rows = hidden unit, this warp's 64 item columns -> reductions into dW_out (H, ldw)
       ptx::mbar_wait(bar_hfull, 0);
       ptx::tc_fence_after_sync();
       const int h = row;
       const bool vec_ok = (ldw & 3) == 0 && (v_begin & 3) == 0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_dw + ((uint32_t)(q * 32) << 16) + c * 32, r);
+        ptx::tmem_ld_32x32(tmem_dw + ((uint32_t)(q * 32) << 16) + half * 64 + c * 32, r);
         ptx::tmem_ld_wait();
-        if (h < H && h < HK) {
-          float* dst = dW + (size_t)h * ldw + v0 + c * 32;
-          const int valid = min(32, v_end - (v0 + c * 32));
+        if (h < H) {
+          float* dst = dW + (size_t)h * ldw + vc0 + c * 32;
+          const int valid = min(32, v_end - (vc0 + c * 32));
           if (vec_ok && valid == 32) {
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -731,13 +747,13 @@ target_logit_kernel(const float* __restrict__ hout, const float* __restrict__ hs
   if (lane == 0) zy[n] = acc + (b_out ? b_out[t] : 0.f);
 }
 
-template <int KB, int NS, bool X3>
+template <int KB, int NS, bool X3, bool BIAS>
 int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end, int splits,
                cudaStream_t st) {
   constexpr int NP = X3 ? 2 : 1;
   const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NS * NP * TILE_B + 256;
-  auto k = ce_tc_forward_kernel<KB, NS, X3>;
+  auto k = ce_tc_forward_kernel<KB, NS, X3, BIAS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   const int n_vtiles = ceil_div(v_end - v_begin, BN);
@@ -774,17 +790,20 @@ extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, 
   if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   cudaStream_t st = as_stream(stream);
-#define FWD(KB, NS)                                                                                                 \
-  return x3 ? launch_fwd<KB, NS, true>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, splits, \
-                                       st)                                                                          \
-            : launch_fwd<KB, NS, false>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end,        \
-                                        splits, st)
-  switch (Hk / KBLK) {
-    case 1: FWD(1, 4);
-    case 2: FWD(2, 4);
-    case 3: FWD(3, 3);
-    default: FWD(4, 3);
+#define FWD2(KB, NS, X3V, BV)                                                                                  \
+  return launch_fwd<KB, NS, X3V, BV>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, splits, st)
+#define FWD(KB, NS)                                          \
+  {                                                          \
+    if (x3) { if (b_out) FWD2(KB, NS, true, true); else FWD2(KB, NS, true, false); }     \
+    else    { if (b_out) FWD2(KB, NS, false, true); else FWD2(KB, NS, false, false); }   \
   }
+  switch (Hk / KBLK) {
+    case 1: FWD(1, 4)
+    case 2: FWD(2, 4)
+    case 3: FWD(3, 3)
+    default: FWD(4, 3)
+  }
+#undef FWD2
 #undef FWD
 }
 

@@ -107,6 +107,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major bf16 operand with the same byte image: rows of 128 B hold 64 consecutive M/N elements, consecutive rows
+// are consecutive K indices, 8-row groups are 1024 B apart (SBO), 64-element M/N blocks are `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // advance along K by `elems` bf16 inside the 128-byte swizzle atom: +elems*2 bytes on the start address field
 __device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t desc, int elems) {
   return desc + (uint64_t)((elems * 2) >> 4);
@@ -114,6 +125,13 @@ __device__ __forceinline__ uint64_t umma_desc_advance_k(uint64_t desc, int elems
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N tile
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same, B operand MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 16); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 // D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

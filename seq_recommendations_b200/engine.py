@@ -75,8 +75,8 @@ class _Work:
             if self.tc["bwd"]:
                 self.Ht_hi = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev)
                 self.Ht_lo = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev) if hp.tc_x3 else None
-            if self.tc["splits"] > self.splits:
-                self.splits = self.tc["splits"]
+            if 2 * self.tc["splits"] > self.splits:       # every CTA emits two partials (one per 64-column half)
+                self.splits = 2 * self.tc["splits"]
                 self.ws_m = torch.empty((self.splits, N), dtype=f32, device=dev)
                 self.ws_s = torch.empty((self.splits, N), dtype=f32, device=dev)
         # pinned staging for host batches
@@ -337,7 +337,7 @@ class HotPath:
                      ptr(w.zy), w.N, self.H, self.V, st)
             call("seqrec_ce_tc_forward", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out),
                  ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, w.tc["splits"], 1 if self.tc_x3 else 0, st)
-            n_splits = w.tc["splits"]
+            n_splits = 2 * w.tc["splits"]
         else:
             self._mark("ce_fwd")
             n_splits = self._ce_splits(w.N)
