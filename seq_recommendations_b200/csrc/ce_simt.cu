@@ -156,14 +156,25 @@ ce_forward_simt_kernel(const float* __restrict__ hout, const float* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------------
 // finalize: merge the per-split stats, CE with Keras' clip, per-token backward coefficient, deterministic loss sum
-__global__ void __launch_bounds__(1024)
+// (per-block partials in a fixed order; the last block to finish adds them up in block order)
+#define FIN_THREADS 256
+#define FIN_MAX_BLOCKS 256
+__device__ double g_fin_partials[FIN_MAX_BLOCKS];
+__device__ unsigned int g_fin_counter = 0;
+
+__global__ void __launch_bounds__(FIN_THREADS)
 ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_s, const float* __restrict__ zy,
                    const uint8_t* __restrict__ mask, float* __restrict__ m_out, float* __restrict__ s_out,
                    float* __restrict__ ce, float* __restrict__ py, float* __restrict__ coef,
                    float* __restrict__ loss_sum, int64_t n_tokens, int splits) {
-  __shared__ double red[32];
+  __shared__ double red[FIN_THREADS / 32];
+  __shared__ bool is_last;
   double local = 0.0;
-  for (int64_t n = threadIdx.x; n < n_tokens; n += blockDim.x) {
+  // fixed token -> (block, thread) assignment, so every partial is reproducible
+  const int64_t per_block = (n_tokens + gridDim.x - 1) / gridDim.x;
+  const int64_t n_begin = blockIdx.x * per_block;
+  const int64_t n_end = min(n_tokens, n_begin + per_block);
+  for (int64_t n = n_begin + threadIdx.x; n < n_end; n += FIN_THREADS) {
     float m = ws_m[n], s = ws_s[n];
     for (int k = 1; k < splits; ++k) merge_ms(m, s, ws_m[(int64_t)k * n_tokens + n], ws_s[(int64_t)k * n_tokens + n]);
     m_out[n] = m;
@@ -186,10 +197,21 @@ ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_
   local = warp_sum_d(local);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
-    v = warp_sum_d(v);
-    if (threadIdx.x == 0 && loss_sum) loss_sum[0] = (float)v;
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int i = 0; i < FIN_THREADS / 32; ++i) v += red[i];
+    g_fin_partials[blockIdx.x] = v;
+    __threadfence();
+    const unsigned int done = atomicAdd(&g_fin_counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) v += *((volatile double*)&g_fin_partials[i]);
+    if (loss_sum) loss_sum[0] = (float)v;
+    g_fin_counter = 0;  // ready for the next (stream-ordered) launch
   }
 }
 
@@ -486,8 +508,10 @@ extern "C" int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const fl
                                   float* m_out, float* s_out, float* ce, float* py, float* coef, float* loss_sum,
                                   int64_t n_tokens, int splits, void* stream) {
   SEQREC_ARG(n_tokens > 0 && splits > 0, 1);
-  ce_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef, loss_sum,
-                                                        n_tokens, splits);
+  int blocks = (int)((n_tokens + 4 * FIN_THREADS - 1) / (4 * FIN_THREADS));
+  if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
+  ce_finalize_kernel<<<blocks, FIN_THREADS, 0, as_stream(stream)>>>(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef,
+                                                                   loss_sum, n_tokens, splits);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }

@@ -343,7 +343,7 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
                          float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end, int accumulate) {
   constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = 2;
+  constexpr int NS = X3 ? 3 : 6;                          // 32 KB (x3) / 16 KB stages: fills the 227 KB budget
   constexpr int HK = KB * KBLK;
   constexpr int NJ = BN / KBLK;                             // 64-item blocks per tile (K blocks of the dH GEMM)
   extern __shared__ uint8_t smem_raw[];
@@ -530,7 +530,7 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                          const float* __restrict__ inv_nvalid, float* __restrict__ dW, int64_t n_tokens, int H,
                          int v_begin, int v_end, int ldw, int tiles_per_split) {
   constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = 2;
+  constexpr int NS = X3 ? 3 : 6;                          // 32 KB (x3) / 16 KB stages: fills the 227 KB budget
   constexpr int HK = KB * KBLK;
   constexpr int NJ = BM / KBLK;                             // 64-token blocks per tile (K blocks of the dW GEMM)
   extern __shared__ uint8_t smem_raw[];
@@ -826,7 +826,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
-  const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)2 * NP * TILE_B + 256;
+  const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)(x3 ? 3 : 6) * NP * TILE_B + 256;
   if (dh) {
     if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, Hk))) return rc;
     if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, Hk))) return rc;
