@@ -1,0 +1,72 @@
+"""Worker of tests/test_gpu_dp.py: run under torchrun (one process per GPU, NCCL).  Every rank trains on its shard of a
+global batch through HotPath(comm=...); rank 0 also trains a single-GPU replica on the WHOLE batch and the two must end
+with the same weights (1-GPU vs N-GPU equality of the global-batch step)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from seq_recommendations_b200 import dist, synthetic  # noqa: E402
+from seq_recommendations_b200.engine import HotPath  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def main():
+    comm = dist.init_from_env("nccl")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    ok = True
+    # (V, H, T, B_global, cell): dense dW_in exchange (small V) and row exchange (V*GH > N*GH), TC and SIMT logits
+    # (100, ...) and (300, ... B=512) take the dense dW_in all-reduce (V <= N_global); the others the row exchange
+    for V, H, T, B, cell, tc in ((900, 64, 10, 64, "GRU", "x3"), (60000, 32, 4, 48, "LSTM", "off"),
+                                 (100, 32, 6, 30, "GRU", "off"), (300, 64, 8, 512, "GRU", "x3")):
+        act = "tanh" if cell == "GRU" else "relu"
+        ws = synthetic.make_weights(cell, V, H, seed=3)
+        steps = [synthetic.make_batch(V, T, B, seed=50 + s, min_len=1) for s in range(3)]
+        hot = HotPath(cell, act, V, H, V, weights=ws, comm=comm, tc=tc)
+        hot.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
+        lo, hi = dist.shard_rows(B, comm.rank, comm.world)
+        losses = [float(hot.train_batch(i[lo:hi], t[lo:hi]).item()) for i, t in steps]
+        mine = hot.get_weights()
+        if comm.rank == 0:
+            solo = dist.Comm.__new__(dist.Comm)
+            solo.enabled, solo.group, solo.rank, solo.world = False, None, 0, 1
+            ref = HotPath(cell, act, V, H, V, weights=ws, comm=solo, tc=tc)
+            ref.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
+            ref_losses = [float(ref.train_batch(i, t).item()) for i, t in steps]
+            errs = [rel(a, b) for a, b in zip(mine, ref.get_weights())]
+            lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+            good = max(errs) < 2e-5 and lerr < 1e-5
+            print("DP world=%d V=%d %s tc=%s: loss err %.2e, weight errs %s -> %s" % (
+                comm.world, V, cell, tc, lerr, ["%.1e" % e for e in errs], "OK" if good else "MISMATCH"), flush=True)
+            ok = ok and good
+        # all ranks must hold identical replicas after the step
+        flat = torch.cat([torch.from_numpy(w).reshape(-1) for w in mine]).to(dev)
+        mx = flat.clone()
+        mn = flat.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(mn, op=torch.distributed.ReduceOp.MIN)
+        # Replicas: the dense exchange gives bit-identical updates on every rank.  The row exchange scatter-adds the
+        # gathered rows with atomics in a rank-local order, so replicas may differ in the last bits (bounded here).
+        from seq_recommendations_b200.dist import embedding_grad_mode
+        G = {"GRU": 3, "LSTM": 4}[cell]
+        dense = embedding_grad_mode(V, G * H, T * (hi - lo) * comm.world) == "dense"
+        spread = float(((mx - mn).abs().max() / flat.abs().max()).item())
+        if (dense and spread != 0.0) or spread > 1e-6:
+            print("rank %d: replicas diverged (dense=%s, spread %.2e)" % (comm.rank, dense, spread), flush=True)
+            ok = False
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    comm.barrier()
+    torch.distributed.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
