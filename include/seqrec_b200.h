@@ -71,9 +71,12 @@ int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8
 
 /* ---- K4: recurrent scan backward (Theano scan gradient) ----------------------------------------------------------
  * dhout [T][B][H] = dLoss/dHout.  xg: in = saved gates, out = dxp (pre-activation gradients, in place).
- * Ut = U^T (G*H, H).  For GRU, cst receives r*h_{t-1} (operand of dU's candidate block). */
-int seqrec_rnn_backward(int cell, int act, float* xg, const float* Ut, const uint8_t* mask, const float* hout,
-                        float* cst, const float* dhout, int T, int B, int H, void* stream);
+ * U (H, G*H) and Ut = U^T (G*H, H).  For GRU, cst receives r*h_{t-1} (operand of dU's candidate block). */
+int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const float* Ut, const uint8_t* mask,
+                        const float* hout, float* cst, const float* dhout, int T, int B, int H, void* stream);
+/* 1 when seqrec_rnn_backward reads Ut for this (cell, H); 0 when the register-resident scan (GRU / SimpleRNN with
+ * H <= 128, U held in registers for all T steps) serves it from U and Ut may be NULL */
+int seqrec_rnn_needs_ut(int cell, int H);
 /* dU (H,G*H) += sum_t hprev_t^T . dxp_t (GRU candidate block uses cst = r*hprev);  db (G*H) += sum_n dxp[n,:].
  * dU and db must be pre-zeroed. */
 int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,
@@ -112,11 +115,16 @@ int seqrec_ce_backward(const float* hout, const float* hscale, const float* W_ou
  *   Bt = W_out^T       (V, Hk)
  *   W  = W_out         (Hk, Vp)  Vp = V padded to a multiple of 8
  * x3 != 0 selects the 3-pass split product (fp32-grade, ~2^-16 relative); forward supports Hk <= 256, backward
- * Hk <= 128 and no output bias.  ws_m / ws_s as in seqrec_ce_forward; the target logit comes from
+ * Hk <= 128 and no output bias.  dh is overwritten unless accumulate_dh != 0; dW_out must be pre-zeroed (both leave
+ * the SM through vector reductions).  ws_m / ws_s as in seqrec_ce_forward; the target logit comes from
  * seqrec_target_logit (exact fp32 dot product). */
 int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
                          const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int Hk, int V, int v_begin,
-                         int v_end, int splits, int x3, void* stream);
+                         int v_end, int x3, void* stream);
+/* rows of ws_m / ws_s (partials per token) seqrec_ce_tc_forward writes for this problem size: the kernels run as a
+ * persistent grid whose CTAs own balanced contiguous runs of (token tile, item tile) pairs, so a token tile's
+ * vocabulary reduction is split over a few CTAs; pass the value as `splits` to seqrec_ce_finalize */
+int seqrec_ce_tc_partials(int64_t n_tokens, int v_begin, int v_end);
 int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Ht_hi, const uint16_t* Ht_lo,
                           const uint16_t* Bt_hi, const uint16_t* Bt_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                           const int32_t* tgt, const float* m, const float* s, const float* coef,

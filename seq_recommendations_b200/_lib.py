@@ -29,13 +29,15 @@ SIGNATURES = {
     "seqrec_gemm_nn": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "seqrec_gemm_tn_atomic": [_p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_forward": [_i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "seqrec_rnn_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_needs_ut": [_i, _i],
     "seqrec_rnn_weight_grad": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_transpose": [_p, _p, _i, _i, _p],
     "seqrec_ce_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_finalize": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
     "seqrec_ce_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
-    "seqrec_ce_tc_forward": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "seqrec_ce_tc_forward": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "seqrec_ce_tc_partials": [_l, _i, _i],
     "seqrec_ce_tc_backward": [_p] * 16 + [_l, _i, _i, _i, _i, _l, _i, _i, _i, _i, _i, _p],
     "seqrec_target_logit": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_predict_probs": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -179,17 +179,39 @@ __device__ __forceinline__ void store_dlogit_row(uint8_t* sD_gen, const float (&
   }
 }
 
+// ---- persistent work partition ------------------------------------------------------------------------------------
+// The (outer, inner) tile pairs are numbered w = outer * n_inner + inner; CTA c of G owns the contiguous range
+// [total*c/G, total*(c+1)/G) (balanced to +-1 tile, "stream-K" style).  A maximal run of tiles with the same `outer`
+// inside a CTA's range is a SEGMENT: the stationary operand is loaded once per segment and the per-segment result
+// (softmax partial, dH or dW accumulator) is flushed at its end.
+struct Share {
+  int64_t w0, w1;
+  int n_inner;
+  __device__ __forceinline__ Share(int64_t total, int n_inner_) : n_inner(n_inner_) {
+    w0 = total * blockIdx.x / gridDim.x;
+    w1 = total * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ __forceinline__ int outer(int64_t w) const { return (int)(w / n_inner); }
+  __device__ __forceinline__ int inner(int64_t w) const { return (int)(w % n_inner); }
+  __device__ __forceinline__ bool seg_first(int64_t w) const { return w == w0 || inner(w) == 0; }
+  __device__ __forceinline__ bool seg_last(int64_t w) const { return w + 1 == w1 || inner(w) == n_inner - 1; }
+};
+// CTA that owns work item w
+__device__ __forceinline__ int cta_of(int64_t w, int64_t total) { return (int)(((w + 1) * gridDim.x - 1) / total); }
+
 // ================================================================================================================
-// forward: per-row running (max, sum-exp) of logits = A . Bt^T over this CTA's item tiles
+// forward: per-row (max, sum-exp) partials of logits = A . Bt^T
 //   A  = hout (optionally x dropout factors), [N, Hk] bf16 hi/lo     (tmA_*,  box 64 x 128)
 //   Bt = W_out^T,                            [V, Hk] bf16 hi/lo     (tmB_*,  box 64 x 128)
-// grid = (token tiles, splits).  smem: A resident (KB blocks), Bt streamed in 64-wide K blocks through NS stages.
+// outer = token tile (A resident per segment), inner = item tile (Bt streamed in 64-wide K blocks, NS stages).
+// Every segment writes one partial per 64-column half into ws[(slot*2 + half)][n], slot = position of the CTA among
+// the CTAs sharing that token tile; slots a token tile does not use are filled with (-inf, 0).
 template <int KB, int NS, bool X3, bool BIAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                      const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
-                     int64_t n_tokens, int v_begin, int v_end, int tiles_per_split) {
+                     int64_t n_tokens, int v_begin, int v_end, int max_slots) {
   constexpr int NP = X3 ? 2 : 1;  // operand parts (hi, lo)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -197,18 +219,18 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   const uint32_t sB = sA + NP * KB * TILE_B;                 // [NS][NP][TILE_B]
   const uint32_t sBar = sB + NS * NP * TILE_B;               // barriers
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, tmem_slot = bar_a + 8;
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 tmem_slot = bar_afree + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * BM;
   const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
-  const int vt0 = blockIdx.y * tiles_per_split;
-  const int vt1 = min(n_vtiles, vt0 + tiles_per_split);
-  const int n_tiles = max(0, vt1 - vt0);
+  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
+  const Share sh(total, n_vtiles);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_afree, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -223,16 +245,22 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0) {
       ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi);
-      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
-        if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
-      }
       Pipe p;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int v0 = v_begin + (vt0 + t) * BN;
+      int seg = 0;
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (sh.seg_first(w)) {
+          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);   // the previous segment's MMAs have read sA
+          const int row0 = sh.outer(w) * BM;
+          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+            if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+          }
+          ++seg;
+        }
+        const int v0 = v_begin + sh.inner(w) * BN;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
@@ -245,14 +273,18 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
-      ptx::mbar_wait(bar_a, 0);
-      ptx::tc_fence_after_sync();
       Pipe p;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int buf = t & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+      int seg = -1, tc = 0;
+      for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+        if (sh.seg_first(w)) {
+          ++seg;
+          ptx::mbar_wait(bar_a, seg & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int buf = tc & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -264,6 +296,7 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           p.advance(NS);
         }
         ptx::umma_commit(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);
       }
     }
   } else {
@@ -271,12 +304,14 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;            // which 64-column half of the tile this warp owns
     const int row = q * 32 + lane;
-    const int64_t n = (int64_t)row0 + row;
     float m = -INFINITY, s = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int buf = t & 1;
-      const int vc0 = v_begin + (vt0 + t) * BN + half * 64;      // first item of this warp's columns
-      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+    int tc = 0;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc & 1;
+      const int tt = sh.outer(w), vt = sh.inner(w);
+      if (sh.seg_first(w)) { m = -INFINITY; s = 0.f; }
+      const int vc0 = v_begin + vt * BN + half * 64;             // first item of this warp's columns
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
       ptx::tc_fence_after_sync();
       float z[64];
       load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
@@ -312,12 +347,21 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         s = s * ptx::ex2_approx(fmaf(m, LOG2E, nb)) + ((add[0] + add[1]) + (add[2] + add[3]));
         m = mn;
       }
-    }
-    // each (split, half) pair is one partial of the vocabulary reduction merged by seqrec_ce_finalize
-    if (n < n_tokens) {
-      const int64_t slot = ((int64_t)blockIdx.y * 2 + half) * n_tokens + n;
-      ws_m[slot] = m;
-      ws_s[slot] = s;
+      if (sh.seg_last(w)) {
+        // one partial of the vocabulary reduction per (slot, half), merged by seqrec_ce_finalize
+        const int64_t n = (int64_t)tt * BM + row;
+        if (n < n_tokens) {
+          const int slot = (int)blockIdx.x - cta_of((int64_t)tt * n_vtiles, total);
+          ws_m[((int64_t)slot * 2 + half) * n_tokens + n] = m;
+          ws_s[((int64_t)slot * 2 + half) * n_tokens + n] = s;
+          if (vt == n_vtiles - 1) {              // last CTA of this token tile: blank the slots nobody writes
+            for (int k = slot + 1; k < max_slots; ++k) {
+              ws_m[((int64_t)k * 2 + half) * n_tokens + n] = -INFINITY;
+              ws_s[((int64_t)k * 2 + half) * n_tokens + n] = 0.f;
+            }
+          }
+        }
+      }
     }
   }
   ptx::tc_fence_before_sync();
@@ -328,11 +372,42 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// flush a [128 x ncols] fp32 TMEM accumulator slice owned by this warp (32 rows x `ncols` columns starting at
+// column col0) into global memory with vector reductions: dst_row points at this thread's row, column col0
+__device__ __forceinline__ void flush_acc_red(uint32_t taddr, int ncols, float* dst_row, int valid_cols, bool row_ok,
+                                              bool vec_ok, const float* scale_row) {
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(taddr + c, r);
+    ptx::tmem_ld_wait();
+    if (!row_ok) continue;
+    const int valid = min(32, valid_cols - c);
+    if (scale_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale_row[c + j]);
+    }
+    if (vec_ok && valid == 32) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        red_add_f4(dst_row + c + 4 * g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
+                                                    __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < valid) atomicAdd(dst_row + c + j, __uint_as_float(r[j]));
+    }
+  }
+}
+
 // ================================================================================================================
-// backward, token-stationary: dh[n,:] = sum_v dlogit[n,v] * W_out[:,v]
-//   per item tile:  S = A.Bt^T (TMEM, double buffered) -> epilogue writes dS (bf16 hi/lo, K-major over items) to
-//   shared memory -> dH (TMEM, persistent accumulator) += dS . W^T with W = W_out [Hk, Vp] bf16 hi/lo (box 64 x Hk)
-// grid = token tiles.  Needs Hk <= 128 (shared-memory budget; larger hidden sizes use the SIMT backward).
+// backward, token-stationary: dh[n,:] += sum_v dlogit[n,v] * W_out[:,v]
+//   outer = token tile (A resident per segment), inner = item tile.  Per item tile:  S = A.Bt^T (TMEM, double
+//   buffered) -> epilogue writes dS (bf16 hi/lo, rows = tokens) to shared memory -> dH (TMEM accumulator of the
+//   segment) += dS . W^T with W = W_out [Hk, Vp] bf16 hi/lo (box 64 x Hk).  At the end of a segment the accumulator is
+//   red-added into the pre-zeroed dh.  The MMA stream is software pipelined across tiles AND segments:
+//   S(w+1) is issued before dH(w).  Needs Hk <= 128 (shared-memory budget).
 template <int KB, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -341,7 +416,7 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                          const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
                          const float* __restrict__ srow, const float* __restrict__ coef,
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
-                         float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end, int accumulate) {
+                         float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end) {
   constexpr int NP = X3 ? 2 : 1;
   constexpr int NS = X3 ? 3 : 6;                          // 32 KB (x3) / 16 KB stages: fills the 227 KB budget
   constexpr int HK = KB * KBLK;
@@ -353,19 +428,23 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]        Bt / W blocks
   const uint32_t sBar = sB + NS * NP * TILE_B;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_dfull = bar_a + 8,
-                 bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8, tmem_slot = bar_hfull + 8;
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
+                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * BM;
-  const int n_tiles = (v_end - v_begin + BN - 1) / BN;
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
+  const Share sh(total, n_vtiles);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_afree, 1);
     ptx::mbar_init(bar_dfull, N_EPI_WARPS);
     ptx::mbar_init(bar_dempty, 1);
     ptx::mbar_init(bar_hfull, 1);
+    ptx::mbar_init(bar_hempty, N_EPI_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -381,17 +460,23 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    // stage order must equal the MMA warp's consumption order: Bt(0), then per tile i: Bt(i+1), W(i)
-    if (lane == 0) {
+    // stage order must equal the MMA warp's consumption order: Bt(w0), then per item w: Bt(w+1), W(w)
+    if (lane == 0 && sh.w0 < sh.w1) {
       ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmW_hi);
-      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
-        if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
-      }
       Pipe p;
-      auto load_bt = [&](int t) {
-        const int v0 = v_begin + t * BN;
+      int seg = 0;
+      auto load_s_operands = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+          const int row0 = sh.outer(w) * BM;
+          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+            if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+          }
+          ++seg;
+        }
+        const int v0 = v_begin + sh.inner(w) * BN;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
@@ -401,8 +486,8 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
       };
-      auto load_w = [&](int t) {
-        const int v0 = v_begin + t * BN;
+      auto load_w = [&](int64_t w) {
+        const int v0 = v_begin + sh.inner(w) * BN;
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
@@ -412,23 +497,28 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
       };
-      load_bt(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) load_bt(t + 1);
-        load_w(t);
+      load_s_operands(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) load_s_operands(w + 1);
+        load_w(w);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && sh.w0 < sh.w1) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(BM, HK);
-      ptx::mbar_wait(bar_a, 0);
-      ptx::tc_fence_after_sync();
       Pipe p;
-      auto issue_s = [&](int t) {
-        const int buf = t & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+      int seg_s = -1, tc_s = 0;      // S stream: segment index, running tile count
+      int seg_d = -1, tc_d = 0;      // dH stream
+      auto issue_s = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          ++seg_s;
+          ptx::mbar_wait(bar_a, seg_s & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int buf = tc_s & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s >> 1) & 1) ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -440,36 +530,50 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
         ptx::umma_commit(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);   // sA may be reloaded once these MMAs have completed
+        ++tc_s;
       };
-      issue_s(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) issue_s(t + 1);
-        ptx::mbar_wait(bar_dfull, t & 1);          // dS(t) is in shared memory
+      issue_s(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) issue_s(w + 1);
+        const bool first = sh.seg_first(w);
+        if (first) {
+          if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
+            ptx::mbar_wait(bar_hempty, seg_d & 1);
+            ptx::tc_fence_after_sync();
+          }
+          ++seg_d;
+        }
+        ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in shared memory
         ptx::tc_fence_after_sync();
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
           ptx::tc_fence_after_sync();
           const uint32_t b = sB + p.stage * NP * TILE_B;
-          mma_kblock<X3>(tmem_dh, sD + j * TILE_B, sD + (NJ + j) * TILE_B, b, b + TILE_B, idesc_h, t == 0 && j == 0);
+          mma_kblock<X3>(tmem_dh, sD + j * TILE_B, sD + (NJ + j) * TILE_B, b, b + TILE_B, idesc_h, first && j == 0);
           ptx::umma_commit(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_dempty);               // dS buffer may be overwritten
+        ptx::umma_commit(bar_dempty);                       // dS buffer may be overwritten
+        if (sh.seg_last(w)) ptx::umma_commit(bar_hfull);
+        ++tc_d;
       }
-      ptx::umma_commit(bar_hfull);
     }
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int64_t n = (int64_t)row0 + row;
-    const RowTerms rt = load_row_terms(n, n_tokens, mrow, srow, coef, tgt, inv_nvalid[0]);
+    const float inv = inv_nvalid[0];
     uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
-    for (int t = 0; t < n_tiles; ++t) {
-      const int buf = t & 1;
-      const int vc0 = v_begin + t * BN + half * 64;
-      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+    RowTerms rt;
+    int tc = 0, seg = -1;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc & 1;
+      const int64_t n = (int64_t)sh.outer(w) * BM + row;
+      if (sh.seg_first(w)) { ++seg; rt = load_row_terms(n, n_tokens, mrow, srow, coef, tgt, inv); }
+      const int vc0 = v_begin + sh.inner(w) * BN + half * 64;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
       ptx::tc_fence_after_sync();
       float z[64];
       load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
@@ -477,32 +581,23 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
       dlogit_half_tile(z, rt, vc0, v_end);
-      ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);     // previous tile's dH MMAs are done with the dS buffer
+      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);    // previous tile's dH MMAs are done with the dS buffer
       store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);
       ptx::fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dfull);
-    }
-    // final: dH accumulator -> global (fp32), optionally times the dropout factors; this warp owns HK/2 columns
-    ptx::mbar_wait(bar_hfull, 0);
-    ptx::tc_fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < HK / 64; ++c) {
-      const int h0 = half * (HK / 2) + c * 32;
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_dh + ((uint32_t)(q * 32) << 16) + h0, r);
-      ptx::tmem_ld_wait();
-      if (n < n_tokens) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int h = h0 + j;
-          if (h < H) {
-            float x = __uint_as_float(r[j]);
-            if (hscale) x *= hscale[n * H + h];
-            if (accumulate) x += dh[n * H + h];
-            dh[n * H + h] = x;
-          }
-        }
+      if (sh.seg_last(w)) {
+        // flush the segment's dH accumulator: this warp owns HK/2 columns of its 32 rows
+        ptx::mbar_wait(bar_hfull, seg & 1);
+        ptx::tc_fence_after_sync();
+        const int h0 = half * (HK / 2);
+        const bool row_ok = n < n_tokens;
+        const bool vec_ok = (H & 3) == 0;
+        flush_acc_red(tmem_dh + ((uint32_t)(q * 32) << 16) + h0, HK / 2, dh + n * H + h0, H - h0, row_ok, vec_ok,
+                      hscale ? hscale + n * H + h0 : nullptr);
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_hempty);
       }
     }
   }
@@ -516,10 +611,10 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
 // ================================================================================================================
 // backward, item-stationary: dW_out[:, v] += sum_n hs[n,:] * dlogit[n,v]
-//   Bt tile resident.  Per token tile:  S = A.Bt^T -> epilogue writes dS row-wise (rows = tokens, like the dH kernel) ->
-//   dW (TMEM [128 x 128 items]) += Ht . dS with Ht = hs^T [Hk, Np] bf16 hi/lo (K-major, box 64 tokens x 128 rows) and
-//   dS read back as an MN-major B operand (K = tokens runs down the rows).
-// grid = (item tiles, token splits); the fp32 result leaves through vector reductions into a pre-zeroed dW_out.
+//   outer = item tile (Bt resident per segment), inner = token tile.  Per token tile:  S = A.Bt^T -> epilogue writes
+//   dS row-wise (rows = tokens, like the dH kernel) -> dW (TMEM [128 x 128 items]) += Ht . dS with Ht = hs^T [Hk, Np]
+//   bf16 hi/lo (K-major, box 64 tokens x 128 rows) and dS read back as an MN-major B operand (K = tokens runs down
+//   the rows).  Segment results leave through red.global.add.v4.f32 into the pre-zeroed dW_out.
 template <int KB, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -528,33 +623,35 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                          const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
                          const float* __restrict__ srow, const float* __restrict__ coef,
                          const float* __restrict__ inv_nvalid, float* __restrict__ dW, int64_t n_tokens, int H,
-                         int v_begin, int v_end, int ldw, int tiles_per_split) {
+                         int v_begin, int v_end, int ldw) {
   constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = X3 ? 3 : 6;                          // 32 KB (x3) / 16 KB stages: fills the 227 KB budget
-  constexpr int HK = KB * KBLK;
+  constexpr int NS = X3 ? 3 : 6;
   constexpr int NJ = BM / KBLK;                             // 64-token blocks per tile (K blocks of the dW GEMM)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBt = base;                                 // [NP][KB][TILE_B]       W_out^T tile (resident)
-  const uint32_t sD = sBt + NP * KB * TILE_B;                // [NP][NJ][TILE_B]       dS^T tile
+  const uint32_t sD = sBt + NP * KB * TILE_B;                // [NP][NJ][TILE_B]       dS tile
   const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]       A / Ht blocks
   const uint32_t sBar = sB + NS * NP * TILE_B;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_dfull = bar_a + 8,
-                 bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8, tmem_slot = bar_hfull + 8;
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
+                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v0 = v_begin + blockIdx.x * BN;
-  const int64_t tok_tiles = (n_tokens + BM - 1) / BM;
-  const int64_t tt0 = (int64_t)blockIdx.y * tiles_per_split;
-  const int n_tiles = (int)max((int64_t)0, min(tok_tiles, tt0 + tiles_per_split) - tt0);
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int n_ttiles = (int)((n_tokens + BM - 1) / BM);
+  const int64_t total = (int64_t)n_vtiles * n_ttiles;
+  const Share sh(total, n_ttiles);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_afree, 1);
     ptx::mbar_init(bar_dfull, N_EPI_WARPS);
     ptx::mbar_init(bar_dempty, 1);
     ptx::mbar_init(bar_hfull, 1);
+    ptx::mbar_init(bar_hempty, N_EPI_WARPS);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -570,16 +667,22 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0 && sh.w0 < sh.w1) {
       ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmT_hi);
-      ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
-        if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
-      }
       Pipe p;
-      auto load_a = [&](int t) {
-        const int r0 = (int)((tt0 + t) * BM);
+      int seg = 0;
+      auto load_s_operands = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+          const int v0 = v_begin + sh.outer(w) * BN;
+          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
+            if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
+          }
+          ++seg;
+        }
+        const int r0 = sh.inner(w) * BM;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
@@ -589,8 +692,8 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
       };
-      auto load_t = [&](int t) {
-        const int r0 = (int)((tt0 + t) * BM);
+      auto load_t = [&](int64_t w) {
+        const int r0 = sh.inner(w) * BM;
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // box = 128 rows (rows >= Hk are zero)
@@ -600,25 +703,29 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
       };
-      load_a(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) load_a(t + 1);
-        load_t(t);
+      load_s_operands(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) load_s_operands(w + 1);
+        load_t(w);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0 && n_tiles > 0) {
+    if (lane == 0 && sh.w0 < sh.w1) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
       // dW GEMM: M = hidden (padded to 128), N = items, K = tokens.  A = Ht block (K-major, from TMA); B = dS exactly
       // as the epilogue wrote it (rows = tokens = K, 64 items per 128-byte row) read as an MN-major operand.
       constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_bmn(128, BN);
-      ptx::mbar_wait(bar_a, 0);
-      ptx::tc_fence_after_sync();
       Pipe p;
-      auto issue_s = [&](int t) {
-        const int buf = t & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((t >> 1) & 1) ^ 1);
+      int seg_s = -1, tc_s = 0, seg_d = -1, tc_d = 0;
+      auto issue_s = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          ++seg_s;
+          ptx::mbar_wait(bar_a, seg_s & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int buf = tc_s & 1;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s >> 1) & 1) ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
@@ -630,11 +737,21 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           p.advance(NS);
         }
         ptx::umma_commit(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);
+        ++tc_s;
       };
-      issue_s(0);
-      for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) issue_s(t + 1);
-        ptx::mbar_wait(bar_dfull, t & 1);
+      issue_s(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) issue_s(w + 1);
+        const bool first = sh.seg_first(w);
+        if (first) {
+          if (seg_d >= 0) {
+            ptx::mbar_wait(bar_hempty, seg_d & 1);
+            ptx::tc_fence_after_sync();
+          }
+          ++seg_d;
+        }
+        ptx::mbar_wait(bar_dfull, tc_d & 1);
         ptx::tc_fence_after_sync();
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
@@ -647,21 +764,22 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             const uint32_t boff = (uint32_t)(j * KBLK + k * 16) * 128;
             const uint64_t db_hi = ptx::umma_desc_mn_sw128(sD + boff, TILE_B);
             const uint64_t db_lo = ptx::umma_desc_mn_sw128(sD + NJ * TILE_B + boff, TILE_B);
-            const uint32_t first = (t == 0 && j == 0 && k == 0) ? 0u : 1u;
+            const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
             if (X3) {
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, first);
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, acc);
               ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_lo, k * 16), db_hi, idesc_w, 1u);
               ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, 1u);
             } else {
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, first);
+              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, acc);
             }
           }
           ptx::umma_commit(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
         ptx::umma_commit(bar_dempty);
+        if (sh.seg_last(w)) ptx::umma_commit(bar_hfull);
+        ++tc_d;
       }
-      ptx::umma_commit(bar_hfull);
     }
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
@@ -670,14 +788,17 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     const int row = q * 32 + lane;
     uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
     const float inv = inv_nvalid[0];
-    const int vc0 = v0 + half * 64;
-    RowTerms rt_next = load_row_terms(tt0 * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int buf = t & 1;
+    int tc = 0, seg = -1;
+    RowTerms rt_next;
+    if (sh.w0 < sh.w1) rt_next = load_row_terms((int64_t)sh.inner(sh.w0) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc & 1;
+      if (sh.seg_first(w)) ++seg;
       const RowTerms rt = rt_next;
-      if (t + 1 < n_tiles)                        // prefetch the next tile's row terms behind this tile's math
-        rt_next = load_row_terms((tt0 + t + 1) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
-      ptx::mbar_wait(bar_tfull + 8 * buf, (t >> 1) & 1);
+      if (w + 1 < sh.w1)                            // prefetch the next tile's row terms behind this tile's math
+        rt_next = load_row_terms((int64_t)sh.inner(w + 1) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+      const int vc0 = v_begin + sh.outer(w) * BN + half * 64;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
       ptx::tc_fence_after_sync();
       float z[64];
       load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
@@ -685,37 +806,22 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
       dlogit_half_tile(z, rt, vc0, v_end);
-      ptx::mbar_wait(bar_dempty, (t & 1) ^ 1);
+      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);
       store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);   // rows = tokens; consumed MN-major by the dW GEMM
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dfull);
-    }
-    if (n_tiles > 0) {
-      // final: dW accumulator rows = hidden unit, this warp's 64 item columns -> reductions into dW_out (H, ldw)
-      ptx::mbar_wait(bar_hfull, 0);
-      ptx::tc_fence_after_sync();
-      const int h = row;
-      const bool vec_ok = (ldw & 3) == 0 && (v_begin & 3) == 0;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_dw + ((uint32_t)(q * 32) << 16) + half * 64 + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (h < H) {
-          float* dst = dW + (size_t)h * ldw + vc0 + c * 32;
-          const int valid = min(32, v_end - (vc0 + c * 32));
-          if (vec_ok && valid == 32) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              red_add_f4(dst + 4 * g, make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]),
-                                                  __uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3])));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < valid) atomicAdd(dst + j, __uint_as_float(r[j]));
-          }
-        }
+      if (sh.seg_last(w)) {
+        // flush the segment's dW accumulator: rows = hidden unit, this warp's 64 item columns
+        ptx::mbar_wait(bar_hfull, seg & 1);
+        ptx::tc_fence_after_sync();
+        const int h = row;
+        const bool vec_ok = (ldw & 3) == 0 && (v_begin & 3) == 0;
+        flush_acc_red(tmem_dw + ((uint32_t)(q * 32) << 16) + half * 64, 64, dW + (size_t)h * ldw + vc0, v_end - vc0,
+                      h < H, vec_ok, nullptr);
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_hempty);
       }
     }
   }
@@ -747,19 +853,29 @@ target_logit_kernel(const float* __restrict__ hout, const float* __restrict__ hs
   if (lane == 0) zy[n] = acc + (b_out ? b_out[t] : 0.f);
 }
 
+// persistent grid: one CTA per SM, or one per tile pair when there are fewer pairs than SMs
+int persistent_grid(int64_t total) { return (int)(total < SEQREC_NUM_SMS ? total : SEQREC_NUM_SMS); }
+
+// partial slots a token tile can need: CTAs sharing one token tile's run of n_inner item tiles
+int forward_slots(int64_t n_tokens, int v_begin, int v_end) {
+  const int64_t n_inner = ceil_div(v_end - v_begin, BN);
+  const int64_t total = ((n_tokens + BM - 1) / BM) * n_inner;
+  const int64_t per = total / persistent_grid(total);      // >= 1: every CTA owns at least `per` tile pairs
+  return (int)((n_inner + per - 1) / per + 1);
+}
+
 template <int KB, int NS, bool X3, bool BIAS>
 int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-               const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end, int splits,
+               const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end,
                cudaStream_t st) {
   constexpr int NP = X3 ? 2 : 1;
   const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NS * NP * TILE_B + 256;
   auto k = ce_tc_forward_kernel<KB, NS, X3, BIAS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
-  const int n_vtiles = ceil_div(v_end - v_begin, BN);
-  const int tps = ceil_div(n_vtiles, splits);
-  dim3 grid(ceil_div(n_tokens, BM), splits);
-  k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, tps);
+  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+  k<<<persistent_grid(total), TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin,
+                                                      v_end, forward_slots(n_tokens, v_begin, v_end));
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -776,11 +892,15 @@ extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const
   return 0;
 }
 
+extern "C" int seqrec_ce_tc_partials(int64_t n_tokens, int v_begin, int v_end) {
+  if (n_tokens <= 0 || v_end <= v_begin) return -1001;
+  return 2 * forward_slots(n_tokens, v_begin, v_end);
+}
+
 extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi,
                                     const uint16_t* Bt_lo, const float* b_out, float* ws_m, float* ws_s,
-                                    int64_t n_tokens, int Hk, int V, int v_begin, int v_end, int splits, int x3,
-                                    void* stream) {
-  SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V && splits >= 1, 1);
+                                    int64_t n_tokens, int Hk, int V, int v_begin, int v_end, int x3, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
   SEQREC_ARG(Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256, 2);
   SEQREC_ARG(A_hi && Bt_hi && (!x3 || (A_lo && Bt_lo)), 3);
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -790,10 +910,10 @@ extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, 
   if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   cudaStream_t st = as_stream(stream);
-#define FWD2(KB, NS, X3V, BV)                                                                                  \
-  return launch_fwd<KB, NS, X3V, BV>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, splits, st)
-#define FWD(KB, NS)                                          \
-  {                                                          \
+#define FWD2(KB, NS, X3V, BV) \
+  return launch_fwd<KB, NS, X3V, BV>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, st)
+#define FWD(KB, NS)                                                                      \
+  {                                                                                      \
     if (x3) { if (b_out) FWD2(KB, NS, true, true); else FWD2(KB, NS, true, false); }     \
     else    { if (b_out) FWD2(KB, NS, false, true); else FWD2(KB, NS, false, false); }   \
   }
@@ -827,7 +947,14 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
   const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)(x3 ? 3 : 6) * NP * TILE_B + 256;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+  const int grid = persistent_grid(total);
   if (dh) {
+    // every segment red-adds its partial dH, so the destination starts from zero unless the caller accumulates
+    if (!accumulate_dh) {
+      cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)n_tokens * H, st);
+      if (e != cudaSuccess) return -(int)e;
+    }
     if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, Hk))) return rc;
     if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, Hk))) return rc;
 #define DH(KBV, X3V)                                                                                          \
@@ -835,9 +962,8 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
     auto k = ce_tc_backward_dh_kernel<KBV, X3V>;                                                              \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     if (e != cudaSuccess) return -(int)e;                                                                     \
-    k<<<ceil_div(n_tokens, BM), TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef,  \
-                                                        inv_nvalid, hscale, dh, n_tokens, H, v_begin, v_end,  \
-                                                        accumulate_dh);                                       \
+    k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid, hscale, \
+                                      dh, n_tokens, H, v_begin, v_end);                                       \
   }
     if (KB == 1) { if (x3) DH(1, true) else DH(1, false) }
     else         { if (x3) DH(2, true) else DH(2, false) }
@@ -847,21 +973,13 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   if (dW_out) {
     if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
-    const int v_tiles = ceil_div(v_end - v_begin, BN);
-    const int64_t tok_tiles = (n_tokens + BM - 1) / BM;
-    int splits = SEQREC_NUM_SMS / v_tiles;                    // keep the grid within one wave of 148 CTAs
-    if (splits < 1) splits = 1;
-    if (splits > tok_tiles) splits = (int)tok_tiles;
-    const int tps = ceil_div(tok_tiles, splits);
-    splits = ceil_div(tok_tiles, tps);
-    dim3 grid(v_tiles, splits);
 #define DW(KBV, X3V)                                                                                          \
   {                                                                                                           \
     auto k = ce_tc_backward_dw_kernel<KBV, X3V>;                                                              \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     if (e != cudaSuccess) return -(int)e;                                                                     \
     k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,        \
-                                      dW_out, n_tokens, H, v_begin, v_end, ldw, tps);                         \
+                                      dW_out, n_tokens, H, v_begin, v_end, ldw);                              \
   }
     if (KB == 1) { if (x3) DW(1, true) else DW(1, false) }
     else         { if (x3) DW(2, true) else DW(2, false) }

@@ -335,11 +335,23 @@ static int launch_bwd(float* xg, const float* Ut, const uint8_t* mask, const flo
     default: return -1002;                                                                  \
   }
 
+// register-resident fast path (rnn_reg.cu)
+bool rnn_reg_applicable(int cell, int H);
+int rnn_reg_launch(int cell, int act, int rb, bool fwd, float* xg, const float* U, const uint8_t* mask, float* hout,
+                   float* cst, const float* dhout, int T, int B, int H, cudaStream_t st);
+
+// rows per CTA of the register-resident scan: 96 of the 128 registers hold U when H > 96, leaving room for 2 rows
+static int reg_rb(int rb, int H) { return H > 96 ? (rb > 2 ? 2 : rb) : (rb > 4 ? 4 : rb); }
+
+extern "C" int seqrec_rnn_needs_ut(int cell, int H) { return rnn_reg_applicable(cell, H) ? 0 : 1; }
+
 extern "C" int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8_t* mask, float* hout,
                                   float* cst, int T, int B, int H, void* stream) {
   SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
   cudaStream_t st = as_stream(stream);
   const int rb = pick_rb(B);
+  if (rnn_reg_applicable(cell, H))
+    return rnn_reg_launch(cell, act, reg_rb(rb, H), true, xg, U, mask, hout, cst, nullptr, T, B, H, st);
   switch (cell) {
     case SEQREC_CELL_SIMPLE: DISPATCH_ACT(launch_fwd, SEQREC_CELL_SIMPLE, xg, U, mask, hout, cst, T, B, H, st)
     case SEQREC_CELL_LSTM: DISPATCH_ACT(launch_fwd, SEQREC_CELL_LSTM, xg, U, mask, hout, cst, T, B, H, st)
@@ -348,12 +360,18 @@ extern "C" int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, 
   }
 }
 
-extern "C" int seqrec_rnn_backward(int cell, int act, float* xg, const float* Ut, const uint8_t* mask,
-                                   const float* hout, float* cst, const float* dhout, int T, int B, int H,
-                                   void* stream) {
+extern "C" int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const float* Ut,
+                                   const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T,
+                                   int B, int H, void* stream) {
   SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
   cudaStream_t st = as_stream(stream);
   const int rb = pick_rb(B);
+  if (rnn_reg_applicable(cell, H)) {
+    SEQREC_ARG(U != nullptr, 2);
+    return rnn_reg_launch(cell, act, reg_rb(rb, H), false, xg, U, mask, const_cast<float*>(hout), cst, dhout, T, B,
+                          H, st);
+  }
+  SEQREC_ARG(Ut != nullptr, 3);
   switch (cell) {
     case SEQREC_CELL_SIMPLE:
       DISPATCH_ACT(launch_bwd, SEQREC_CELL_SIMPLE, xg, Ut, mask, hout, cst, dhout, T, B, H, st)

@@ -75,8 +75,8 @@ class _Work:
             if self.tc["bwd"]:
                 self.Ht_hi = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev)
                 self.Ht_lo = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev) if hp.tc_x3 else None
-            if 2 * self.tc["splits"] > self.splits:       # every CTA emits two partials (one per 64-column half)
-                self.splits = 2 * self.tc["splits"]
+            if self.tc["splits"] > self.splits:
+                self.splits = self.tc["splits"]
                 self.ws_m = torch.empty((self.splits, N), dtype=f32, device=dev)
                 self.ws_s = torch.empty((self.splits, N), dtype=f32, device=dev)
         # pinned staging for host batches
@@ -135,6 +135,7 @@ class HotPath:
         self.dW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
         self.aW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
         self.Ut = torch.empty((self.GH, self.H), dtype=f32, device=dev)
+        self._needs_ut = _lib.load().seqrec_rnn_needs_ut(CELL[cell], self.H) != 0
         self.touched = torch.zeros(self.F, dtype=torch.int32, device=dev)
         self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
         self.n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -187,9 +188,7 @@ class HotPath:
         """Which logits kernels serve a batch of N tokens."""
         fwd = (self.tc_mode != "off" and self.Hk <= 256 and self.V >= 256 and N >= 128)
         bwd = fwd and self.Hk <= 128 and not self.out_bias
-        tiles = (N + 127) // 128
-        v_tiles = (self.V + 127) // 128
-        splits = max(1, min(v_tiles, NUM_SMS // tiles)) if tiles <= NUM_SMS else 1
+        splits = _lib.load().seqrec_ce_tc_partials(N, 0, self.V) if fwd else 0   # partial rows the TC forward writes
         return dict(fwd=fwd, bwd=bwd, splits=splits)
 
     def _stage_weight_operands(self):
@@ -336,8 +335,8 @@ class HotPath:
                 call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
                      ptr(w.zy), w.N, self.H, self.V, st)
             call("seqrec_ce_tc_forward", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out),
-                 ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, w.tc["splits"], 1 if self.tc_x3 else 0, st)
-            n_splits = 2 * w.tc["splits"]
+                 ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, 1 if self.tc_x3 else 0, st)
+            n_splits = w.tc["splits"]
         else:
             self._mark("ce_fwd")
             n_splits = self._ce_splits(w.N)
@@ -395,9 +394,10 @@ class HotPath:
         self._mark("ce_bwd")
         self._backward_ce(w)
         self._mark("rnn_bwd")
-        call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
-        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),
-             ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        if self._needs_ut:
+            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
+             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
         self._mark("rnn_wgrad")
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
@@ -503,9 +503,10 @@ class HotPath:
         self.flat_g.zero_()
         self._backward_ce(w)
         dh = w.dh.clone()
-        call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
-        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.mask), ptr(w.hout),
-             ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        if self._needs_ut:
+            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
+             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
         self.n_rows.zero_()
