@@ -76,22 +76,32 @@ struct Pipe {  // ring of NS stages
 template <bool X3>
 __device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                            uint32_t idesc, bool first) {
+  // called by the whole (converged) MMA warp: descriptors are warp-uniform, one elected lane issues
   const uint64_t da_hi = ptx::umma_desc_k_sw128(a_hi), db_hi = ptx::umma_desc_k_sw128(b_hi);
   const uint64_t da_lo = ptx::umma_desc_k_sw128(a_lo), db_lo = ptx::umma_desc_k_sw128(b_lo);
+  if (ptx::elect_one()) {
 #pragma unroll
-  for (int k = 0; k < KBLK / 16; ++k) {
-    const int e = k * 16;
-    if (X3) {
-      // small cross terms first, the dominant hi.hi product last
-      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_lo, e), idesc,
-                     (first && k == 0) ? 0u : 1u);
-      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_lo, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
-      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
-    } else {
-      ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc,
-                     (first && k == 0) ? 0u : 1u);
+    for (int k = 0; k < KBLK / 16; ++k) {
+      const int e = k * 16;
+      if (X3) {
+        // small cross terms first, the dominant hi.hi product last
+        ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_lo, e), idesc,
+                       (first && k == 0) ? 0u : 1u);
+        ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_lo, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
+        ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc, 1u);
+      } else {
+        ptx::umma_bf16(tmem_d, ptx::umma_desc_advance_k(da_hi, e), ptx::umma_desc_advance_k(db_hi, e), idesc,
+                       (first && k == 0) ? 0u : 1u);
+      }
     }
   }
+  __syncwarp();
+}
+
+// tcgen05.commit by the elected lane of the converged MMA warp (the lane that issued the MMAs)
+__device__ __forceinline__ void commit_elect(uint32_t bar) {
+  if (ptx::elect_one()) ptx::umma_commit(bar);
+  __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
@@ -245,35 +255,39 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi);
+    {
+      if (lane == 0) { ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); }
       Pipe p;
       int seg = 0;
       for (int64_t w = sh.w0; w < sh.w1; ++w) {
         if (sh.seg_first(w)) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);   // the previous segment's MMAs have read sA
           const int row0 = sh.outer(w) * BM;
-          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
-            if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+            for (int kb = 0; kb < KB; ++kb) {
+              ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+              if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+            }
           }
           ++seg;
         }
         const int v0 = v_begin + sh.inner(w) * BN;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          }
           p.advance(NS);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
       Pipe p;
       int seg = -1, tc = 0;
@@ -292,11 +306,11 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           ptx::tc_fence_after_sync();
           const uint32_t b = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
-          ptx::umma_commit(bar_empty + 8 * p.stage);
+          commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);
+        commit_elect(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) commit_elect(bar_afree);
       }
     }
   } else {
@@ -461,28 +475,32 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
     // stage order must equal the MMA warp's consumption order: Bt(w0), then per item w: Bt(w+1), W(w)
-    if (lane == 0 && sh.w0 < sh.w1) {
-      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmW_hi);
+    if (sh.w0 < sh.w1) {
+      if (lane == 0) { ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmW_hi); }
       Pipe p;
       int seg = 0;
       auto load_s_operands = [&](int64_t w) {
         if (sh.seg_first(w)) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
           const int row0 = sh.outer(w) * BM;
-          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
-            if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+            for (int kb = 0; kb < KB; ++kb) {
+              ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
+              if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
+            }
           }
           ++seg;
         }
         const int v0 = v_begin + sh.inner(w) * BN;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+          }
           p.advance(NS);
         }
       };
@@ -490,10 +508,12 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const int v0 = v_begin + sh.inner(w) * BN;
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmW_hi, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmW_lo, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmW_hi, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmW_lo, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
+          }
           p.advance(NS);
         }
       };
@@ -505,7 +525,7 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0 && sh.w0 < sh.w1) {
+    if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(BM, HK);
       Pipe p;
@@ -526,11 +546,11 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::tc_fence_after_sync();
           const uint32_t b = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc_s, kb == 0);
-          ptx::umma_commit(bar_empty + 8 * p.stage);
+          commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);   // sA may be reloaded once these MMAs have completed
+        commit_elect(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) commit_elect(bar_afree);   // sA may be reloaded once these MMAs have completed
         ++tc_s;
       };
       issue_s(sh.w0);
@@ -551,11 +571,11 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::tc_fence_after_sync();
           const uint32_t b = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(tmem_dh, sD + j * TILE_B, sD + (NJ + j) * TILE_B, b, b + TILE_B, idesc_h, first && j == 0);
-          ptx::umma_commit(bar_empty + 8 * p.stage);
+          commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_dempty);                       // dS buffer may be overwritten
-        if (sh.seg_last(w)) ptx::umma_commit(bar_hfull);
+        commit_elect(bar_dempty);                       // dS buffer may be overwritten
+        if (sh.seg_last(w)) commit_elect(bar_hfull);
         ++tc_d;
       }
     }
@@ -667,28 +687,32 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0 && sh.w0 < sh.w1) {
-      ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmT_hi);
+    if (sh.w0 < sh.w1) {
+      if (lane == 0) { ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmT_hi); }
       Pipe p;
       int seg = 0;
       auto load_s_operands = [&](int64_t w) {
         if (sh.seg_first(w)) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
           const int v0 = v_begin + sh.outer(w) * BN;
-          ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
-            if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+            for (int kb = 0; kb < KB; ++kb) {
+              ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
+              if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
+            }
           }
           ++seg;
         }
         const int r0 = sh.inner(w) * BM;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmA_hi, bar_full + 8 * p.stage, kb * KBLK, r0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmA_lo, bar_full + 8 * p.stage, kb * KBLK, r0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmA_hi, bar_full + 8 * p.stage, kb * KBLK, r0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmA_lo, bar_full + 8 * p.stage, kb * KBLK, r0);
+          }
           p.advance(NS);
         }
       };
@@ -696,10 +720,12 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         const int r0 = sh.inner(w) * BM;
         for (int j = 0; j < NJ; ++j) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // box = 128 rows (rows >= Hk are zero)
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmT_hi, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmT_lo, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // box = 128 rows (rows >= Hk are zero)
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmT_hi, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmT_lo, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
+          }
           p.advance(NS);
         }
       };
@@ -711,7 +737,7 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0 && sh.w0 < sh.w1) {
+    if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
       // dW GEMM: M = hidden (padded to 128), N = items, K = tokens.  A = Ht block (K-major, from TMA); B = dS exactly
       // as the epilogue wrote it (rows = tokens = K, 64 items per 128-byte row) read as an MN-major operand.
@@ -733,11 +759,11 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::tc_fence_after_sync();
           const uint32_t a = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, a, a + TILE_B, sBt + kb * TILE_B, sBt + (KB + kb) * TILE_B, idesc_s, kb == 0);
-          ptx::umma_commit(bar_empty + 8 * p.stage);
+          commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) ptx::umma_commit(bar_afree);
+        commit_elect(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) commit_elect(bar_afree);
         ++tc_s;
       };
       issue_s(sh.w0);
@@ -758,26 +784,31 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::tc_fence_after_sync();
           const uint32_t a = sB + p.stage * NP * TILE_B;     // Ht block: rows = hidden, K = 64 tokens
           const uint64_t da_hi = ptx::umma_desc_k_sw128(a), da_lo = ptx::umma_desc_k_sw128(a + TILE_B);
+          // 16 tokens = 16 rows of 128 B (2048 B) further down the dS image per K step; the two 64-item blocks of the
+          // tile are TILE_B apart (LBO)
+          const uint64_t db_hi0 = ptx::umma_desc_mn_sw128(sD + (uint32_t)(j * KBLK) * 128, TILE_B);
+          const uint64_t db_lo0 = ptx::umma_desc_mn_sw128(sD + NJ * TILE_B + (uint32_t)(j * KBLK) * 128, TILE_B);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KBLK / 16; ++k) {
-            // 16 tokens = 16 rows of 128 B further down the dS image; its two 64-item blocks are TILE_B apart (LBO)
-            const uint32_t boff = (uint32_t)(j * KBLK + k * 16) * 128;
-            const uint64_t db_hi = ptx::umma_desc_mn_sw128(sD + boff, TILE_B);
-            const uint64_t db_lo = ptx::umma_desc_mn_sw128(sD + NJ * TILE_B + boff, TILE_B);
-            const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
-            if (X3) {
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, acc);
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_lo, k * 16), db_hi, idesc_w, 1u);
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, 1u);
-            } else {
-              ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, acc);
+            for (int k = 0; k < KBLK / 16; ++k) {
+              const uint64_t db_hi = db_hi0 + (uint64_t)((k * 16 * 128) >> 4);
+              const uint64_t db_lo = db_lo0 + (uint64_t)((k * 16 * 128) >> 4);
+              const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
+              if (X3) {
+                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, acc);
+                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_lo, k * 16), db_hi, idesc_w, 1u);
+                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, 1u);
+              } else {
+                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, acc);
+              }
             }
           }
-          ptx::umma_commit(bar_empty + 8 * p.stage);
+          __syncwarp();
+          commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
-        ptx::umma_commit(bar_dempty);
-        if (sh.seg_last(w)) ptx::umma_commit(bar_hfull);
+        commit_elect(bar_dempty);
+        if (sh.seg_last(w)) commit_elect(bar_hfull);
         ++tc_d;
       }
     }

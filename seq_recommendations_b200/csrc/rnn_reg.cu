@@ -5,6 +5,9 @@
 // thread (s, c) keeps the K-slice s of the gate columns of hidden unit c (forward) or of row c of U (backward) in
 // registers, so a timestep reads only the RB hidden vectors from shared memory (warp-wide broadcasts), does its share
 // of the (RB x H).(H x G*H) product as register FFMAs, and the four K-slices are summed through shared memory.
+// Everything a step needs from global memory (input projection / saved gates / dL/dh / mask) is prefetched one step
+// ahead into shared memory with cp.async, so neither load latency nor staging registers sit on the sequential path:
+// 96 of the 128 registers per thread hold U.
 // Same semantics, inputs and outputs as the generic kernels in rnn_scan.cu (Keras-2.0.x GRU: reset applied BEFORE the
 // recurrent matmul -> two dependent matvec phases per step; Theano K.rnn mask switch).
 #include "common.cuh"
@@ -16,19 +19,42 @@ constexpr int KS = 4;  // K-slices
 template <int CELL>
 struct Gates { static constexpr int G = (CELL == SEQREC_CELL_GRU) ? 3 : 1; };
 
-// acc[r] += sum_i vec[r*ldv + k0 + i] * u[i]   (vec in shared memory, read as warp-wide float4 broadcasts)
-template <int RB, int KPT>
-__device__ __forceinline__ void dot_slice(float (&acc)[RB], const float* __restrict__ vec, int ldv, int k0,
-                                          const float (&u)[KPT]) {
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// acc[g][r] += sum_i vec[r*ldv + k0 + i] * u[g0 + g][i] for NG gates sharing the same vector; the float4 loads of the
+// next quad are issued before the FFMAs of the current one (software pipelined, fully unrolled)
+template <int RB, int KPT, int NG, int GT>
+__device__ __forceinline__ void dot_slices(float (&acc)[NG][RB], const float* __restrict__ vec, int ldv, int k0,
+                                           const float (&u)[GT][KPT], int g0) {
+  float4 hq[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) hq[r] = *reinterpret_cast<const float4*>(vec + r * ldv + k0);
 #pragma unroll
   for (int i = 0; i < KPT; i += 4) {
+    float4 hn[RB];
+    if (i + 4 < KPT) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const float4 h = *reinterpret_cast<const float4*>(vec + r * ldv + k0 + i);
-      acc[r] = fmaf(h.x, u[i], acc[r]);
-      acc[r] = fmaf(h.y, u[i + 1], acc[r]);
-      acc[r] = fmaf(h.z, u[i + 2], acc[r]);
-      acc[r] = fmaf(h.w, u[i + 3], acc[r]);
+      for (int r = 0; r < RB; ++r) hn[r] = *reinterpret_cast<const float4*>(vec + r * ldv + k0 + i + 4);
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        acc[g][r] = fmaf(hq[r].x, u[g0 + g][i], acc[g][r]);
+        acc[g][r] = fmaf(hq[r].y, u[g0 + g][i + 1], acc[g][r]);
+        acc[g][r] = fmaf(hq[r].z, u[g0 + g][i + 2], acc[g][r]);
+        acc[g][r] = fmaf(hq[r].w, u[g0 + g][i + 3], acc[g][r]);
+      }
+    if (i + 4 < KPT) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) hq[r] = hn[r];
     }
   }
 }
@@ -39,13 +65,17 @@ __global__ void __launch_bounds__(KS * 128, 1)
 rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, const uint8_t* __restrict__ mask,
                        float* __restrict__ hout, int T, int B, int H) {
   constexpr int G = Gates<CELL>::G;
+  constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;   // gates whose recurrent product uses h_{t-1} itself
   constexpr int KP = KS * KPT;                 // padded hidden size seen by the dot products
   const int CG = blockDim.x / KS;
   const int GH = G * H;
   extern __shared__ __align__(16) float smem[];
-  float* h_s = smem;                           // [RB][KP]  h_{t-1}
-  float* rh_s = h_s + RB * KP;                 // [RB][KP]  GRU: r * h_{t-1}
+  float* h_s = smem;                           // [RB][KP]        h_{t-1}
+  float* rh_s = h_s + RB * KP;                 // [RB][KP]        GRU: r * h_{t-1}
   float* part_s = rh_s + RB * KP;              // [KS][RB][G][CG] partial sums
+  float* x_s = part_s + KS * RB * G * CG;      // [2][RB][G][CG]  input projection, double buffered (cp.async)
+  float* zr_s = x_s + 2 * RB * G * CG;         // [RB][2][CG]     GRU: z and r of this step
+  int* m_s = reinterpret_cast<int*>(zr_s + RB * 2 * CG);  // [2][RB] mask of this / next step
   const int tid = threadIdx.x;
   const int s = tid / CG, c = tid - s * CG;
   const int b0 = blockIdx.x * RB;
@@ -60,97 +90,113 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
       u[g][i] = (k < H && c < H) ? U[(size_t)k * GH + g * H + c] : 0.f;
     }
   for (int i = tid; i < 2 * RB * KP; i += blockDim.x) h_s[i] = 0.f;   // h_s and rh_s
-  // Everything a step reads from global memory is prefetched one step ahead, so no load latency sits on the
-  // sequential critical path.
-  float xpre[RB][G];                           // input projection of the current step (owners only)
-  bool mpre[RB];                               // mask of the current step
-  float hreg[RB];                              // owner's copy of h_{t-1}[c]
+
+  auto prefetch_x = [&](int t) {               // owners: xp of step t -> x_s[t & 1]
+    if (owner && t < T) {
 #pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    hreg[r] = 0.f;
-    mpre[r] = (owner && b0 + r < B) ? (mask[(size_t)b0 + r] != 0) : false;
+      for (int r = 0; r < RB; ++r)
+        if (b0 + r < B) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-      xpre[r][g] = (owner && b0 + r < B) ? xg[((size_t)b0 + r) * GH + g * H + c] : 0.f;
+          for (int g = 0; g < G; ++g)
+            cp_async4(x_s + (((t & 1) * RB + r) * G + g) * CG + c, xg + ((size_t)t * B + b0 + r) * GH + g * H + c);
+        }
+    }
+    cp_async_commit();
+  };
+  // mask: thread tid < RB pipelines it through two registers so the global load is issued two steps ahead
+  int m1 = 0, m2 = 0;
+  if (tid < RB) {
+    const bool ok = b0 + tid < B;
+    m_s[tid] = ok ? (mask[b0 + tid] != 0) : 0;
+    m1 = (ok && 1 < T) ? (mask[(size_t)1 * B + b0 + tid] != 0) : 0;
+    m2 = (ok && 2 < T) ? (mask[(size_t)2 * B + b0 + tid] != 0) : 0;
   }
+  prefetch_x(0);
   __syncthreads();
 
   for (int t = 0; t < T; ++t) {
     const size_t tok0 = (size_t)t * B + b0;
-    constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;   // gates whose recurrent product uses h_{t-1} itself
-    // ---- phase 1: partial h.U over this thread's K-slice
+    const float* xc = x_s + (t & 1) * RB * G * CG;
+    prefetch_x(t + 1);                         // lands in the other buffer behind this step's matvecs
+    // ---- phase 1: partial h.U over this thread's K-slice (all gates that see h_{t-1} share the loads)
+    {
+      float acc[G1][RB];
 #pragma unroll
-    for (int g = 0; g < G1; ++g) {
-      float acc[RB];
+      for (int g = 0; g < G1; ++g)
 #pragma unroll
-      for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-      dot_slice<RB, KPT>(acc, h_s, KP, s * KPT, u[g]);
+        for (int r = 0; r < RB; ++r) acc[g][r] = 0.f;
+      dot_slices<RB, KPT, G1, G>(acc, h_s, KP, s * KPT, u, 0);
 #pragma unroll
-      for (int r = 0; r < RB; ++r) part_s[((s * RB + r) * G + g) * CG + c] = acc[r];
+      for (int g = 0; g < G1; ++g)
+#pragma unroll
+        for (int r = 0; r < RB; ++r) part_s[((s * RB + r) * G + g) * CG + c] = acc[g][r];
     }
+    cp_async_wait<1>();                        // this step's xp (issued one step ago) has landed (own elements)
     __syncthreads();
-    float zreg[RB], rreg[RB];
-    if (CELL == SEQREC_CELL_GRU) {
+    if constexpr (CELL == SEQREC_CELL_GRU) {
       if (owner) {
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
-          float az = xpre[r][0], ar = xpre[r][1];
+          float az = xc[(r * G + 0) * CG + c], ar = xc[(r * G + 1) * CG + c];
 #pragma unroll
           for (int q = 0; q < KS; ++q) {
             az += part_s[((q * RB + r) * G + 0) * CG + c];
             ar += part_s[((q * RB + r) * G + 1) * CG + c];
           }
-          zreg[r] = hard_sigmoid_f(az);
-          rreg[r] = hard_sigmoid_f(ar);
-          rh_s[r * KP + c] = rreg[r] * hreg[r];
+          const float z = hard_sigmoid_f(az), rr = hard_sigmoid_f(ar);
+          zr_s[(r * 2 + 0) * CG + c] = z;
+          zr_s[(r * 2 + 1) * CG + c] = rr;
+          rh_s[r * KP + c] = rr * h_s[r * KP + c];
         }
       }
       __syncthreads();
       // ---- phase 2: candidate, (r*h).U_h
-      float acc[RB];
+      float acc[1][RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-      dot_slice<RB, KPT>(acc, rh_s, KP, s * KPT, u[2]);
+      for (int r = 0; r < RB; ++r) acc[0][r] = 0.f;
+      dot_slices<RB, KPT, 1, G>(acc, rh_s, KP, s * KPT, u, G - 1);
 #pragma unroll
-      for (int r = 0; r < RB; ++r) part_s[((s * RB + r) * G + 2) * CG + c] = acc[r];
+      for (int r = 0; r < RB; ++r) part_s[((s * RB + r) * G + 2) * CG + c] = acc[0][r];
       __syncthreads();
     }
-    // ---- phase 3: gate math, state update under the mask, stores; prefetch the next step's input projection
+    // ---- phase 3: gate math, state update under the mask, stores
     if (owner) {
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         if (b0 + r >= B) continue;
         const size_t tok = tok0 + r;
-        const bool m = mpre[r];
+        const bool m = m_s[(t & 1) * RB + r] != 0;
+        const float hp = h_s[r * KP + c];
         float hn;
         float* gp = xg + tok * GH;
-        if (CELL == SEQREC_CELL_GRU) {
-          float ah = xpre[r][2];
+        if constexpr (CELL == SEQREC_CELL_GRU) {
+          float ah = xc[(r * G + 2) * CG + c];
 #pragma unroll
           for (int q = 0; q < KS; ++q) ah += part_s[((q * RB + r) * G + 2) * CG + c];
           const float hh = act_f<ACT>(ah);
-          hn = zreg[r] * hreg[r] + (1.0f - zreg[r]) * hh;
-          gp[c] = zreg[r]; gp[H + c] = rreg[r]; gp[2 * H + c] = hh;
+          const float z = zr_s[(r * 2 + 0) * CG + c], rr = zr_s[(r * 2 + 1) * CG + c];
+          hn = z * hp + (1.0f - z) * hh;
+          gp[c] = z; gp[H + c] = rr; gp[2 * H + c] = hh;
         } else {
-          float a = xpre[r][0];
+          float a = xc[(r * G + 0) * CG + c];
 #pragma unroll
           for (int q = 0; q < KS; ++q) a += part_s[((q * RB + r) * G + 0) * CG + c];
           hn = act_f<ACT>(a);
           gp[c] = hn;
         }
-        const float hv = m ? hn : hreg[r];
-        hreg[r] = hv;
+        const float hv = m ? hn : hp;
         h_s[r * KP + c] = hv;
         hout[tok * H + c] = hv;
-        if (t + 1 < T) {
-          mpre[r] = mask[tok + B] != 0;
-#pragma unroll
-          for (int g = 0; g < G; ++g) xpre[r][g] = xg[(tok + B) * GH + g * H + c];
-        }
       }
+    }
+    if (tid < RB) {
+      m_s[((t + 1) & 1) * RB + tid] = m1;
+      m1 = m2;
+      m2 = (b0 + tid < B && t + 3 < T) ? (mask[(size_t)(t + 3) * B + b0 + tid] != 0) : 0;
     }
     __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -161,12 +207,18 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
                         const float* __restrict__ hout, float* __restrict__ cst, const float* __restrict__ dhout,
                         int T, int B, int H) {
   constexpr int G = Gates<CELL>::G;
+  constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;
+  constexpr int NI = (CELL == SEQREC_CELL_GRU) ? 5 : 2;   // prefetched per-step inputs: dh, gates..., h_{t-1}
   constexpr int KP = KS * KPT;
   const int CG = blockDim.x / KS;
   const int GH = G * H;
   extern __shared__ __align__(16) float smem[];
-  float* da_s = smem;                          // [G][RB][KP] pre-activation gradients of this step
+  float* da_s = smem;                          // [G][RB][KP]      pre-activation gradients of this step
   float* part_s = da_s + G * RB * KP;          // [KS][RB][CG]
+  float* in_s = part_s + KS * RB * CG;         // [2][RB][NI][CG]  per-step inputs, double buffered (cp.async)
+  float* dd_s = in_s + 2 * RB * NI * CG;       // [RB][CG]         direct part of dL/dh_{t-1}
+  float* dc_s = dd_s + RB * CG;                // [RB][CG]         dL/dh_t carried from later steps
+  int* m_s = reinterpret_cast<int*>(dc_s + RB * CG);   // [2][RB]
   const int tid = threadIdx.x;
   const int s = tid / CG, c = tid - s * CG;
   const int b0 = blockIdx.x * RB;
@@ -181,140 +233,161 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
       u[g][i] = (j < H && c < H) ? U[(size_t)c * GH + g * H + j] : 0.f;
     }
   for (int i = tid; i < G * RB * KP; i += blockDim.x) da_s[i] = 0.f;
-  float dh_carry[RB];
+  for (int i = tid; i < 2 * RB * CG; i += blockDim.x) dd_s[i] = 0.f;   // dd_s and dc_s
+
+  // in_s[buf][r][0] = dL/dhout, [1..3] = saved gates z, r, hh (SimpleRNN: [1] = output y), [4] = h_{t-1}
+  auto prefetch_in = [&](int t) {
+    if (owner && t >= 0) {
+      float* dst = in_s + (size_t)(t & 1) * RB * NI * CG;
 #pragma unroll
-  for (int r = 0; r < RB; ++r) dh_carry[r] = 0.f;
-  // Per-step global inputs of the owners, prefetched one step ahead (no load latency on the sequential path):
-  // dL/dhout, the saved gates (GRU: z, r, hh; SimpleRNN: the output y), h_{t-1} and the mask.
-  struct StepIn { float dh, g0, g1, g2, hprev; bool m; };
-  auto load_step = [&](int t, int r) {
-    StepIn in;
-    in.dh = 0.f; in.g0 = 0.f; in.g1 = 0.f; in.g2 = 0.f; in.hprev = 0.f; in.m = false;
-    if (owner && b0 + r < B && t >= 0) {
-      const size_t tok = (size_t)t * B + b0 + r;
-      in.m = mask[tok] != 0;
-      in.dh = dhout[tok * H + c];
-      if (CELL == SEQREC_CELL_GRU) {
-        const float* gp = xg + tok * GH;
-        in.g0 = gp[c]; in.g1 = gp[H + c]; in.g2 = gp[2 * H + c];
-        in.hprev = (t > 0) ? hout[(tok - B) * H + c] : 0.f;
-      } else {
-        in.g0 = hout[tok * H + c];
-      }
+      for (int r = 0; r < RB; ++r)
+        if (b0 + r < B) {
+          const size_t tok = (size_t)t * B + b0 + r;
+          cp_async4(dst + (r * NI + 0) * CG + c, dhout + tok * H + c);
+          if (CELL == SEQREC_CELL_GRU) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) cp_async4(dst + (r * NI + 1 + g) * CG + c, xg + tok * GH + g * H + c);
+            if (t > 0) cp_async4(dst + (r * NI + 4) * CG + c, hout + (tok - B) * H + c);
+          } else {
+            cp_async4(dst + (r * NI + 1) * CG + c, hout + tok * H + c);
+          }
+        }
     }
-    return in;
+    cp_async_commit();
   };
-  StepIn pre[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) pre[r] = load_step(T - 1, r);
+  int m1 = 0, m2 = 0;
+  if (tid < RB) {
+    const bool ok = b0 + tid < B;
+    m_s[((T - 1) & 1) * RB + tid] = ok ? (mask[(size_t)(T - 1) * B + b0 + tid] != 0) : 0;
+    m1 = (ok && T - 2 >= 0) ? (mask[(size_t)(T - 2) * B + b0 + tid] != 0) : 0;
+    m2 = (ok && T - 3 >= 0) ? (mask[(size_t)(T - 3) * B + b0 + tid] != 0) : 0;
+  }
+  prefetch_in(T - 1);
   __syncthreads();
 
   for (int t = T - 1; t >= 0; --t) {
     const size_t tok0 = (size_t)t * B + b0;
-    float direct[RB], hp[RB], rr[RB];
-    bool on[RB];
+    const float* ic = in_s + (size_t)(t & 1) * RB * NI * CG;
+    prefetch_in(t - 1);
+    cp_async_wait<1>();                        // this step's inputs (own elements) have landed
     // ---- phase 1 (owners): elementwise gate gradients
+    if (owner) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      direct[r] = 0.f; hp[r] = 0.f; rr[r] = 0.f; on[r] = false;
-      const StepIn in = pre[r];
-      pre[r] = load_step(t - 1, r);            // in flight behind this step's matvec phases
-      if (!owner || b0 + r >= B) continue;
-      const size_t tok = tok0 + r;
-      const bool m = in.m;
-      const float dh = in.dh + dh_carry[r];
-      on[r] = m;
-      if (!m) {
-        direct[r] = dh;                        // masked step: h_t = h_{t-1}, no gate gradient
+      for (int r = 0; r < RB; ++r) {
+        if (b0 + r >= B) continue;
+        const size_t tok = tok0 + r;
+        const bool m = m_s[(t & 1) * RB + r] != 0;
+        const float dh = ic[(r * NI + 0) * CG + c] + dc_s[r * CG + c];
+        if (!m) {
+          dd_s[r * CG + c] = dh;               // masked step: h_t = h_{t-1}, no gate gradient
 #pragma unroll
-        for (int g = 0; g < G; ++g) da_s[(g * RB + r) * KP + c] = 0.f;
-        if (CELL == SEQREC_CELL_GRU) cst[tok * H + c] = 0.f;
-        continue;
-      }
-      if (CELL == SEQREC_CELL_GRU) {
-        const float z = in.g0, rg = in.g1, hh = in.g2;
-        const float hprev = in.hprev;
-        da_s[(0 * RB + r) * KP + c] = dh * (hprev - hh) * hard_sigmoid_grad_from_y(z);
-        da_s[(2 * RB + r) * KP + c] = dh * (1.0f - z) * act_grad_from_y<ACT>(hh);
-        direct[r] = dh * z;
-        hp[r] = hprev;
-        rr[r] = rg;
-        cst[tok * H + c] = rg * hprev;         // operand of dU's candidate block
-      } else {
-        da_s[(0 * RB + r) * KP + c] = dh * act_grad_from_y<ACT>(in.g0);
+          for (int g = 0; g < G; ++g) da_s[(g * RB + r) * KP + c] = 0.f;
+          if (CELL == SEQREC_CELL_GRU) cst[tok * H + c] = 0.f;
+          continue;
+        }
+        if (CELL == SEQREC_CELL_GRU) {
+          const float z = ic[(r * NI + 1) * CG + c], rg = ic[(r * NI + 2) * CG + c], hh = ic[(r * NI + 3) * CG + c];
+          const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
+          da_s[(0 * RB + r) * KP + c] = dh * (hprev - hh) * hard_sigmoid_grad_from_y(z);
+          da_s[(2 * RB + r) * KP + c] = dh * (1.0f - z) * act_grad_from_y<ACT>(hh);
+          dd_s[r * CG + c] = dh * z;
+          cst[tok * H + c] = rg * hprev;       // operand of dU's candidate block
+        } else {
+          da_s[(0 * RB + r) * KP + c] = dh * act_grad_from_y<ACT>(ic[(r * NI + 1) * CG + c]);
+          dd_s[r * CG + c] = 0.f;
+        }
       }
     }
     __syncthreads();
-    if (CELL == SEQREC_CELL_GRU) {
+    if constexpr (CELL == SEQREC_CELL_GRU) {
       // ---- phase 2: d(r*h_{t-1})[c] = sum_j da_h[j] * U[c][2H + j]
       {
-        float acc[RB];
+        float acc[1][RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-        dot_slice<RB, KPT>(acc, da_s + 2 * RB * KP, KP, s * KPT, u[2]);
+        for (int r = 0; r < RB; ++r) acc[0][r] = 0.f;
+        dot_slices<RB, KPT, 1, G>(acc, da_s + 2 * RB * KP, KP, s * KPT, u, 2);
 #pragma unroll
-        for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[r];
+        for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[0][r];
       }
       __syncthreads();
       if (owner) {
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
+          if (b0 + r >= B || m_s[(t & 1) * RB + r] == 0) continue;
           float d_rh = 0.f;
 #pragma unroll
           for (int q = 0; q < KS; ++q) d_rh += part_s[(q * RB + r) * CG + c];
-          if (on[r]) {
-            da_s[(1 * RB + r) * KP + c] = d_rh * hp[r] * hard_sigmoid_grad_from_y(rr[r]);
-            direct[r] += d_rh * rr[r];
-          }
+          const float rg = ic[(r * NI + 2) * CG + c];
+          const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
+          da_s[(1 * RB + r) * KP + c] = d_rh * hprev * hard_sigmoid_grad_from_y(rg);
+          dd_s[r * CG + c] += d_rh * rg;
         }
       }
       __syncthreads();
     }
     // ---- phase 3: dh_{t-1}[c] = direct + sum_j da[j] * U[c][j] over the gates that see h_{t-1} directly
     {
-      constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;
-      float acc[RB];
+      float acc[1][RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+      for (int r = 0; r < RB; ++r) acc[0][r] = 0.f;
 #pragma unroll
-      for (int g = 0; g < G1; ++g) dot_slice<RB, KPT>(acc, da_s + g * RB * KP, KP, s * KPT, u[g]);
+      for (int g = 0; g < G1; ++g) dot_slices<RB, KPT, 1, G>(acc, da_s + g * RB * KP, KP, s * KPT, u, g);
       // phase 2's partials were consumed before the barrier above, so part_s can be reused
 #pragma unroll
-      for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[r];
+      for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[0][r];
     }
     __syncthreads();
     if (owner) {
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         if (b0 + r >= B) continue;
-        float v = direct[r];
+        float v = dd_s[r * CG + c];
 #pragma unroll
         for (int q = 0; q < KS; ++q) v += part_s[(q * RB + r) * CG + c];
-        dh_carry[r] = v;
-        // dxp[t] = da (overwrites the saved gates, already consumed in phase 1)
+        dc_s[r * CG + c] = v;
+        // dxp[t] = da (overwrites the saved gates, already copied to shared memory by the prefetch)
         float* gp = xg + (tok0 + r) * GH;
 #pragma unroll
         for (int g = 0; g < G; ++g) gp[g * H + c] = da_s[(g * RB + r) * KP + c];
       }
     }
+    if (tid < RB) {
+      m_s[((t - 1) & 1) * RB + tid] = m1;
+      m1 = m2;
+      m2 = (b0 + tid < B && t - 3 >= 0) ? (mask[(size_t)(t - 3) * B + b0 + tid] != 0) : 0;
+    }
     __syncthreads();
   }
+  cp_async_wait<0>();
 }
 
 template <int CELL, int ACT, int RB, int KPT>
 int launch_pair(bool fwd, float* xg, const float* U, const uint8_t* mask, float* hout, float* cst, const float* dhout,
                 int T, int B, int H, cudaStream_t st) {
   constexpr int G = Gates<CELL>::G;
+  constexpr int NI = (CELL == SEQREC_CELL_GRU) ? 5 : 2;
   const int CG = (H + 31) / 32 * 32;
   const int threads = KS * CG;
   const int grid = ceil_div(B, RB);
   constexpr int KP = KS * KPT;
   if (fwd) {
-    const size_t smem = sizeof(float) * (size_t)(2 * RB * KP + KS * RB * G * CG);
-    rnn_forward_reg_kernel<CELL, ACT, RB, KPT><<<grid, threads, smem, st>>>(xg, U, mask, hout, T, B, H);
+    const size_t smem = sizeof(float) * (size_t)(2 * RB * KP + KS * RB * G * CG + 2 * RB * G * CG + RB * 2 * CG) +
+                        sizeof(int) * 2 * RB;
+    auto k = rnn_forward_reg_kernel<CELL, ACT, RB, KPT>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return -(int)e;
+    }
+    k<<<grid, threads, smem, st>>>(xg, U, mask, hout, T, B, H);
   } else {
-    const size_t smem = sizeof(float) * (size_t)(G * RB * KP + KS * RB * CG);
-    rnn_backward_reg_kernel<CELL, ACT, RB, KPT><<<grid, threads, smem, st>>>(xg, U, mask, hout, cst, dhout, T, B, H);
+    const size_t smem = sizeof(float) * (size_t)(G * RB * KP + KS * RB * CG + 2 * RB * NI * CG + 2 * RB * CG) +
+                        sizeof(int) * 2 * RB;
+    auto k = rnn_backward_reg_kernel<CELL, ACT, RB, KPT>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return -(int)e;
+    }
+    k<<<grid, threads, smem, st>>>(xg, U, mask, hout, cst, dhout, T, B, H);
   }
   SEQREC_CHECK_LAUNCH();
   return 0;
