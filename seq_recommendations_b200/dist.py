@@ -41,6 +41,13 @@ class Comm:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
+    def reduce_scatter_sum(self, out, inp):
+        """out (n, ...) = sum over ranks of this rank's block of inp (world*n, ...)."""
+        if not self.enabled:
+            out.copy_(inp)
+            return
+        dist.reduce_scatter_tensor(out, inp.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+
     def barrier(self):
         if self.enabled:
             dist.barrier(group=self.group)

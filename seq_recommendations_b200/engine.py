@@ -86,7 +86,7 @@ class _Work:
 
 class HotPath:
     def __init__(self, cell, act, in_dim, hidden, n_items, out_bias=False, input_kind="ids", weights=None,
-                 device=None, comm=None, seed=0, tc="x3"):
+                 device=None, comm=None, seed=0, tc="x3", vocab_parallel=False):
         if not torch.cuda.is_available():
             raise _lib.SeqrecError("seq_recommendations_b200 needs a CUDA device (sm_100a); there is no CPU path")
         _lib.load()
@@ -104,6 +104,17 @@ class HotPath:
         self.out_bias = bool(out_bias)
         self.input_kind = input_kind
         self.comm = comm if comm is not None else Comm()
+        # Vocabulary-parallel logits (large catalogs): W_out / b_out are column-sharded, every rank
+        # scores ALL ranks' tokens against its V/P items; the recurrent part stays data parallel.  self.V is the
+        # LOCAL item count from here on, self.V_total the catalog size, self.v_lo the first local item.
+        self.V_total = self.V
+        self.v_lo = 0
+        self.vocab_parallel = bool(vocab_parallel) and self.comm.enabled
+        if self.vocab_parallel:
+            if self.V_total % self.comm.world:
+                raise ValueError("vocab_parallel needs n_items divisible by the number of ranks")
+            self.V = self.V_total // self.comm.world
+            self.v_lo = self.comm.rank * self.V
         self.dropout_in = 0.0
         self.dropout_out = 0.0
         self.seed = int(seed)
@@ -225,13 +236,24 @@ class HotPath:
         return ws
 
     def get_weights(self):
-        """Keras `get_weights()` order: [W_in, U, b, W_out (, b_out)] as float32 numpy arrays."""
-        return [w.detach().cpu().numpy().copy() for w in self.weight_list()]
+        """Keras `get_weights()` order: [W_in, U, b, W_out (, b_out)] as float32 numpy arrays (full catalog width: the
+        column shards of a vocabulary-parallel model are gathered)."""
+        out = []
+        for i, w in enumerate(self.weight_list()):
+            if self.vocab_parallel and i >= 3:
+                full = self.comm.all_gather_cat(w.detach().t().contiguous() if w.dim() == 2 else w.detach())
+                w = full.t() if w.dim() == 2 else full
+            out.append(w.detach().cpu().numpy().copy())
+        return out
 
     def set_weights(self, weights):
         ws = self.weight_list()
         if len(weights) != len(ws):
             raise ValueError("expected %d weight arrays, got %d" % (len(ws), len(weights)))
+        if self.vocab_parallel:
+            weights = list(weights)
+            for i in range(3, len(weights)):
+                weights[i] = np.asarray(weights[i])[..., self.v_lo:self.v_lo + self.V]
         for dst, src in zip(ws, weights):
             src = np.asarray(src, dtype=np.float32)
             if tuple(src.shape) != tuple(dst.shape):
@@ -321,6 +343,12 @@ class HotPath:
             w.hscale = self._dropout((w.N, self.H), self.dropout_out)
 
     def _forward_ce(self, w, with_targets=True, training=False):
+        n_splits = self._ce_partials(w, with_targets, training)
+        self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets)
+
+    def _ce_partials(self, w, with_targets=True, training=False):
+        """Logits kernels only: per-token partial (max, sum-exp) rows in w.ws_m / w.ws_s and the target logit in w.zy.
+        Returns the number of partial rows."""
         st = self.stream
         if w.tc["fwd"]:
             self._mark("stage_operands")
@@ -343,8 +371,11 @@ class HotPath:
             call("seqrec_ce_forward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
                  ptr(w.tgt) if with_targets else None, ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy), w.N, self.H, self.V, 0,
                  self.V, self.V, n_splits, 0, st)
-        call("seqrec_ce_finalize", ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
-             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, st)
+        return n_splits
+
+    def _finalize_ce(self, w, ws_m, ws_s, n_splits, with_targets=True):
+        call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
+             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
         self._mark("misc")
 
     def _backward_ce(self, w):
@@ -366,6 +397,11 @@ class HotPath:
         w = self.work(int(B), int(T))
         self._stage(w, ids, tgt, x_dense)
         self._forward_hidden(w, training=False)
+        if self.vocab_parallel:
+            # loss_sum already covers every rank's tokens: report this rank's share so callers can all-reduce as usual
+            wg = self._vp_forward(w, training=False)
+            lo = self.comm.rank * w.N
+            return wg.ce[lo:lo + w.N].sum().reshape(1), w.n_valid_i.to(torch.float32)
         self._forward_ce(w)
         return w.loss_sum.clone(), w.n_valid_i.to(torch.float32)
 
@@ -374,6 +410,8 @@ class HotPath:
         one-element device tensor (no host sync)."""
         if self.opt is None:
             raise _lib.SeqrecError("compile_model / set_optimizer must be called before training")
+        if self.vocab_parallel:
+            return self._train_batch_vp(ids, tgt, x_dense)
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         st = self.stream
@@ -393,18 +431,17 @@ class HotPath:
         self.flat_g.zero_()
         self._mark("ce_bwd")
         self._backward_ce(w)
+        # data parallel: dW_out / db_out are final here -- their all-reduce runs on NCCL's stream behind the recurrent
+        # backward pass; the (small) dU / db reduction follows the weight-gradient GEMM
+        (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
+        head = o_b + s_b
+        pending = [comm.all_reduce_sum(self.flat_g[head:], async_op=True)] if comm.enabled else []
         self._mark("rnn_bwd")
         if self._needs_ut:
             call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
         call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
              ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
-        self._mark("rnn_wgrad")
-        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
-             w.T, w.B, self.H, st)
-        self._mark("allreduce")
-        comm.all_reduce_sum(self.flat_g)
-
-        # ---- input-kernel gradient
+        # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs
         self._mark("scatter")
         self.n_rows.zero_()
         if w.x_dense is None:
@@ -414,7 +451,7 @@ class HotPath:
             elif embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense":
                 call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                      ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
-                comm.all_reduce_sum(self.dW_in)
+                pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
                 all_ids = comm.all_gather_cat(w.ids.view(-1))
                 call("seqrec_mark_rows", ptr(all_ids), None, ptr(self.touched), ptr(self.rows), ptr(self.n_rows),
                      all_ids.numel(), self.F, st)
@@ -429,13 +466,101 @@ class HotPath:
         else:
             self.dW_in.zero_()
             call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
-            comm.all_reduce_sum(self.dW_in)
+            if comm.enabled:
+                pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
+        self._mark("rnn_wgrad")
+        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
+             w.T, w.B, self.H, st)
+        self._mark("allreduce")
+        if comm.enabled:
+            pending.append(comm.all_reduce_sum(self.flat_g[:head], async_op=True))
 
-        # ---- global-norm clip + Adagrad
+        # ---- global-norm clip + Adagrad (needs every reduced gradient: clipnorm is global)
+        for h in pending:
+            if h is not None:
+                h.wait()
         self._mark("optim")
         self._apply_update(w)
         self._w_version += 1
         self._mark("end")
+        return loss
+
+    # ------------------------------------------------------------------------------------------------ vocabulary parallel
+    def _vp_forward(self, w, training):
+        """Shared by training and evaluation: every rank scores ALL ranks' tokens against its item shard, then the
+        per-token (max, sum-exp) partials and the target logit are merged across ranks.  Returns the work object that
+        holds the global-token buffers (token order: rank-major blocks of each rank's time-major tokens)."""
+        comm = self.comm
+        wg = self.work(w.B * comm.world, w.T)
+        hs = w.hout.view(w.N, self.H)
+        if w.hscale is not None:
+            hs = hs * w.hscale
+        wg.hout.view(wg.N, self.H).copy_(comm.all_gather_cat(hs))
+        wg.hscale = None
+        tgt_all = comm.all_gather_cat(w.tgt.view(-1))
+        wg.mask.view(-1).copy_(comm.all_gather_cat(w.mask.view(-1)))
+        local = (tgt_all >= self.v_lo) & (tgt_all < self.v_lo + self.V)
+        wg.tgt.view(-1).copy_(torch.where(local, tgt_all - self.v_lo, torch.full_like(tgt_all, -1)))
+        wg.zy.zero_()
+        n_splits = self._ce_partials(wg, True, training)
+        # local merge -> (m_r, s_r) per token, exchange, global merge with the owner's target logit
+        call("seqrec_ce_finalize", ptr(wg.ws_m), ptr(wg.ws_s), None, None, ptr(wg.m), ptr(wg.s), None, None, None, None,
+             wg.N, n_splits, self.stream)
+        m_all = comm.all_gather_cat(wg.m)
+        s_all = comm.all_gather_cat(wg.s)
+        comm.all_reduce_sum(wg.zy)
+        self._finalize_ce(wg, m_all, s_all, comm.world, True)
+        return wg
+
+    def _train_batch_vp(self, ids, tgt, x_dense=None):
+        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
+        w = self.work(int(B), int(T))
+        st = self.stream
+        comm = self.comm
+        self._stage(w, ids, tgt, x_dense)
+        n_valid = w.n_valid_i.to(torch.float32)
+        comm.all_reduce_sum(n_valid)
+        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        self._forward_hidden(w, training=True)
+        wg = self._vp_forward(w, training=True)
+        loss = wg.loss_sum * self.inv_nvalid      # identical on every rank: the sum runs over all ranks' tokens
+        # ---- backward: dW_out / db_out of the shard are complete locally; dh is summed over the item shards
+        self.flat_g.zero_()
+        self._backward_ce(wg)
+        comm.reduce_scatter_sum(w.dh.view(w.N, self.H), wg.dh.view(wg.N, self.H))
+        if w.hscale is not None:
+            w.dh.view(w.N, self.H).mul_(w.hscale)
+        if self._needs_ut:
+            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
+             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
+             w.T, w.B, self.H, st)
+        (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
+        head = o_b + s_b
+        comm.all_reduce_sum(self.flat_g[:head])   # replicated recurrent parameters
+        self.n_rows.zero_()
+        all_ids = comm.all_gather_cat(w.ids.view(-1))
+        all_mask = comm.all_gather_cat(w.mask.view(-1))
+        all_dxp = comm.all_gather_cat(w.xg.view(w.N, self.GH))
+        all_scale = comm.all_gather_cat(w.in_scale) if w.in_scale is not None else None
+        call("seqrec_scatter_add_rows", ptr(all_dxp), ptr(all_ids), ptr(all_mask), ptr(all_scale), ptr(self.dW_in),
+             ptr(self.touched), ptr(self.rows), ptr(self.n_rows), all_ids.numel(), self.F, self.GH, st)
+        # ---- global norm: replicated gradients count once, the sharded ones are summed over ranks
+        o = self.opt
+        max_rows = min(self.F, w.N * comm.world)
+        self.sumsq.zero_()
+        if o["clipnorm"] > 0:
+            call("seqrec_sumsq", ptr(self.flat_g[head:]), self.flat_g.numel() - head, ptr(self.sumsq), st)
+            comm.all_reduce_sum(self.sumsq)
+            call("seqrec_sumsq", ptr(self.flat_g[:head]), head, ptr(self.sumsq), st)
+            call("seqrec_sumsq_rows", ptr(self.dW_in), ptr(self.rows), ptr(self.n_rows), self.GH, max_rows,
+                 ptr(self.sumsq), st)
+        call("seqrec_adagrad", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_a), self.flat_p.numel(), o["lr"],
+             o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+        call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows), ptr(self.n_rows),
+             ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+        self._w_version += 1
         return loss
 
     def _segments(self):
@@ -536,6 +661,8 @@ class HotPath:
 
     def predict_batch(self, ids, x_dense=None):
         """model.predict: (B,T,V) float32 softmax probabilities on the device."""
+        if self.vocab_parallel:
+            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)
@@ -548,6 +675,8 @@ class HotPath:
 
     def target_prob_batch(self, ids, tgt, x_dense=None):
         """p(true next item) per step, clipped to [1e-7, 1-1e-7] like model.py:108-110; (B,T) device tensor."""
+        if self.vocab_parallel:
+            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, tgt, x_dense)
@@ -557,6 +686,8 @@ class HotPath:
 
     def topk_batch(self, ids, k, last_step_only=True, x_dense=None):
         """Top-k next items: (B,k) ids and probabilities for the last step, or (B,T,k) for every step."""
+        if self.vocab_parallel:
+            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)

@@ -521,7 +521,7 @@ class RNNFullModel(BaseRNNModel):
                  y_to_z=True,
                  y_to_z_initializer="glorot_normal",
                  y_to_y=True, x_to_y=True, x_to_z=False, z_to_y_dropout=0.0, diag_b=True, y_to_z_dropout=0.0,
-                 z_to_z_dropout=0.0, seed=None, comm=None):
+                 z_to_z_dropout=0.0, seed=None, comm=None, vocab_parallel=False):
         BaseRNNModel.__init__(self, y_dim, model_name=model_name, rnn_type=rnn_type)
         if not (x_to_z or y_to_z):
             raise ValueError("ERROR: the model needs an input into z's! either x or y should be added.")
@@ -539,7 +539,7 @@ class RNNFullModel(BaseRNNModel):
         kinit = y_to_z_initializer if rnn_type == "LSTM" else "glorot_uniform"
         ws = _init_weights(rnn_type, y_dim, z_dim, y_dim, bool(toy_bias), kernel_init=kinit, seed=seed)
         hot = HotPath(rnn_type, z_to_z_activation, y_dim, z_dim, y_dim, out_bias=bool(toy_bias), weights=ws, comm=comm,
-                      seed=0 if seed is None else seed)
+                      seed=0 if seed is None else seed, vocab_parallel=vocab_parallel)
         hot.dropout_in = float(y_to_z_dropout)
         hot.dropout_out = float(z_to_y_dropout)
         rnn_w = ["W_in", "U"] + (["b"] if z_bias else [])

@@ -24,12 +24,14 @@ def main():
     ok = True
     # (V, H, T, B_global, cell): dense dW_in exchange (small V) and row exchange (V*GH > N*GH), TC and SIMT logits
     # (100, ...) and (300, ... B=512) take the dense dW_in all-reduce (V <= N_global); the others the row exchange
-    for V, H, T, B, cell, tc in ((900, 64, 10, 64, "GRU", "x3"), (60000, 32, 4, 48, "LSTM", "off"),
-                                 (100, 32, 6, 30, "GRU", "off"), (300, 64, 8, 512, "GRU", "x3")):
+    # the last two run the vocabulary-parallel logits (W_out column shards, reduce-scattered dh)
+    for V, H, T, B, cell, tc, vp in ((900, 64, 10, 64, "GRU", "x3", False), (60000, 32, 4, 48, "LSTM", "off", False),
+                                     (100, 32, 6, 30, "GRU", "off", False), (300, 64, 8, 512, "GRU", "x3", False),
+                                     (4096, 128, 8, 64, "GRU", "x3", True), (998, 32, 5, 40, "LSTM", "off", True)):
         act = "tanh" if cell == "GRU" else "relu"
         ws = synthetic.make_weights(cell, V, H, seed=3)
         steps = [synthetic.make_batch(V, T, B, seed=50 + s, min_len=1) for s in range(3)]
-        hot = HotPath(cell, act, V, H, V, weights=ws, comm=comm, tc=tc)
+        hot = HotPath(cell, act, V, H, V, weights=ws, comm=comm, tc=tc, vocab_parallel=vp)
         hot.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
         lo, hi = dist.shard_rows(B, comm.rank, comm.world)
         losses = [float(hot.train_batch(i[lo:hi], t[lo:hi]).item()) for i, t in steps]
@@ -43,8 +45,8 @@ def main():
             errs = [rel(a, b) for a, b in zip(mine, ref.get_weights())]
             lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
             good = max(errs) < 2e-5 and lerr < 1e-5
-            print("DP world=%d V=%d %s tc=%s: loss err %.2e, weight errs %s -> %s" % (
-                comm.world, V, cell, tc, lerr, ["%.1e" % e for e in errs], "OK" if good else "MISMATCH"), flush=True)
+            print("DP world=%d V=%d %s tc=%s vocab_parallel=%s: loss err %.2e, weight errs %s -> %s" % (
+                comm.world, V, cell, tc, vp, lerr, ["%.1e" % e for e in errs], "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
         # all ranks must hold identical replicas after the step
         flat = torch.cat([torch.from_numpy(w).reshape(-1) for w in mine]).to(dev)
@@ -56,7 +58,7 @@ def main():
         # gathered rows with atomics in a rank-local order, so replicas may differ in the last bits (bounded here).
         from seq_recommendations_b200.dist import embedding_grad_mode
         G = {"GRU": 3, "LSTM": 4}[cell]
-        dense = embedding_grad_mode(V, G * H, T * (hi - lo) * comm.world) == "dense"
+        dense = (not vp) and embedding_grad_mode(V, G * H, T * (hi - lo) * comm.world) == "dense"
         spread = float(((mx - mn).abs().max() / flat.abs().max()).item())
         if (dense and spread != 0.0) or spread > 1e-6:
             print("rank %d: replicas diverged (dense=%s, spread %.2e)" % (comm.rank, dense, spread), flush=True)
