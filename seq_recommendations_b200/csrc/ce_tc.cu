@@ -432,14 +432,13 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
                          float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end) {
   constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = X3 ? 3 : 6;                          // 32 KB (x3) / 16 KB stages: fills the 227 KB budget
+  constexpr int NS = X3 ? 5 : 10;                         // 32 KB (x3) / 16 KB stages next to the resident A tile
   constexpr int HK = KB * KBLK;
   constexpr int NJ = BN / KBLK;                             // 64-item blocks per tile (K blocks of the dH GEMM)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                                  // [NP][KB][TILE_B]        hout tile (resident)
-  const uint32_t sD = sA + NP * KB * TILE_B;                 // [NP][NJ][TILE_B]        dS tile
-  const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]        Bt / W blocks
+  const uint32_t sB = sA + NP * KB * TILE_B;                 // [NS][NP][TILE_B]        Bt / W blocks
   const uint32_t sBar = sB + NS * NP * TILE_B;
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
                  bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
@@ -470,7 +469,11 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // TMEM columns: [0,256) logits double buffer | [256,384) dH accumulator | [384,448) dS hi | [448,512) dS lo.
+  // dS never touches shared memory: the epilogue packs it to bf16 pairs and tcgen05.st's it as the A operand of the
+  // second GEMM (128 token lanes x 128 items = 64 packed columns per part), halving that GEMM's shared-memory reads.
   const uint32_t tmem_dh = tmem_base + 2 * BN;
+  const uint32_t tmem_ds = tmem_base + 2 * BN + 128;
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- TMA producer
@@ -570,7 +573,22 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
           ptx::tc_fence_after_sync();
           const uint32_t b = sB + p.stage * NP * TILE_B;
-          mma_kblock<X3>(tmem_dh, sD + j * TILE_B, sD + (NJ + j) * TILE_B, b, b + TILE_B, idesc_h, first && j == 0);
+          const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KBLK / 16; ++k) {
+              const uint32_t a_hi = tmem_ds + j * (KBLK / 2) + k * 8, a_lo = a_hi + BN / 2;
+              const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
+              if (X3) {
+                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc_h, acc);
+                ptx::umma_bf16_ts(tmem_dh, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, 1u);
+                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, 1u);
+              } else {
+                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, acc);
+              }
+            }
+          }
+          __syncwarp();
           commit_elect(bar_empty + 8 * p.stage);
           p.advance(NS);
         }
@@ -585,7 +603,6 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const float inv = inv_nvalid[0];
-    uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
     RowTerms rt;
     int tc = 0, seg = -1;
     for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
@@ -601,9 +618,24 @@ ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
       dlogit_half_tile(z, rt, vc0, v_end);
-      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);    // previous tile's dH MMAs are done with the dS buffer
-      store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);
-      ptx::fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core (async proxy)
+      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);    // previous tile's dH MMAs are done with the dS operand
+      ptx::tc_fence_after_sync();
+      {
+        // this thread's 64 dlogits -> 32 packed bf16 pairs (hi) and 32 (lo) at columns [half*32, half*32+32)
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float x0 = z[2 * e], x1 = z[2 * e + 1];
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
+          if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
+        }
+        const uint32_t dst = tmem_ds + ((uint32_t)(q * 32) << 16) + half * 32;
+        ptx::tmem_st_32x32(dst, hi);
+        if (X3) ptx::tmem_st_32x32(dst + BN / 2, lo);
+        ptx::tmem_st_wait();
+      }
+      ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_dfull);
       if (sh.seg_last(w)) {
@@ -978,6 +1010,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
   const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)(x3 ? 3 : 6) * NP * TILE_B + 256;
+  const size_t smem_dh = 1024 + (size_t)NP * KB * TILE_B + (size_t)(x3 ? 5 : 10) * NP * TILE_B + 256;
   const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
   const int grid = persistent_grid(total);
   if (dh) {
@@ -991,9 +1024,9 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
 #define DH(KBV, X3V)                                                                                          \
   {                                                                                                           \
     auto k = ce_tc_backward_dh_kernel<KBV, X3V>;                                                              \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dh);       \
     if (e != cudaSuccess) return -(int)e;                                                                     \
-    k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid, hscale, \
+    k<<<grid, TC_THREADS, smem_dh, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid, hscale, \
                                       dh, n_tokens, H, v_begin, v_end);                                       \
   }
     if (KB == 1) { if (x3) DH(1, true) else DH(1, false) }
