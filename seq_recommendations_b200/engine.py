@@ -65,6 +65,11 @@ class _Work:
         self.hscale = None
         self.in_scale = None
         self.x_dense = None
+        self.pin_event = None
+        self.pin_dirty = False
+        self.graph = None
+        self.graph_calls = 0
+        self.graph_loss = None
         # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
         self.tc = hp._tc_plan(N)
         if self.tc["fwd"]:
@@ -155,6 +160,7 @@ class HotPath:
         self.trainable = {"W_in": True, "U": True, "b": True, "W_out": True, "b_out": True}
         self.opt = None
         self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
+        self.use_graphs = os.environ.get("SEQREC_GRAPHS", "1") == "1"
         # tensor-core logits path: 'x3' = 3-pass bf16 split products (fp32-grade, the default), 'bf16' = single pass,
         # 'off' = exact-fp32 SIMT kernels.  SEQREC_TC overrides.  Small / odd problems always take the SIMT kernels.
         self.tc_mode = os.environ.get("SEQREC_TC", tc)
@@ -274,7 +280,13 @@ class HotPath:
         self.reset_optimizer_state()
 
     # ------------------------------------------------------------------------------------------------ batch ingest
-    def _stage(self, w, ids, tgt, x_dense=None):
+    def _format(self, w, have_t=True):
+        """(B,T) device ids/targets -> time-major ids/targets/mask + valid-token count (the in-graph part of ingest)."""
+        w.n_valid_i.zero_()
+        call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
+             ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, self.stream)
+
+    def _stage(self, w, ids, tgt, x_dense=None, format_now=True):
         """Host (numpy / pinned torch) or device batch -> time-major device buffers.  ids (B,T) int32, pad < 0."""
         st = self.stream
 
@@ -287,20 +299,30 @@ class HotPath:
                 else:
                     dst.copy_(src, non_blocking=True)  # pinned source: async H2D
             else:
+                # the pinned staging buffer is reused every call: wait until the previous asynchronous copy out of it
+                # has really run (with CUDA-graph replay the host can be a whole step ahead of the device)
+                if w.pin_event is not None:
+                    w.pin_event.synchronize()
                 pin.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)))
                 dst.copy_(pin, non_blocking=True)
+                w.pin_dirty = True
             return dst
 
-        w.n_valid_i.zero_()
         w.x_dense = None
         if x_dense is None:
             to_dev(w.ids_bt, w.pin_ids, ids)
             have_t = tgt is not None
             if have_t:
                 to_dev(w.tgt_bt, w.pin_tgt, tgt)
-            call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
-                 ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, st)
+            if w.pin_dirty:
+                w.pin_event = torch.cuda.Event()
+                w.pin_event.record(torch.cuda.current_stream(self.device))
+                w.pin_dirty = False
+            if not format_now:
+                return
+            self._format(w, have_t)
         else:
+            w.n_valid_i.zero_()
             # dense-feature input (RNNBaseline): x_dense (B,T,F) float; mask = any(x != 0) (model.py:246)
             xd = x_dense if isinstance(x_dense, torch.Tensor) else torch.from_numpy(
                 np.ascontiguousarray(x_dense, dtype=np.float32))
@@ -414,10 +436,36 @@ class HotPath:
             return self._train_batch_vp(ids, tgt, x_dense)
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
+        self._mark("ingest")
+        graphable = (self.use_graphs and x_dense is None and self.prof is None and not self.comm.enabled and
+                     self.dropout_in == 0 and self.dropout_out == 0)
+        if not graphable:
+            self._stage(w, ids, tgt, x_dense)
+            return self._train_core(w)
+        # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~45 short launches of a step are
+        # submitted as one graph, which removes the launch gaps between them.  The first step of a (B,T) shape runs
+        # eagerly, the second one captures.
+        self._stage(w, ids, tgt, None, format_now=False)
+        if w.graph is None:
+            w.graph_calls += 1
+            if w.graph_calls < 2:
+                self._format(w)
+                return self._train_core(w)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._format(w)
+                w.graph_loss = self._train_core(w)
+            w.graph = g
+        w.graph.replay()
+        self._w_version += 1
+        return w.graph_loss
+
+    def _train_core(self, w):
+        """forward + backward + exchange + update on the staged batch (everything after the host->device copy)."""
         st = self.stream
         comm = self.comm
-        self._mark("ingest")
-        self._stage(w, ids, tgt, x_dense)
+        self._split_version = -1                  # a training step always follows a weight update: re-stage W_out
         n_valid = w.n_valid_i.to(torch.float32)
         comm.all_reduce_sum(n_valid)
         torch.reciprocal(n_valid, out=self.inv_nvalid)
