@@ -161,6 +161,7 @@ class HotPath:
         self.opt = None
         self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
         self.use_graphs = os.environ.get("SEQREC_GRAPHS", "1") == "1"
+        self.graph_collectives = os.environ.get("SEQREC_GRAPH_COLLECTIVES", "1") == "1"   # capture NCCL calls too
         # tensor-core logits path: 'x3' = 3-pass bf16 split products (fp32-grade, the default), 'bf16' = single pass,
         # 'off' = exact-fp32 SIMT kernels.  SEQREC_TC overrides.  Small / odd problems always take the SIMT kernels.
         self.tc_mode = os.environ.get("SEQREC_TC", tc)
@@ -437,7 +438,8 @@ class HotPath:
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._mark("ingest")
-        graphable = (self.use_graphs and x_dense is None and self.prof is None and not self.comm.enabled and
+        graphable = (self.use_graphs and x_dense is None and self.prof is None and
+                     (not self.comm.enabled or self.graph_collectives) and
                      self.dropout_in == 0 and self.dropout_out == 0)
         if not graphable:
             self._stage(w, ids, tgt, x_dense)
