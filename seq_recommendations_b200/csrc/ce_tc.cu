@@ -896,6 +896,326 @@ ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   }
 }
 
+// ================================================================================================================
+// backward for wide hidden layers (Hk up to 256), ONE kernel template for both gradients.
+//   P = the stationary side (128 rows per tile), Q = the streamed side (128 rows per tile):
+//     ITEM_ST = false: P = tokens, Q = items   ->  out = dh     [n, h] += sum_v dS[n, v] . W_out[h, v]
+//     ITEM_ST = true : P = items,  Q = tokens  ->  out = dW_out [h, v] += sum_n dS^T[v, n] . hs[n, h]
+//   X = stationary operand [P_total, Hk] (A | Bt), resident in shared memory for a whole segment
+//   Y = streamed operand of the logits GEMM [Q_total, Hk] (Bt | A):    S[P, Q] = X . Y^T   (M=128, N=128, K=Hk)
+//   Z = K-major operand of the second GEMM [Hk, Q_total] (W | Ht):     acc[P, Hk] += dS[P, Q] . Z^T
+// The epilogue turns S into dS (rows = lanes = P) and tcgen05.st's it as packed bf16 hi/lo into TENSOR MEMORY, where
+// it is the A operand of the second GEMM (TS-mode MMA) -- dS never occupies shared memory, which is what makes
+// Hk = 256 fit: 128 KB resident X (x3) + 3 stages of 32 KB.  TMEM: S (double buffered only when Hk <= 128) |
+// accumulator (128-column chunks of the hidden axis) | dS hi | dS lo = 512 columns.
+// In the item-stationary variant the per-token softmax terms vary along the COLUMNS of the tile: the epilogue warps
+// stage {-m.log2e, coef/s, coef, target} of the tile's 128 tokens in shared memory and read them as broadcasts.
+template <int KB, bool X3>
+struct TsCfg {
+  static constexpr int NP = X3 ? 2 : 1;
+  static constexpr int NS_RAW = (224 * 1024 - NP * KB * TILE_B) / (NP * TILE_B);
+  static constexpr int NS = NS_RAW > 8 ? 8 : NS_RAW;
+  static constexpr int HK = KB * KBLK;
+  static constexpr int NC = (HK + 127) / 128;               // 128-wide hidden chunks of the second GEMM
+  static constexpr int ACC_COLS = NC * 128;
+  static constexpr int SBUF = (2 * BN + ACC_COLS + BN <= 512) ? 2 : 1;
+  static constexpr uint32_t TERMS_B = 128 * 16;             // per-token terms of one streamed tile (ITEM_ST)
+  static constexpr uint32_t SMEM_NEED = NP * KB * TILE_B + NS * NP * TILE_B + TERMS_B + 256;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int KB, bool X3, bool ITEM_ST>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                         const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                         const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant__ CUtensorMap tmZ_lo,
+                         const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
+                         const float* __restrict__ srow, const float* __restrict__ coef,
+                         const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
+                         float* __restrict__ out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
+                         uint32_t smem_bytes) {
+  using C = TsCfg<KB, X3>;
+  constexpr int NP = C::NP, NS = C::NS, NC = C::NC, SBUF = C::SBUF;
+  constexpr int NJ = BN / KBLK;                             // 64-wide K blocks of the second GEMM per tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sX = base;                                  // [NP][KB][TILE_B]   stationary operand
+  const uint32_t sB = sX + NP * KB * TILE_B;                 // [NS][NP][TILE_B]   Y / Z blocks
+  const uint32_t sT = sB + NS * NP * TILE_B;                 // float4[128]        per-token terms (ITEM_ST)
+  const uint32_t sBar = sT + C::TERMS_B;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
+                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && base - ptx::smem_u32(smem_raw) + C::SMEM_NEED > smem_bytes) {
+    printf("seqrec_b200: ce_tc_backward_ts shared-memory layout does not fit (%u needed)\n", C::SMEM_NEED);
+    __trap();
+  }
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int n_ttiles = (int)((n_tokens + BM - 1) / BM);
+  const int64_t total = (int64_t)n_vtiles * n_ttiles;
+  const Share sh(total, ITEM_ST ? n_ttiles : n_vtiles);
+  // first row of the stationary / streamed operand of work item w
+  auto p_row0 = [&](int64_t w) { return ITEM_ST ? v_begin + sh.outer(w) * BN : sh.outer(w) * BM; };
+  auto q_row0 = [&](int64_t w) { return ITEM_ST ? sh.inner(w) * BM : v_begin + sh.inner(w) * BN; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
+    ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_afree, 1);
+    ptx::mbar_init(bar_dfull, N_EPI_WARPS);
+    ptx::mbar_init(bar_dempty, 1);
+    ptx::mbar_init(bar_hfull, 1);
+    ptx::mbar_init(bar_hempty, N_EPI_WARPS);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_acc = tmem_base + SBUF * BN;
+  const uint32_t tmem_ds = tmem_acc + C::ACC_COLS;           // 64 packed columns hi, then 64 lo
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    // stage order = the MMA warp's consumption order: Y(w0), then per work item w: Y(w+1), Z(w)
+    if (sh.w0 < sh.w1) {
+      if (lane == 0) { ptx::prefetch_tmap(&tmX_hi); ptx::prefetch_tmap(&tmY_hi); ptx::prefetch_tmap(&tmZ_hi); }
+      Pipe p;
+      int seg = 0;
+      auto load_s_operands = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+          const int row0 = p_row0(w);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
+            for (int kb = 0; kb < KB; ++kb) {
+              ptx::tma_load_2d(sX + kb * TILE_B, &tmX_hi, bar_a, kb * KBLK, row0);
+              if (X3) ptx::tma_load_2d(sX + (KB + kb) * TILE_B, &tmX_lo, bar_a, kb * KBLK, row0);
+            }
+          }
+          ++seg;
+        }
+        const int q0 = q_row0(w);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+            const uint32_t dst = sB + p.stage * NP * TILE_B;
+            ptx::tma_load_2d(dst, &tmY_hi, bar_full + 8 * p.stage, kb * KBLK, q0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmY_lo, bar_full + 8 * p.stage, kb * KBLK, q0);
+          }
+          p.advance(NS);
+        }
+      };
+      auto load_z = [&](int64_t w) {
+        const int q0 = q_row0(w);
+        for (int j = 0; j < NJ; ++j)
+          for (int c = 0; c < NC; ++c) {
+            ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // rows >= Hk arrive as zeros
+              const uint32_t dst = sB + p.stage * NP * TILE_B;
+              ptx::tma_load_2d(dst, &tmZ_hi, bar_full + 8 * p.stage, q0 + j * KBLK, c * 128);
+              if (X3) ptx::tma_load_2d(dst + TILE_B, &tmZ_lo, bar_full + 8 * p.stage, q0 + j * KBLK, c * 128);
+            }
+            p.advance(NS);
+          }
+      };
+      load_s_operands(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) load_s_operands(w + 1);
+        load_z(w);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (sh.w0 < sh.w1) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+      Pipe p;
+      int seg_s = -1, tc_s = 0, seg_d = -1, tc_d = 0;
+      auto issue_s = [&](int64_t w) {
+        if (sh.seg_first(w)) {
+          ++seg_s;
+          ptx::mbar_wait(bar_a, seg_s & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int buf = tc_s % SBUF;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s / SBUF) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t b = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(d, sX + kb * TILE_B, sX + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
+          commit_elect(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        commit_elect(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) commit_elect(bar_afree);
+        ++tc_s;
+      };
+      issue_s(sh.w0);
+      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1) issue_s(w + 1);
+        const bool first = sh.seg_first(w);
+        if (first) {
+          if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
+            ptx::mbar_wait(bar_hempty, seg_d & 1);
+            ptx::tc_fence_after_sync();
+          }
+          ++seg_d;
+        }
+        ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in tensor memory
+        ptx::tc_fence_after_sync();
+        for (int j = 0; j < NJ; ++j)
+          for (int c = 0; c < NC; ++c) {
+            ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t b = sB + p.stage * NP * TILE_B;
+            const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
+            const uint32_t d = tmem_acc + c * 128;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k) {
+                const uint32_t a_hi = tmem_ds + j * (KBLK / 2) + k * 8, a_lo = a_hi + BN / 2;
+                const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
+                if (X3) {
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc, acc);
+                  ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+                } else {
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, acc);
+                }
+              }
+            }
+            __syncwarp();
+            commit_elect(bar_empty + 8 * p.stage);
+            p.advance(NS);
+          }
+        commit_elect(bar_dempty);                           // the dS columns may be overwritten
+        if (sh.seg_last(w)) commit_elect(bar_hfull);
+        ++tc_d;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int e = threadIdx.x - 64;                          // 0..255 among the epilogue threads
+    const float inv = inv_nvalid[0];
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float4* sT_gen = reinterpret_cast<float4*>(smem_raw + (sT - ptx::smem_u32(smem_raw)));
+    RowTerms rt;                                             // !ITEM_ST: this thread's token row; ITEM_ST: prefetch
+    int tc = 0, seg = -1;
+    if (ITEM_ST && sh.w0 < sh.w1) {
+      if (e < 128) {
+        rt = load_row_terms((int64_t)sh.inner(sh.w0) * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
+        sT_gen[e] = make_float4(rt.nb, rt.scale, rt.cf, __int_as_float(rt.tg));
+      }
+      epi_bar_sync();
+    }
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc % SBUF;
+      if (sh.seg_first(w)) {
+        ++seg;
+        if (!ITEM_ST) rt = load_row_terms((int64_t)sh.outer(w) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+      }
+      if (ITEM_ST && e < 128 && w + 1 < sh.w1)               // next tile's token terms, behind this tile's math
+        rt = load_row_terms((int64_t)sh.inner(w + 1) * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc / SBUF) & 1);
+      ptx::tc_fence_after_sync();
+      float z[64];
+      load_half_tile(tmem_base + lane_off + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      if (!ITEM_ST) {
+        dlogit_half_tile(z, rt, v_begin + sh.inner(w) * BN + half * 64, v_end);
+      } else {
+        const int v = v_begin + sh.outer(w) * BN + row;      // this thread's item
+        const bool row_ok = v < v_end;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float4 t = sT_gen[half * 64 + j];            // {-m.log2e, coef/s, coef, target} of token column j
+          float x = ptx::ex2_approx(fmaf(z[j], LOG2E, t.x)) * t.y;
+          if (__float_as_int(t.w) == v) x -= t.z;
+          z[j] = row_ok ? x : 0.f;
+        }
+      }
+      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);              // the previous tile's second GEMM has consumed dS
+      ptx::tc_fence_after_sync();
+      {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x0 = z[2 * i], x1 = z[2 * i + 1];
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&hv);
+          if (X3) lo[i] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
+        }
+        const uint32_t dst = tmem_ds + lane_off + half * 32;
+        ptx::tmem_st_32x32(dst, hi);
+        if (X3) ptx::tmem_st_32x32(dst + BN / 2, lo);
+        ptx::tmem_st_wait();
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_dfull);
+      if (ITEM_ST && w + 1 < sh.w1) {
+        epi_bar_sync();                                      // every epilogue thread has read this tile's terms
+        if (e < 128) sT_gen[e] = make_float4(rt.nb, rt.scale, rt.cf, __int_as_float(rt.tg));
+        epi_bar_sync();
+      }
+      if (sh.seg_last(w)) {
+        ptx::mbar_wait(bar_hfull, seg & 1);
+        ptx::tc_fence_after_sync();
+        const int h0 = half * (C::ACC_COLS / 2);             // this warp's hidden columns of its 32 rows
+        if (!ITEM_ST) {
+          const int64_t n = (int64_t)sh.outer(w) * BM + row;
+          flush_acc_red(tmem_acc + lane_off + h0, C::ACC_COLS / 2, out + n * H + h0, H - h0, n < n_tokens,
+                        (H & 3) == 0, hscale ? hscale + n * H + h0 : nullptr);
+        } else {
+          const int v = v_begin + sh.outer(w) * BN + row;
+          const bool row_ok = v < v_end;
+#pragma unroll 1
+          for (int c = 0; c < C::ACC_COLS / 2; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(tmem_acc + lane_off + h0 + c, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int h = h0 + c + j;                    // lanes = consecutive items: coalesced reductions
+                if (h < H) atomicAdd(out + (size_t)h * ldw + v, __uint_as_float(r[j]));
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_hempty);
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // exact fp32 target logit: zy[n] = sum_h hs[n,h] * W_out[h, tgt[n]] (+ b_out[tgt[n]]); one warp per token
 __global__ void __launch_bounds__(256)
 target_logit_kernel(const float* __restrict__ hout, const float* __restrict__ hscale,
@@ -941,6 +1261,46 @@ int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorM
                                                       v_end, forward_slots(n_tokens, v_begin, v_end));
   SEQREC_CHECK_LAUNCH();
   return 0;
+}
+
+template <int KB, bool X3, bool ITEM_ST>
+int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
+                  const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo, const int32_t* tgt,
+                  const float* m, const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
+                  float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw, cudaStream_t st) {
+  using C = TsCfg<KB, X3>;
+  size_t smem = (size_t)C::SMEM_NEED + 1024;                 // slack for the 1024-byte alignment of the tiles
+  if (smem > 227 * 1024) smem = 227 * 1024;                  // (the kernel traps if the aligned layout does not fit)
+  auto k = ce_tc_backward_ts_kernel<KB, X3, ITEM_ST>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  k<<<grid, TC_THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
+                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_ts(int KB, bool x3, bool item_st, int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo,
+              const CUtensorMap& y_hi, const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo,
+              const int32_t* tgt, const float* m, const float* s, const float* coef, const float* inv_nvalid,
+              const float* hscale, float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
+              cudaStream_t st) {
+#define TS3(KBV, X3V, ISV)                                                                                         \
+  return launch_ts_one<KBV, X3V, ISV>(grid, x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, \
+                                      out, n_tokens, H, v_begin, v_end, ldw, st)
+#define TS2(KBV)                                                         \
+  {                                                                      \
+    if (x3) { if (item_st) TS3(KBV, true, true); else TS3(KBV, true, false); }     \
+    else    { if (item_st) TS3(KBV, false, true); else TS3(KBV, false, false); }   \
+  }
+  switch (KB) {
+    case 1: TS2(1)
+    case 2: TS2(2)
+    case 3: TS2(3)
+    default: TS2(4)
+  }
+#undef TS2
+#undef TS3
 }
 
 }  // namespace
@@ -998,7 +1358,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
                                      int64_t Np, int v_begin, int v_end, int ldw, int accumulate_dh, int x3,
                                      void* stream) {
   SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
-  SEQREC_ARG((Hk == 64 || Hk == 128) && H <= Hk, 2);
+  SEQREC_ARG((Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256) && H <= Hk, 2);
   SEQREC_ARG(Vp >= V && Vp % 8 == 0 && Np >= n_tokens && Np % 8 == 0 && ldw >= v_end, 3);
   cudaStream_t st = as_stream(stream);
   CUtensorMap a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, t_hi, t_lo;
@@ -1009,6 +1369,32 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
+  // Hk > 128: the unified kernel with dS in tensor memory (SEQREC_CE_BWD_TS=1 routes the narrow shapes there too, so
+  // the two implementations can be compared on the same problem)
+  static const bool force_ts = [] { const char* e = getenv("SEQREC_CE_BWD_TS"); return e && e[0] == '1'; }();
+  if (KB > 2 || force_ts) {
+    const int64_t total_ts = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+    const int grid_ts = persistent_grid(total_ts);
+    if (dh) {
+      if (!accumulate_dh) {
+        cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)n_tokens * H, st);
+        if (e != cudaSuccess) return -(int)e;
+      }
+      if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
+      if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
+      if ((rc = launch_ts(KB, x3 != 0, false, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
+                          hscale, dh, n_tokens, H, v_begin, v_end, ldw, st)))
+        return rc;
+    }
+    if (dW_out) {
+      if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
+      if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
+      if ((rc = launch_ts(KB, x3 != 0, true, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
+                          nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, st)))
+        return rc;
+    }
+    return 0;
+  }
   const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)(x3 ? 3 : 6) * NP * TILE_B + 256;
   const size_t smem_dh = 1024 + (size_t)NP * KB * TILE_B + (size_t)(x3 ? 5 : 10) * NP * TILE_B + 256;
   const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);

@@ -205,7 +205,7 @@ class HotPath:
     def _tc_plan(self, N):
         """Which logits kernels serve a batch of N tokens."""
         fwd = (self.tc_mode != "off" and self.Hk <= 256 and self.V >= 256 and N >= 128)
-        bwd = fwd and self.Hk <= 128 and not self.out_bias
+        bwd = fwd and not self.out_bias
         splits = _lib.load().seqrec_ce_tc_partials(N, 0, self.V) if fwd else 0   # partial rows the TC forward writes
         return dict(fwd=fwd, bwd=bwd, splits=splits)
 
