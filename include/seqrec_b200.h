@@ -77,6 +77,14 @@ int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const floa
 /* 1 when seqrec_rnn_backward reads Ut for this (cell, H); 0 when the register-resident scan (GRU / SimpleRNN with
  * H <= 128, U held in registers for all T steps) serves it from U and Ut may be NULL */
 int seqrec_rnn_needs_ut(int cell, int H);
+/* ---- K3 on the tcgen05 tensor cores (csrc/rnn_tc.cu): same contract as seqrec_rnn_forward for LSTM / GRU with
+ * H = 128 or 256.  A cluster of H/32 CTAs owns 64 batch rows for all T steps; each CTA keeps its slice of the
+ * recurrent kernel in shared memory as a bf16 hi/lo operand (3-pass split products, fp32 accumulate in TMEM) and the
+ * new hidden state is all-gathered through distributed shared memory every step.
+ * Ut_hi / Ut_lo = seqrec_split_bf16(U, transpose = 1): U^T (G*H, H) as bf16 hi / lo, leading dimension H. */
+int seqrec_rnn_tc_applicable(int cell, int H);
+int seqrec_rnn_tc_forward(int cell, int act, float* xg, const uint16_t* Ut_hi, const uint16_t* Ut_lo,
+                          const uint8_t* mask, float* hout, float* cst, int T, int B, int H, void* stream);
 /* dU (H,G*H) += sum_t hprev_t^T . dxp_t (GRU candidate block uses cst = r*hprev);  db (G*H) += sum_n dxp[n,:].
  * dU and db must be pre-zeroed. */
 int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,

@@ -19,6 +19,7 @@
 // Tiles: 128 tokens x 128 items; K (= hidden, padded to 64) is walked in 64-element blocks (one 128-byte swizzle row).
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -31,36 +32,9 @@ constexpr int N_EPI_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ---- host: TMA descriptors --------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-      q != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
 // bf16 matrix (rows, cols) with leading dimension ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
-// Out-of-bounds elements are filled with zeros by the TMA unit.
 int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return -1030;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return -1031;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {KBLK, box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -1032;
+  return tma::make_2d_bf16(m, ptr, rows, cols, ld, KBLK, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // ---- device helpers ---------------------------------------------------------------------------------------------

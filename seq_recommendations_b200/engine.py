@@ -152,6 +152,15 @@ class HotPath:
         self.aW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
         self.Ut = torch.empty((self.GH, self.H), dtype=f32, device=dev)
         self._needs_ut = _lib.load().seqrec_rnn_needs_ut(CELL[cell], self.H) != 0
+        # tensor-core recurrent scan (csrc/rnn_tc.cu): LSTM / GRU with H in {128, 256}.  The register-resident SIMT scan
+        # stays the default for GRU-128 (2 us per step already); SEQREC_RNN_TC=1 / 0 forces / disables it.
+        lib = _lib.load()
+        tc_ok = lib.seqrec_rnn_tc_applicable(CELL[cell], self.H) != 0
+        env = os.environ.get("SEQREC_RNN_TC", "")
+        self.rnn_tc = tc_ok and (env == "1" or (env != "0" and (self.H > 128 or cell == "LSTM")))
+        if tc_ok:
+            self.Ut_hi = torch.empty((self.GH, self.H), dtype=torch.bfloat16, device=dev)
+            self.Ut_lo = torch.empty((self.GH, self.H), dtype=torch.bfloat16, device=dev)
         self.touched = torch.zeros(self.F, dtype=torch.int32, device=dev)
         self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
         self.n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -359,8 +368,14 @@ class HotPath:
         else:
             call("seqrec_gemm_nn", ptr(w.x_dense), ptr(self.W_in), ptr(self.b), ptr(w.xg), w.N, self.GH, self.F, 0, st)
         self._mark("rnn_fwd")
-        call("seqrec_rnn_forward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(w.mask), ptr(w.hout),
-             ptr(w.cst), w.T, w.B, self.H, st)
+        if self.rnn_tc:
+            call("seqrec_split_bf16", ptr(self.U), None, ptr(self.Ut_hi), ptr(self.Ut_lo), self.H, self.GH, self.H, 1,
+                 st)
+            call("seqrec_rnn_tc_forward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut_hi), ptr(self.Ut_lo),
+                 ptr(w.mask), ptr(w.hout), ptr(w.cst), w.T, w.B, self.H, st)
+        else:
+            call("seqrec_rnn_forward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(w.mask),
+                 ptr(w.hout), ptr(w.cst), w.T, w.B, self.H, st)
         self._mark("misc")
         if training and self.dropout_out > 0:
             w.hscale = self._dropout((w.N, self.H), self.dropout_out)
