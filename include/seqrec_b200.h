@@ -85,6 +85,12 @@ int seqrec_rnn_needs_ut(int cell, int H);
 int seqrec_rnn_tc_applicable(int cell, int H);
 int seqrec_rnn_tc_forward(int cell, int act, float* xg, const uint16_t* Ut_hi, const uint16_t* Ut_lo,
                           const uint8_t* mask, float* hout, float* cst, int T, int B, int H, void* stream);
+/* K4 on the tensor cores, same contract as seqrec_rnn_backward: each CTA forms the K-split partial product of ITS gate
+ * columns with U[:, cols] (bf16 hi/lo, resident in shared memory) and dL/dh_{t-1} is reduce-scattered through
+ * distributed shared memory.  U_hi / U_lo = seqrec_split_bf16(U, transpose = 0): (H, G*H), leading dimension G*H. */
+int seqrec_rnn_tc_backward(int cell, int act, float* xg, const uint16_t* U_hi, const uint16_t* U_lo,
+                           const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T, int B, int H,
+                           void* stream);
 /* dU (H,G*H) += sum_t hprev_t^T . dxp_t (GRU candidate block uses cst = r*hprev);  db (G*H) += sum_n dxp[n,:].
  * dU and db must be pre-zeroed. */
 int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,

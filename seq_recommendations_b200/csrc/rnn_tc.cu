@@ -31,6 +31,13 @@ constexpr int UPC = 32;          // hidden units per CTA
 constexpr int RT_THREADS = 192;  // warps 0-3 epilogue (TMEM lane quadrants), warp 4 TMA + MMA, warp 5 exchange
 constexpr float RT_LOG2E = 1.4426950408889634f;
 
+// optional timeline capture (scripts/time_rnn.py): CTA 0 stores clock64() at the protocol points of the first rounds
+long long* g_rnn_tc_dbg = nullptr;
+#define RT_DBG(round, slot)                                                                   \
+  do {                                                                                        \
+    if (dbg && blockIdx.x == 0 && (round) < 64) dbg[(round) * 8 + (slot)] = clock64();        \
+  } while (0)
+
 // tanh through ex2.approx / fast division: absolute error ~2e-7 (fp32 rounding level); tanhf costs ~5x more on the
 // sequential path
 template <int ACT>
@@ -111,7 +118,7 @@ template <int CELL, int ACT, int CS>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_constant__ CUtensorMap tmU_lo,
                       float* __restrict__ xg, const uint8_t* __restrict__ mask, float* __restrict__ hout,
-                      float* __restrict__ cst, int T, int B) {
+                      float* __restrict__ cst, int T, int B, long long* __restrict__ dbg) {
   using C = FwdCfg<CELL, CS>;
   constexpr int H = C::H, G = C::G, GH = G * H, RPS = C::RPS, KB = C::KB;
   constexpr bool LSTM = CELL == SEQREC_CELL_LSTM;
@@ -176,6 +183,7 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
     for (int r = 0; r < R; ++r) {
       if (r > 0) {
         ptx::mbar_wait_cluster(bar_hfull, (uint32_t)(r - 1) & 1u);      // all CS slices of the operand have landed
+        if (lane == 0) RT_DBG(r, 0);
         if (r < R - 1 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar_hfull, 2 * C::H_PART);
         __syncwarp();
       }
@@ -186,21 +194,26 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
       const uint32_t ureg = sU + (sub_b ? C::UA_BYTES : 0u);
       const uint32_t idesc = ptx::umma_idesc_bf16(BMR, nh);
       if (ptx::elect_one()) {
+        // descriptor bases once per round; every MMA then needs one 32-bit add per operand (the address field never
+        // carries out of its 14 bits), so the single issuing thread keeps up with the tensor pipe
+        const uint64_t a_hi0 = ptx::umma_desc_k_sw64(sH), a_lo0 = ptx::umma_desc_k_sw64(sH + C::H_PART);
+        const uint64_t b_hi0 = ptx::umma_desc_k_sw128(ureg), b_lo0 = ptx::umma_desc_k_sw128(ureg + C::U_PART);
+#pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t d = tmem_base + ((uint32_t)(hh * 16) << 16);  // second M=64 atom on lanes 16..31 of each quadrant
-#pragma unroll 4
+          const uint32_t bh = (uint32_t)(hh * nh) * 8u;                // (hh * nh rows * 128 B) >> 4
+          const uint32_t kstride = (uint32_t)nr * 8u;                  // one K block of the U region, >> 4
+#pragma unroll
           for (int s = 0; s < H / 16; ++s) {
-            const uint32_t a_off = (uint32_t)(s >> 1) * 4096u + (uint32_t)(s & 1) * 32u;
-            const uint32_t b_off = (uint32_t)((s >> 2) * nr + hh * nh) * 128u + (uint32_t)(s & 3) * 32u;
-            const uint64_t a_hi = ptx::umma_desc_k_sw64(sH + a_off), a_lo = ptx::umma_desc_k_sw64(sH + C::H_PART + a_off);
-            const uint64_t b_hi = ptx::umma_desc_k_sw128(ureg + b_off),
-                           b_lo = ptx::umma_desc_k_sw128(ureg + C::U_PART + b_off);
-            ptx::umma_bf16(d, a_hi, b_lo, idesc, s > 0 ? 1u : 0u);
-            ptx::umma_bf16(d, a_lo, b_hi, idesc, 1u);
-            ptx::umma_bf16(d, a_hi, b_hi, idesc, 1u);
+            const uint32_t a_off = (uint32_t)(s >> 1) * 256u + (uint32_t)(s & 1) * 2u;     // byte offsets >> 4
+            const uint32_t b_off = (uint32_t)(s >> 2) * kstride + bh + (uint32_t)(s & 3) * 2u;
+            ptx::umma_bf16(d, a_hi0 + a_off, b_lo0 + b_off, idesc, s > 0 ? 1u : 0u);
+            ptx::umma_bf16(d, a_lo0 + a_off, b_hi0 + b_off, idesc, 1u);
+            ptx::umma_bf16(d, a_hi0 + a_off, b_hi0 + b_off, idesc, 1u);
           }
         }
         ptx::umma_commit(bar_acc);
+        RT_DBG(r, 1);
       }
       __syncwarp();
     }
@@ -208,7 +221,9 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
     // ------------------------------------------------------------------------------------- exchange (all-gather)
     for (int r = 0; r + 1 < R; ++r) {
       ptx::mbar_wait(bar_staged, (uint32_t)r & 1u);          // this CTA's slice of round r is staged
+      if (lane == 0) RT_DBG(r, 4);
       ptx::mbar_wait_cluster(bar_free, (uint32_t)r & 1u);    // every CTA's MMA of round r has read its operand
+      if (lane == 0) RT_DBG(r, 5);
       if (ptx::elect_one()) {
         const uint32_t src = sS + (uint32_t)(r & 1) * 2u * C::STG;
         for (uint32_t p = 0; p < (uint32_t)CS; ++p) {
@@ -217,6 +232,7 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
           ptx::bulk_copy_to_cluster(dst, src, C::STG, bar);
           ptx::bulk_copy_to_cluster(dst + C::H_PART, src + C::STG, C::STG, bar);
         }
+        RT_DBG(r, 6);
       }
       __syncwarp();
     }
@@ -235,8 +251,9 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
     auto after_acc = [&](int r) {                            // MMA of round r is complete
       ptx::mbar_wait(bar_acc, (uint32_t)r & 1u);
       ptx::tc_fence_after_sync();
-      if (warp == 0 && lane == 0 && r + 1 < R)
-        for (uint32_t p = 0; p < (uint32_t)CS; ++p) ptx::mbar_arrive_cluster(ptx::mapa(bar_free, p));
+      if (threadIdx.x == 0) RT_DBG(r, 2);
+      // "my MMA has finished reading my operand": one lane per peer, no data to publish -> relaxed arrives
+      if (warp == 0 && lane < CS && r + 1 < R) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(bar_free, (uint32_t)lane));
     };
     auto stage = [&](int r, const float (&v)[16]) {
       if (r + 1 < R) {
@@ -245,6 +262,7 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_staged);
+        if (threadIdx.x == 0) RT_DBG(r, 3);
       }
     };
 
@@ -358,7 +376,7 @@ int launch_fwd(float* xg, const uint16_t* Ut_hi, const uint16_t* Ut_lo, const ui
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, k, tm_hi, tm_lo, xg, mask, hout, cst, T, B);
+  e = cudaLaunchKernelEx(&cfg, k, tm_hi, tm_lo, xg, mask, hout, cst, T, B, g_rnn_tc_dbg);
   if (e != cudaSuccess) return -(int)e;
   SEQREC_CHECK_LAUNCH();
   return 0;
@@ -376,7 +394,360 @@ int dispatch_act_fwd(int act, float* xg, const uint16_t* Ut_hi, const uint16_t* 
   }
 }
 
+
+// ================================================================================================================
+// K4 on the tensor cores: the scan's backward pass (Theano's scan gradient of the layer above), same cluster layout.
+//   CTA c owns hidden units J_c = [32c, 32c+32) of 64 batch rows: it computes the pre-activation gradients da of ITS
+//   gate columns locally (elementwise, fp32), writes them as the bf16 hi/lo A operand [64 rows x (gates x 32)], and
+//   the tensor core forms the K-SPLIT partial product  P_c[64, H] = da_c . U[:, cols_c]^T  (M = 64, N = H in two
+//   interleaved halves, fp32 in TMEM).  dL/dh_{t-1} = sum_c P_c is REDUCE-SCATTERED through distributed shared memory:
+//   every thread stores the 32-unit slice that belongs to CTA p straight from its registers into p's receive buffer
+//   (st.shared::cluster), p sums the CS partials of its own units in a fixed order (deterministic).
+//   U[:, cols_c] (H rows x gates x 32 columns, bf16 hi/lo, 64-byte-swizzled K blocks of one gate each) is loaded once.
+//   GRU: two rounds per step (d(r*h) through U_h first, then z,r through U_zr), LSTM: one.
+// xg: in = saved gates, out = dxp; cst: LSTM cell states (in), GRU r*h_{t-1} (out, operand of dU) -- as rnn_scan.cu.
+template <int CELL, int CS>
+struct BwdCfg {
+  static constexpr int H = CS * UPC;
+  static constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : 3;
+  static constexpr int NBLK = G;                                      // K blocks = gates (32 own columns each)
+  static constexpr uint32_t UBLK = H * 64;                            // one K block of the U operand: H rows x 64 B
+  static constexpr uint32_t U_PART = NBLK * UBLK;
+  static constexpr uint32_t A_PART = NBLK * 4096;                     // da operand: 64 rows x 64 B per gate
+  static constexpr uint32_t RECV = CS * 8192;                         // [source CTA][64 rows][32 fp32]
+  static constexpr uint32_t SMEM = 2 * U_PART + 2 * A_PART + RECV + 64 + 1024;
+  static constexpr int TMEM_COLS = H / 2;                             // accumulator columns per interleaved half
+};
+
+template <int CELL, int ACT, int CS>
+__global__ void __launch_bounds__(RT_THREADS, 1)
+rnn_tc_backward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_constant__ CUtensorMap tmU_lo,
+                       float* __restrict__ xg, const uint8_t* __restrict__ mask, const float* __restrict__ hout,
+                       float* __restrict__ cst, const float* __restrict__ dhout, int T, int B,
+                       long long* __restrict__ dbg) {
+  using C = BwdCfg<CELL, CS>;
+  constexpr int H = C::H, G = C::G, GH = G * H;
+  constexpr bool LSTM = CELL == SEQREC_CELL_LSTM;
+  constexpr int NH = H / 2;                                  // MMA N per half
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sU = base;                                  // [2 parts][G blocks][H rows][64 B]
+  const uint32_t sA = sU + 2 * C::U_PART;                    // [2 parts][G blocks][64 rows][64 B]
+  const uint32_t sR = sA + 2 * C::A_PART;                    // [CS][64 rows][128 B], 16-byte chunks XOR (row & 7)
+  const uint32_t sBar = sR + C::RECV;
+  const uint32_t bar_u = sBar, bar_aready = sBar + 8, bar_acc = sBar + 16, bar_rfull = sBar + 24,
+                 bar_rfree = sBar + 32, tmem_slot = sBar + 40;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int b0 = (int)(blockIdx.x / CS) * BMR;
+  // MMA rounds: LSTM one per step, GRU two; the step t = 0 needs none (dL/dh_{-1} is not used)
+  const int RPS = LSTM ? 1 : 2;
+  const int R = (T - 1) * RPS;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar_u, 1);
+    ptx::mbar_init(bar_aready, 4);
+    ptx::mbar_init(bar_acc, 1);
+    ptx::mbar_init(bar_rfull, 4 * CS);
+    ptx::mbar_init(bar_rfree, 4 * CS);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------------------------- TMA (once) + MMA issuer
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(bar_u, 2 * C::U_PART);
+      for (int part = 0; part < 2; ++part)
+        for (int g = 0; g < G; ++g)                          // K block g = columns g*H + 32*rank .. +32 of every row of U
+          ptx::tma_load_2d(sU + part * C::U_PART + g * C::UBLK, part ? &tmU_lo : &tmU_hi, bar_u,
+                           g * H + (int)rank * UPC, 0);
+    }
+    __syncwarp();
+    ptx::mbar_wait(bar_u, 0);
+    const uint32_t idesc = ptx::umma_idesc_bf16(BMR, NH);
+    for (int r = 0; r < R; ++r) {
+      ptx::mbar_wait(bar_aready, (uint32_t)r & 1u);          // da of this round is in shared memory
+      ptx::tc_fence_after_sync();
+      // K blocks of this round: LSTM all four gates; GRU round A = candidate block, round B = z and r blocks
+      const int kb0 = LSTM ? 0 : ((r & 1) ? 0 : 2);
+      const int kb1 = LSTM ? 4 : ((r & 1) ? 2 : 3);
+      if (ptx::elect_one()) {
+        const uint64_t a_hi0 = ptx::umma_desc_k_sw64(sA), a_lo0 = ptx::umma_desc_k_sw64(sA + C::A_PART);
+        const uint64_t b_hi0 = ptx::umma_desc_k_sw64(sU), b_lo0 = ptx::umma_desc_k_sw64(sU + C::U_PART);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t d = tmem_base + ((uint32_t)(hh * 16) << 16);
+          for (int kb = kb0; kb < kb1; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t a_off = (uint32_t)kb * 256u + (uint32_t)ks * 2u;                       // byte offsets >> 4
+              const uint32_t b_off = (uint32_t)kb * (C::UBLK >> 4) + (uint32_t)(hh * NH) * 4u + (uint32_t)ks * 2u;
+              ptx::umma_bf16(d, a_hi0 + a_off, b_lo0 + b_off, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+              ptx::umma_bf16(d, a_lo0 + a_off, b_hi0 + b_off, idesc, 1u);
+              ptx::umma_bf16(d, a_hi0 + a_off, b_hi0 + b_off, idesc, 1u);
+            }
+        }
+        ptx::umma_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------------------------- elementwise + exchange
+    const int q = warp;
+    const int row = 16 * q + (lane & 15), hh = lane >> 4;
+    const int b = b0 + row;
+    const bool valid = b < B;
+    const int u0 = (int)rank * UPC + hh * 16;
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t rsw = (uint32_t)(row & 7);
+    float rec[16], dcar[16], dd[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { rec[j] = 0.f; dcar[j] = 0.f; dd[j] = 0.f; }
+    int xr = 0;                                              // exchange rounds done
+
+    // A operand block g <- this thread's 16 values; then tell the MMA warp (after every block of the round is in)
+    auto put_block = [&](int g, const float (&v)[16]) {
+      stage_slice(sA + (uint32_t)g * 4096u, sA + C::A_PART + (uint32_t)g * 4096u, row, hh, v);
+    };
+    auto a_ready = [&]() {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_aready);
+    };
+    // partial products of this CTA -> the owners of the hidden units (straight from the accumulator registers)
+    auto send = [&]() {
+      if (threadIdx.x == 0) RT_DBG(xr, 0);
+      ptx::mbar_wait(bar_acc, (uint32_t)xr & 1u);
+      ptx::tc_fence_after_sync();
+      if (threadIdx.x == 0) RT_DBG(xr, 1);
+      ptx::mbar_wait_cluster(bar_rfree, ((uint32_t)xr & 1u) ^ 1u);   // every peer has consumed the previous exchange
+      if (threadIdx.x == 0) RT_DBG(xr, 2);
+#pragma unroll 1
+      for (int i = 0; i < CS / 2; ++i) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + 32 * i, v);
+        ptx::tmem_ld_wait();
+        const uint32_t p = (uint32_t)(hh * (CS / 2) + i);    // owner of units [hh*H/2 + 32i, +32)
+        const uint32_t dst = ptx::mapa(sR + rank * 8192u + (uint32_t)row * 128u, p);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k)
+          ptx::st_cluster_f4(dst + ((k ^ rsw) << 4),
+                             make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
+                                         __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])));
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      // one lane per peer: the release (cumulative over the warp's stores through __syncwarp) is paid once, in parallel
+      if (lane < CS) ptx::mbar_arrive_cluster(ptx::mapa(bar_rfull, (uint32_t)lane));
+      if (threadIdx.x == 0) RT_DBG(xr, 3);
+    };
+    // receive: sum the CS partials of OUR units in a fixed order (deterministic), then free the buffer for the peers
+    auto recv = [&](float (&sum)[16]) {
+      ptx::mbar_wait_cluster(bar_rfull, (uint32_t)xr & 1u);
+      if (threadIdx.x == 0) RT_DBG(xr, 4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum[j] = 0.f;
+#pragma unroll 2
+      for (uint32_t src = 0; src < (uint32_t)CS; ++src) {
+        const uint32_t a = sR + src * 8192u + (uint32_t)row * 128u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          float4 t;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                       : "r"(a + ((((uint32_t)hh * 4u + k) ^ rsw) << 4)));
+          sum[4 * k] += t.x; sum[4 * k + 1] += t.y; sum[4 * k + 2] += t.z; sum[4 * k + 3] += t.w;
+        }
+      }
+      __syncwarp();
+      if (lane < CS) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(bar_rfree, (uint32_t)lane));
+      if (threadIdx.x == 0) RT_DBG(xr, 5);
+      ++xr;
+    };
+
+    // per-step inputs live in registers and are PREFETCHED for step t-1 between send() and recv(): the global-load
+    // latency hides behind the exchange instead of sitting on the sequential path
+    float dh[16], g0[16], g1[16], g2[16], g3[16], c0[16], c1[16];
+    bool m = false;
+    auto load_step = [&](int t) {
+      const size_t tok = (size_t)t * B + (valid ? b : 0);
+      m = valid && mask[tok] != 0;
+      const float* gp = xg + tok * GH + u0;
+      load16(dh, dhout + tok * H + u0, valid);
+      load16(g0, gp, m); load16(g1, gp + H, m); load16(g2, gp + 2 * H, m);
+      if constexpr (LSTM) {
+        load16(g3, gp + 3 * H, m);
+        load16(c0, cst + tok * H + u0, m);
+        load16(c1, cst + (tok - (size_t)B) * H + u0, m && t > 0);        // c_{t-1}
+      } else {
+        load16(c1, hout + (tok - (size_t)B) * H + u0, m && t > 0);       // h_{t-1}
+      }
+    };
+    load_step(T - 1);
+
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t tok = (size_t)t * B + (valid ? b : 0);
+      float* gp = xg + tok * GH + u0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dh[j] += rec[j];
+      if constexpr (LSTM) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (m) {
+            const float ac = act_fast<ACT>(c0[j]);
+            const float d_o = dh[j] * ac;
+            const float dc = dcar[j] + dh[j] * g3[j] * act_grad_from_y<ACT>(ac);
+            const float ai = dc * g2[j] * hard_sigmoid_grad_from_y(g0[j]);
+            const float af = dc * c1[j] * hard_sigmoid_grad_from_y(g1[j]);
+            const float ag = dc * g0[j] * act_grad_from_y<ACT>(g2[j]);
+            const float ao = d_o * hard_sigmoid_grad_from_y(g3[j]);
+            dcar[j] = dc * g1[j];
+            dd[j] = 0.f;
+            g0[j] = ai; g1[j] = af; g2[j] = ag; g3[j] = ao;
+          } else {                                           // masked step: state held, no gate gradient
+            dd[j] = dh[j];
+            g0[j] = 0.f; g1[j] = 0.f; g2[j] = 0.f; g3[j] = 0.f;
+          }
+        }
+        if (t > 0) {
+          put_block(0, g0); put_block(1, g1); put_block(2, g2); put_block(3, g3);
+          a_ready();
+        }
+        if (valid) { store16(gp, g0); store16(gp + H, g1); store16(gp + 2 * H, g2); store16(gp + 3 * H, g3); }
+        if (t > 0) {
+          send();
+          load_step(t - 1);
+          float sum[16];
+          recv(sum);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rec[j] = dd[j] + sum[j];
+        }
+      } else {
+        // g0 = z, g1 = r, g2 = candidate, c1 = h_{t-1}
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          c0[j] = g1[j] * c1[j];                             // operand of dU's candidate block (0 on masked steps)
+          if (m) {
+            const float az = dh[j] * (c1[j] - g2[j]) * hard_sigmoid_grad_from_y(g0[j]);
+            const float ah = dh[j] * (1.0f - g0[j]) * act_grad_from_y<ACT>(g2[j]);
+            dd[j] = dh[j] * g0[j];
+            g0[j] = az; g2[j] = ah;
+          } else {
+            dd[j] = dh[j];
+            g0[j] = 0.f; g2[j] = 0.f;
+          }
+        }
+        if (t > 0) {
+          // ---- round A: d(r*h_{t-1}) = da_h . U_h^T
+          put_block(2, g2);
+          a_ready();
+          if (valid) store16(cst + tok * H + u0, c0);
+          float drh[16];
+          send();
+          recv(drh);
+          // ---- round B: da_r, then dL/dh_{t-1} = direct + [da_z, da_r] . U_zr^T
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float ar = m ? drh[j] * c1[j] * hard_sigmoid_grad_from_y(g1[j]) : 0.f;
+            if (m) dd[j] += drh[j] * g1[j];
+            g1[j] = ar;
+          }
+          put_block(0, g0); put_block(1, g1);
+          a_ready();
+          if (valid) { store16(gp, g0); store16(gp + H, g1); store16(gp + 2 * H, g2); }
+          send();
+          load_step(t - 1);
+          float sum[16];
+          recv(sum);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rec[j] = dd[j] + sum[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g1[j] = 0.f;          // h_{-1} = 0: the reset gate has no gradient at t = 0
+          if (valid) {
+            store16(cst + tok * H + u0, c0);
+            store16(gp, g0); store16(gp + H, g1); store16(gp + 2 * H, g2);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+}
+
+template <int CELL, int ACT, int CS>
+int launch_bwd(float* xg, const uint16_t* U_hi, const uint16_t* U_lo, const uint8_t* mask, const float* hout,
+               float* cst, const float* dhout, int T, int B, cudaStream_t st) {
+  using C = BwdCfg<CELL, CS>;
+  CUtensorMap tm_hi, tm_lo;
+  int rc;
+  // U (H rows, G*H columns) bf16; box = 32 gate columns (one K block) x all H rows, 64-byte swizzle
+  if ((rc = tma::make_2d_bf16(&tm_hi, U_hi, C::H, (uint64_t)C::G * C::H, (uint64_t)C::G * C::H, 32, C::H,
+                              CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
+  if ((rc = tma::make_2d_bf16(&tm_lo, U_lo, C::H, (uint64_t)C::G * C::H, (uint64_t)C::G * C::H, 32, C::H,
+                              CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
+  auto k = rnn_tc_backward_kernel<CELL, ACT, CS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return -(int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ceil_div(B, BMR) * CS));
+  cfg.blockDim = dim3(RT_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, k, tm_hi, tm_lo, xg, mask, hout, cst, dhout, T, B, g_rnn_tc_dbg);
+  if (e != cudaSuccess) return -(int)e;
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int CELL, int CS>
+int dispatch_act_bwd(int act, float* xg, const uint16_t* U_hi, const uint16_t* U_lo, const uint8_t* mask,
+                     const float* hout, float* cst, const float* dhout, int T, int B, cudaStream_t st) {
+  switch (act) {
+    case SEQREC_ACT_RELU:
+      return launch_bwd<CELL, SEQREC_ACT_RELU, CS>(xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+    case SEQREC_ACT_TANH:
+      return launch_bwd<CELL, SEQREC_ACT_TANH, CS>(xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+    case SEQREC_ACT_LINEAR:
+      return launch_bwd<CELL, SEQREC_ACT_LINEAR, CS>(xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+    default: return -1002;
+  }
+}
+
 }  // namespace
+
+/* diagnostics only (not in the public header): device buffer of 64 x 8 clock64() stamps written by CTA 0 */
+extern "C" int seqrec_rnn_tc_debug_buffer(long long* dev_buf) {
+  g_rnn_tc_dbg = dev_buf;
+  return 0;
+}
 
 extern "C" int seqrec_rnn_tc_applicable(int cell, int H) {
   return ((cell == SEQREC_CELL_LSTM || cell == SEQREC_CELL_GRU) && (H == 128 || H == 256)) ? 1 : 0;
@@ -394,4 +765,18 @@ extern "C" int seqrec_rnn_tc_forward(int cell, int act, float* xg, const uint16_
   }
   if (H == 256) return dispatch_act_fwd<SEQREC_CELL_GRU, 8>(act, xg, Ut_hi, Ut_lo, mask, hout, cst, T, B, st);
   return dispatch_act_fwd<SEQREC_CELL_GRU, 4>(act, xg, Ut_hi, Ut_lo, mask, hout, cst, T, B, st);
+}
+
+extern "C" int seqrec_rnn_tc_backward(int cell, int act, float* xg, const uint16_t* U_hi, const uint16_t* U_lo,
+                                      const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T,
+                                      int B, int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && seqrec_rnn_tc_applicable(cell, H), 1);
+  SEQREC_ARG(xg && U_hi && U_lo && mask && hout && cst && dhout, 2);
+  cudaStream_t st = as_stream(stream);
+  if (cell == SEQREC_CELL_LSTM) {
+    if (H == 256) return dispatch_act_bwd<SEQREC_CELL_LSTM, 8>(act, xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+    return dispatch_act_bwd<SEQREC_CELL_LSTM, 4>(act, xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+  }
+  if (H == 256) return dispatch_act_bwd<SEQREC_CELL_GRU, 8>(act, xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
+  return dispatch_act_bwd<SEQREC_CELL_GRU, 4>(act, xg, U_hi, U_lo, mask, hout, cst, dhout, T, B, st);
 }

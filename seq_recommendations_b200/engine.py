@@ -157,10 +157,13 @@ class HotPath:
         lib = _lib.load()
         tc_ok = lib.seqrec_rnn_tc_applicable(CELL[cell], self.H) != 0
         env = os.environ.get("SEQREC_RNN_TC", "")
+        self.Ut_hi = self.Ut_lo = self.U_hi = self.U_lo = None
         self.rnn_tc = tc_ok and (env == "1" or (env != "0" and (self.H > 128 or cell == "LSTM")))
         if tc_ok:
             self.Ut_hi = torch.empty((self.GH, self.H), dtype=torch.bfloat16, device=dev)
             self.Ut_lo = torch.empty((self.GH, self.H), dtype=torch.bfloat16, device=dev)
+            self.U_hi = torch.empty((self.H, self.GH), dtype=torch.bfloat16, device=dev)
+            self.U_lo = torch.empty((self.H, self.GH), dtype=torch.bfloat16, device=dev)
         self.touched = torch.zeros(self.F, dtype=torch.int32, device=dev)
         self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
         self.n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -380,6 +383,20 @@ class HotPath:
         if training and self.dropout_out > 0:
             w.hscale = self._dropout((w.N, self.H), self.dropout_out)
 
+    def _rnn_backward(self, w):
+        """K4: dL/dhout (w.dh) -> dxp in place of the saved gates (w.xg)."""
+        st = self.stream
+        if self.rnn_tc:
+            call("seqrec_split_bf16", ptr(self.U), None, ptr(self.U_hi), ptr(self.U_lo), self.H, self.GH, self.GH, 0,
+                 st)
+            call("seqrec_rnn_tc_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U_hi), ptr(self.U_lo),
+                 ptr(w.mask), ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+            return
+        if self._needs_ut:
+            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
+             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+
     def _forward_ce(self, w, with_targets=True, training=False):
         n_splits = self._ce_partials(w, with_targets, training)
         self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets)
@@ -502,10 +519,7 @@ class HotPath:
         head = o_b + s_b
         pending = [comm.all_reduce_sum(self.flat_g[head:], async_op=True)] if comm.enabled else []
         self._mark("rnn_bwd")
-        if self._needs_ut:
-            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
-        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
-             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        self._rnn_backward(w)
         # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs
         self._mark("scatter")
         self.n_rows.zero_()
@@ -595,10 +609,7 @@ class HotPath:
         comm.reduce_scatter_sum(w.dh.view(w.N, self.H), wg.dh.view(wg.N, self.H))
         if w.hscale is not None:
             w.dh.view(w.N, self.H).mul_(w.hscale)
-        if self._needs_ut:
-            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
-        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
-             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        self._rnn_backward(w)
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
@@ -693,10 +704,7 @@ class HotPath:
         self.flat_g.zero_()
         self._backward_ce(w)
         dh = w.dh.clone()
-        if self._needs_ut:
-            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
-        call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
-             ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+        self._rnn_backward(w)
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
         self.n_rows.zero_()

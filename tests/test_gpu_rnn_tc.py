@@ -59,6 +59,28 @@ def test_tc_scan_loss_and_gradients_match_oracle(cell, act, H, T, B):
         assert rel_err(g, r.numpy()) <= 1e-4, (name, rel_err(g, r.numpy()))
 
 
+@pytest.mark.parametrize("cell,act,H,T,B", CASES)
+def test_tc_backward_scan_matches_simt_scan(cell, act, H, T, B):
+    """Same saved gates and dL/dhout into both backward scans: dxp (and the GRU's r*h operand) must agree."""
+    from seq_recommendations_b200._lib import ACT, CELL, call, ptr
+    V = 500
+    ids, tgt = synthetic.make_batch(V, T, B, seed=22, min_len=1)
+    out = {}
+    for tc_scan in (True, False):
+        hot, _ = _pair(cell, act, V, H, 18, False)          # the SAME (SIMT) forward feeds both backward scans:
+        hot.hidden_batch(ids)                                # activation kinks must not flip between the two runs
+        hot.rnn_tc = tc_scan
+        w = hot.work(B, T)
+        g = torch.Generator(device="cpu").manual_seed(5)
+        w.dh.copy_(torch.randn(w.dh.shape, generator=g).to(w.dh.device) * w.mask.view(T, B, 1))
+        hot._rnn_backward(w)
+        torch.cuda.synchronize()
+        out[tc_scan] = (w.xg.cpu().numpy().copy(), w.cst.cpu().numpy().copy())
+    assert rel_err(out[True][0], out[False][0]) <= 5e-5, rel_err(out[True][0], out[False][0])
+    if cell == "GRU":
+        assert rel_err(out[True][1], out[False][1]) <= 5e-5
+
+
 def test_tc_scan_long_sequence_many_clusters():
     """T = 200 (cfg5's length), 5 clusters: error does not grow with the number of exchange rounds."""
     V, H, T, B = 300, 256, 200, 300
