@@ -95,6 +95,13 @@ int seqrec_rnn_tc_backward(int cell, int act, float* xg, const uint16_t* U_hi, c
  * dU and db must be pre-zeroed. */
 int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,
                            int T, int B, int H, void* stream);
+/* the same gradient as one split-K tcgen05 GEMM over all tokens (csrc/wgrad_tc.cu; LSTM / GRU, H = 128 or 256):
+ * dxp_hi/lo (N, G*H), h_hi/lo (N, H) and -- GRU only -- c_hi/c_lo (N, H) are the seqrec_split_bf16 images of dxp, hout
+ * and cst; both operands are consumed token-major (MN-major UMMA operands), 3-pass split products, fp32 accumulate.
+ * db is summed from the fp32 dxp. */
+int seqrec_rnn_weight_grad_tc(int cell, const float* dxp, const uint16_t* dxp_hi, const uint16_t* dxp_lo,
+                              const uint16_t* h_hi, const uint16_t* h_lo, const uint16_t* c_hi, const uint16_t* c_lo,
+                              float* dU, float* db, int T, int B, int H, void* stream);
 /* out (cols, rows) = in (rows, cols)^T */
 int seqrec_transpose(const float* in, float* out, int rows, int cols, void* stream);
 

@@ -70,6 +70,7 @@ class _Work:
         self.graph = None
         self.graph_calls = 0
         self.graph_loss = None
+        self.D_hi = self.D_lo = self.Hs_hi = self.Hs_lo = self.C_hi = self.C_lo = None   # bf16 operands of the dU GEMM
         # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
         self.tc = hp._tc_plan(N)
         if self.tc["fwd"]:
@@ -158,6 +159,8 @@ class HotPath:
         tc_ok = lib.seqrec_rnn_tc_applicable(CELL[cell], self.H) != 0
         env = os.environ.get("SEQREC_RNN_TC", "")
         self.Ut_hi = self.Ut_lo = self.U_hi = self.U_lo = None
+        # recurrent weight gradient as a split-K tcgen05 GEMM over all tokens (csrc/wgrad_tc.cu); SEQREC_WGRAD_TC=0 disables
+        self.wgrad_tc = tc_ok and os.environ.get("SEQREC_WGRAD_TC", "1") != "0"
         self.rnn_tc = tc_ok and (env == "1" or (env != "0" and (self.H > 128 or cell == "LSTM")))
         if tc_ok:
             self.Ut_hi = torch.empty((self.GH, self.H), dtype=torch.bfloat16, device=dev)
@@ -397,6 +400,29 @@ class HotPath:
         call("seqrec_rnn_backward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(self.Ut), ptr(w.mask),
              ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
 
+    def _rnn_weight_grad(self, w):
+        """dU, db from dxp (w.xg), hout and (GRU) r*h_{t-1} (w.cst)."""
+        st = self.stream
+        if self.wgrad_tc:
+            if w.D_hi is None:
+                bf = torch.bfloat16
+                w.D_hi = torch.empty((w.N, self.GH), dtype=bf, device=self.device)
+                w.D_lo = torch.empty((w.N, self.GH), dtype=bf, device=self.device)
+                w.Hs_hi = torch.empty((w.N, self.H), dtype=bf, device=self.device)
+                w.Hs_lo = torch.empty((w.N, self.H), dtype=bf, device=self.device)
+                if self.cell == "GRU":
+                    w.C_hi = torch.empty((w.N, self.H), dtype=bf, device=self.device)
+                    w.C_lo = torch.empty((w.N, self.H), dtype=bf, device=self.device)
+            call("seqrec_split_bf16", ptr(w.xg), None, ptr(w.D_hi), ptr(w.D_lo), w.N, self.GH, self.GH, 0, st)
+            call("seqrec_split_bf16", ptr(w.hout), None, ptr(w.Hs_hi), ptr(w.Hs_lo), w.N, self.H, self.H, 0, st)
+            if self.cell == "GRU":
+                call("seqrec_split_bf16", ptr(w.cst), None, ptr(w.C_hi), ptr(w.C_lo), w.N, self.H, self.H, 0, st)
+            call("seqrec_rnn_weight_grad_tc", CELL[self.cell], ptr(w.xg), ptr(w.D_hi), ptr(w.D_lo), ptr(w.Hs_hi),
+                 ptr(w.Hs_lo), ptr(w.C_hi), ptr(w.C_lo), ptr(self.dU), ptr(self.db), w.T, w.B, self.H, st)
+            return
+        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
+             w.T, w.B, self.H, st)
+
     def _forward_ce(self, w, with_targets=True, training=False):
         n_splits = self._ce_partials(w, with_targets, training)
         self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets)
@@ -548,8 +574,7 @@ class HotPath:
             if comm.enabled:
                 pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
         self._mark("rnn_wgrad")
-        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
-             w.T, w.B, self.H, st)
+        self._rnn_weight_grad(w)
         self._mark("allreduce")
         if comm.enabled:
             pending.append(comm.all_reduce_sum(self.flat_g[:head], async_op=True))
@@ -610,8 +635,7 @@ class HotPath:
         if w.hscale is not None:
             w.dh.view(w.N, self.H).mul_(w.hscale)
         self._rnn_backward(w)
-        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
-             w.T, w.B, self.H, st)
+        self._rnn_weight_grad(w)
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
         comm.all_reduce_sum(self.flat_g[:head])   # replicated recurrent parameters
@@ -705,8 +729,7 @@ class HotPath:
         self._backward_ce(w)
         dh = w.dh.clone()
         self._rnn_backward(w)
-        call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
-             w.T, w.B, self.H, st)
+        self._rnn_weight_grad(w)
         self.n_rows.zero_()
         if w.x_dense is None:
             call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),

@@ -90,3 +90,18 @@ def test_tc_scan_long_sequence_many_clusters():
         hot, _ = _pair("GRU", "tanh", V, H, 9, tc_scan)
         hid[tc_scan] = hot.hidden_batch(ids).cpu().numpy()
     assert rel_err(hid[True], hid[False]) <= 5e-5
+
+
+@pytest.mark.parametrize("cell,H,T,B", [("LSTM", 256, 9, 70), ("GRU", 256, 12, 33), ("GRU", 128, 50, 256), ("LSTM", 128, 3, 5)])
+def test_tc_weight_gradient_matches_simt_gemm(cell, H, T, B):
+    """dU / db from the split-K tcgen05 GEMM (MN-major operands, wgrad_tc.cu) vs the fp32 SIMT GEMM on the same dxp."""
+    V = 300
+    ids, tgt = synthetic.make_batch(V, T, B, seed=31, min_len=1)
+    out = {}
+    for tc_w in (True, False):
+        hot, _ = _pair(cell, "tanh", V, H, 23, False)
+        hot.wgrad_tc = tc_w
+        _, grads, _ = hot.grad_batch(ids, tgt)
+        out[tc_w] = (grads[1], grads[2])
+    assert rel_err(out[True][0], out[False][0]) <= 2e-5, rel_err(out[True][0], out[False][0])
+    assert rel_err(out[True][1], out[False][1]) <= 1e-6
