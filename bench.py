@@ -38,52 +38,104 @@ def load_peaks():
         return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
+def load_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed ncu --set full
+    capture of this workload (profiles/traffic.json, written by scripts/summarize_ncu.py); None when not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the run: an NVML polling thread (5 ms period) when nvidia_ml_py is
+    importable, else `nvidia-smi -lms 100` in a subprocess.  stop() reports the median clock under load."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.p = self.f = self.thread = None
+        self._stop = threading.Event()
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        try:
+                            bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, bit in self.REASONS.items():
+                            if bits & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.005)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark(self):
+        """Samples taken before this call are dropped (start of the timed region)."""
+        if self.thread is not None:
+            del self.sm[:]
+            self.reasons.clear()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            out["source"] = "nvml"
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1]))
+                    self.mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            os.unlink(self.f.name)
+            out["source"] = "nvidia-smi"
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["sm_max_mhz"] = float(max(self.mx)) if self.mx else None
+            out["samples"] = len(self.sm)
+        out["reasons"] = sorted(self.reasons)
         return out
 
 
@@ -150,7 +202,7 @@ def run_reference(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_cpu(cfg, max(1, args.steps), max(1, min(args.warmup, 2)), budget_s=120.0)
+    r = time_cpu(cfg, max(1, args.steps), max(1, min(args.warmup, 2)), budget_s=60.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "sequences/sec", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -164,11 +216,87 @@ def run_reference(args, cfg, name):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_scoring(args, cfg, name):
+    """configs[4] (inference): sequences scored per second -- recurrent scan over T steps, then top-k next items of the
+    last step (`last`) or p(true next item) at every step (`all`).  One step = one batch of B sequences."""
+    import torch
+    from seq_recommendations_b200 import _lib
+    from seq_recommendations_b200.engine import HotPath
+    from seq_recommendations_b200 import synthetic
+    torch.cuda.set_device(0)
+    V, H, T, B, k = cfg["V"], cfg["H"], cfg["T"], cfg["B"], 20
+    ws = synthetic.make_weights(cfg["cell"], V, H, seed=0)
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, tc=args.tc)
+    ids, tgt = synthetic.make_batch(V, T, B, seed=0)
+    pin_i, pin_t = torch.from_numpy(ids).pin_memory(), torch.from_numpy(tgt).pin_memory()
+    dev_i, dev_t = pin_i.cuda(), pin_t.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {}
+    clocks = ClockSampler(0)
+    for mode in ("last", "all"):
+        fn = (lambda i, t: hot.topk_batch(i, k, last_step_only=True)[0]) if mode == "last" else (
+            lambda i, t: hot.target_prob_batch(i, t))
+        for _ in range(max(args.warmup, 3)):
+            fn(dev_i, dev_t)
+        torch.cuda.synchronize()
+        if mode == "last":
+            clocks.mark()
+        evs = []
+        _lib.launch_count(reset=True)
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(dev_i, dev_t)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        launches = _lib.launch_count()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        e2e = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn(pin_i, pin_t)
+            r.cpu()
+            e2e.append(time.perf_counter() - t0)
+        out[mode] = dict(ms=ms, e2e_ms=float(np.mean(e2e)) * 1e3, launches=launches, d2h=int(r.numel() * r.element_size()))
+    clk = clocks.stop()
+    peaks = load_peaks()
+    G = 3 if cfg["cell"] == "GRU" else 4
+    flops_all = B * T * (2 * G * H * H + 2 * H * V)
+    line = {
+        "metric": "sequences scored/sec", "value": B / (out["last"]["ms"] * 1e-3), "unit": "sequences/sec", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": out["last"]["ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core GEMMs)" if hot.tc_x3 else hot.tc_mode,
+        "data": "synthetic",
+        "config": {"workload": name, "cell": cfg["cell"], "V": V, "H": H, "T": T, "B": B, "k": k,
+                   "mode": "top-%d next items of the last step" % k,
+                   "l2": "256 MiB memset between timed steps (outside the events)"},
+        "clocks": clk,
+        "e2e": {"value": B / (out["last"]["e2e_ms"] * 1e-3), "unit": "sequences/sec", "ms_per_step": out["last"]["e2e_ms"],
+                "h2d_bytes_per_step": B * T * 4, "d2h_bytes_per_step": out["last"]["d2h"],
+                "api": "HotPath.topk_batch(pinned host ids, k, last_step_only=True) -> ids.cpu()"},
+        "gpu_launches": out["last"]["launches"],
+        "all_steps_target_prob": {"value": B / (out["all"]["ms"] * 1e-3), "unit": "sequences/sec",
+                                  "ms_per_step": out["all"]["ms"], "e2e_ms_per_step": out["all"]["e2e_ms"],
+                                  "algorithmic_tflops": flops_all / (out["all"]["ms"] * 1e-3) / 1e12,
+                                  "frac_of_bf16_sustained": flops_all / (out["all"]["ms"] * 1e-3) / 1e12 / peaks["bf16_sustained"]},
+        "roofline": {"kernel": "seqrec_ce_tc_forward over all B*T tokens (all-steps mode)", "bound": "tensor",
+                     "achieved": flops_all / (out["all"]["ms"] * 1e-3) / 1e12, "peak": peaks["bf16_sustained"],
+                     "unit": "TFLOP/s", "frac": flops_all / (out["all"]["ms"] * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                     "traffic": None},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -181,6 +309,8 @@ def main():
     cfg = dict(synthetic.CONFIGS[args.config])
     if args.impl == "reference":
         return run_reference(args, cfg, args.config)
+    if args.config.startswith("cfg5"):
+        return run_scoring(args, cfg, args.config)
 
     import torch
     from seq_recommendations_b200 import _lib, dist
@@ -210,15 +340,17 @@ def main():
         comm.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler is already running; its samples are reset when the timed region starts)
+    clocks = ClockSampler(local) if rank == 0 else None
     for s in range(args.warmup):
         hot.train_batch(*resident[s % n_batches])
     sync_all()
 
     # ---- timed: K steps, inputs resident in HBM (the step replays as one CUDA graph at N=1)
-    clocks = ClockSampler(local) if rank == 0 else None
     evs = []
     sync_all()
+    if clocks is not None:
+        clocks.mark()
     t_wall = time.perf_counter()
     for s in range(args.steps):
         flush.zero_()
@@ -279,9 +411,12 @@ def main():
         "kernel": "seqrec_ce_%sbackward (logits recompute + dH + dW_out, %s)" % (
             ("tc_", "tcgen05 bf16 %s, fp32 accumulate in TMEM" % ("3-pass hi/lo split" if hot.tc_x3 else "single pass"))
             if hot.work(B, T).tc["bwd"] else ("", "fp32 SIMT")),
-        "mma_flops_issued": work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 6 / 4 if hot.work(B, T).tc["bwd"] else 1.5),
+        # issued by the kernels: logits recompute + gradient GEMM in BOTH kernels (4 GEMMs for 2 algorithmic ones), each
+        # product in 3 bf16 passes in x3 mode
+        "mma_flops_issued": work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 2.0 if hot.work(B, T).tc["bwd"] else 1.5),
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+        "frac": achieved / peaks["bf16_sustained"], "traffic": load_traffic(args.config),
+        "peak_source": peaks["src"] + " bf16 sustained",
         "ms_per_launch": dom_ms,
         "others": {
             "gather_gbs": work["gather_bytes"] / (per_step.get("gather", 1e9) * 1e-3) / 1e9,

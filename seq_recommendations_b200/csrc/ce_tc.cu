@@ -360,6 +360,231 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   }
 }
 
+// 16 consecutive 32-bit columns, registers -> TMEM (thread i writes lane base + i)
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// this thread's row of a K-major bf16 matrix (global memory, leading dimension ld elements), K elements
+// [k0, k0 + 32*nchunks) -> packed pairs in TMEM columns [tcol, tcol + 16*nchunks): the A-operand image of a TS-mode MMA
+__device__ __forceinline__ void row_to_tmem(uint32_t tcol, const uint16_t* __restrict__ src, int64_t row, int ld,
+                                            int k0, int nchunks, bool row_ok) {
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t v[16];
+    if (row_ok) {
+      const uint4* g = reinterpret_cast<const uint4*>(src + row * ld + k0 + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 t = __ldg(g + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0u;
+    }
+    tmem_st_32x16(tcol + 16 * c, v);
+  }
+}
+
+// ================================================================================================================
+// forward, A operand in TENSOR MEMORY.  An SS-mode M=128 x N=128 MMA reads 8 KB of shared memory per 64 tensor cycles
+// -- exactly the 128 B/clk the SM's shared memory delivers -- so with the TMA writes of the streamed operand on top
+// the SS kernel above is shared-memory bound (ncu: tensor pipe 57 % active).  Here the stationary token tile lives in
+// TMEM as the A operand (TS-mode MMA): only the streamed W_out^T blocks cross shared memory (64 B/clk), and the whole
+// shared memory is a deeper TMA ring.  The epilogue warps load the A rows from global memory at the start of a segment
+// (one thread = one token row) and tcgen05.st them as packed bf16 pairs.
+//   TMEM columns: [0, 256) logits double buffer | A hi (HK/2) | A lo (HK/2)
+template <int KB, int NS, bool X3, bool BIAS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_forward_atm_kernel(const uint16_t* __restrict__ A_hi, const uint16_t* __restrict__ A_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
+                         int64_t n_tokens, int v_begin, int v_end, int max_slots) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int HK = KB * KBLK;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;                                  // [NS][NP][TILE_B]
+  const uint32_t sBar = sB + NS * NP * TILE_B;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 tmem_slot = bar_afree + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
+  const Share sh(total, n_vtiles);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
+    ptx::mbar_init(bar_a, N_EPI_WARPS);
+    ptx::mbar_init(bar_afree, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_a = tmem_base + 2 * BN;                // hi: HK/2 columns, lo: the next HK/2
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) ptx::prefetch_tmap(&tmB_hi);
+    Pipe p;
+    for (int64_t w = sh.w0; w < sh.w1; ++w) {
+      const int v0 = v_begin + sh.inner(w) * BN;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+        }
+        p.advance(NS);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+    Pipe p;
+    int seg = -1, tc = 0;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      if (sh.seg_first(w)) {
+        ++seg;
+        ptx::mbar_wait(bar_a, seg & 1);                      // the epilogue warps have stored the token tile
+        ptx::tc_fence_after_sync();
+      }
+      const int buf = tc & 1;
+      ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d = tmem_base + buf * BN;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t b = sB + p.stage * NP * TILE_B;
+        const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k) {
+            const uint32_t a_hi = tmem_a + kb * (KBLK / 2) + k * 8, a_lo = a_hi + HK / 2;
+            const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
+            if (X3) {
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc, acc);
+              ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+            } else {
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, acc);
+            }
+          }
+        }
+        __syncwarp();
+        commit_elect(bar_empty + 8 * p.stage);
+        p.advance(NS);
+      }
+      commit_elect(bar_tfull + 8 * buf);
+      if (sh.seg_last(w)) commit_elect(bar_afree);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float m = -INFINITY, s = 0.f;
+    int tc = 0, seg = -1;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc & 1;
+      const int tt = sh.outer(w), vt = sh.inner(w);
+      if (sh.seg_first(w)) {
+        ++seg;
+        m = -INFINITY; s = 0.f;
+        if (seg > 0) {                                       // the previous segment's MMAs have consumed the old tile
+          ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int64_t n = (int64_t)tt * BM + row;
+        // this warp's half of the K range: HK/2 elements = HK/4 packed columns per part
+        row_to_tmem(tmem_a + lane_off + half * (HK / 4), A_hi, n, HK, half * (HK / 2), HK / 64, n < n_tokens);
+        if (X3)
+          row_to_tmem(tmem_a + lane_off + HK / 2 + half * (HK / 4), A_lo, n, HK, half * (HK / 2), HK / 64,
+                      n < n_tokens);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_a);
+      }
+      const int vc0 = v_begin + vt * BN + half * 64;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      float z[64];
+      load_half_tile(tmem_base + lane_off + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      if (BIAS || vc0 + 64 > v_end) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int v = vc0 + j;
+          if (v < v_end) { if (BIAS) z[j] += __ldg(b_out + v); }
+          else z[j] = -INFINITY;
+        }
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        mx[0] = fmaxf(mx[0], z[j]); mx[1] = fmaxf(mx[1], z[j + 1]);
+        mx[2] = fmaxf(mx[2], z[j + 2]); mx[3] = fmaxf(mx[3], z[j + 3]);
+      }
+      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (cmax > -INFINITY) {
+        const float mn = fmaxf(m, cmax);
+        const float nb = -mn * LOG2E;
+        float add[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          add[0] += ptx::ex2_approx(fmaf(z[j], LOG2E, nb));
+          add[1] += ptx::ex2_approx(fmaf(z[j + 1], LOG2E, nb));
+          add[2] += ptx::ex2_approx(fmaf(z[j + 2], LOG2E, nb));
+          add[3] += ptx::ex2_approx(fmaf(z[j + 3], LOG2E, nb));
+        }
+        s = s * ptx::ex2_approx(fmaf(m, LOG2E, nb)) + ((add[0] + add[1]) + (add[2] + add[3]));
+        m = mn;
+      }
+      if (sh.seg_last(w)) {
+        const int64_t n = (int64_t)tt * BM + row;
+        if (n < n_tokens) {
+          const int slot = (int)blockIdx.x - cta_of((int64_t)tt * n_vtiles, total);
+          ws_m[((int64_t)slot * 2 + half) * n_tokens + n] = m;
+          ws_s[((int64_t)slot * 2 + half) * n_tokens + n] = s;
+          if (vt == n_vtiles - 1) {
+            for (int k = slot + 1; k < max_slots; ++k) {
+              ws_m[((int64_t)k * 2 + half) * n_tokens + n] = -INFINITY;
+              ws_s[((int64_t)k * 2 + half) * n_tokens + n] = 0.f;
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // flush a [128 x ncols] fp32 TMEM accumulator slice owned by this warp (32 rows x `ncols` columns starting at
 // column col0) into global memory with vector reductions: dst_row points at this thread's row, column col0
 __device__ __forceinline__ void flush_acc_red(uint32_t taddr, int ncols, float* dst_row, int valid_cols, bool row_ok,
@@ -1277,6 +1502,23 @@ int launch_ts(int KB, bool x3, bool item_st, int grid, const CUtensorMap& x_hi, 
 #undef TS3
 }
 
+template <int KB, bool X3, bool BIAS>
+int launch_fwd_atm(const uint16_t* A_hi, const uint16_t* A_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                   const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end,
+                   cudaStream_t st) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int NS = X3 ? 6 : 12;
+  const size_t smem = 1024 + (size_t)NS * NP * TILE_B + 256;
+  auto k = ce_tc_forward_atm_kernel<KB, NS, X3, BIAS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+  k<<<persistent_grid(total), TC_THREADS, smem, st>>>(A_hi, A_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin,
+                                                      v_end, forward_slots(n_tokens, v_begin, v_end));
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -1307,6 +1549,27 @@ extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, 
   if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   cudaStream_t st = as_stream(stream);
+  // SEQREC_CE_FWD_ATM=1 selects the variant that keeps the token tile in tensor memory (TS-mode MMA).  Measured equal
+  // to the SS-mode kernel on B200 (cfg2 0.118 ms, cfg3 5.7 ms either way: the forward is bound by its exp2 epilogue,
+  // not by shared-memory bandwidth), so the SS kernel stays the default.
+  static const bool atm = [] { const char* e = getenv("SEQREC_CE_FWD_ATM"); return e && e[0] == '1'; }();
+  if (atm) {
+#define ATM2(KB, X3V, BV) \
+  return launch_fwd_atm<KB, X3V, BV>(A_hi, x3 ? A_lo : A_hi, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, st)
+#define ATM(KB)                                                                      \
+  {                                                                                  \
+    if (x3) { if (b_out) ATM2(KB, true, true); else ATM2(KB, true, false); }         \
+    else    { if (b_out) ATM2(KB, false, true); else ATM2(KB, false, false); }       \
+  }
+    switch (Hk / KBLK) {
+      case 1: ATM(1)
+      case 2: ATM(2)
+      case 3: ATM(3)
+      default: ATM(4)
+    }
+#undef ATM2
+#undef ATM
+  }
 #define FWD2(KB, NS, X3V, BV) \
   return launch_fwd<KB, NS, X3V, BV>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, st)
 #define FWD(KB, NS)                                                                      \

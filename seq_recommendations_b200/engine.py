@@ -788,11 +788,16 @@ class HotPath:
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)
         self._forward_hidden(w, training=False)
-        self._forward_ce(w, with_targets=False)
         if last_step_only:
-            off = (w.T - 1) * w.B
-            hrows, m, s, n = w.hout[w.T - 1], w.m[off:off + w.B], w.s[off:off + w.B], w.B
+            # softmax statistics of the last step only: a (B, 1) problem over the rows hout[T-1]
+            wl = self.work(int(B), 1)
+            wl.hout.copy_(w.hout[w.T - 1:w.T])
+            wl.mask.copy_(w.mask[w.T - 1:w.T])
+            wl.hscale = None
+            self._forward_ce(wl, with_targets=False)
+            hrows, m, s, n = wl.hout[0], wl.m, wl.s, wl.B
         else:
+            self._forward_ce(w, with_targets=False)
             hrows, m, s, n = w.hout, w.m, w.s, w.N
         out_i = torch.empty((n, k), dtype=torch.int32, device=self.device)
         out_p = torch.empty((n, k), dtype=torch.float32, device=self.device)
