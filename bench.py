@@ -302,6 +302,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--tc", default="x3", choices=["x3", "bf16", "off"], help="logits GEMM mode (x3 = fp32-grade)")
+    ap.add_argument("--vocab-parallel", type=int, default=-1,
+                    help="1: column-shard W_out over the ranks (default for cfg4 when N > 1), 0: replicate")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -327,7 +329,9 @@ def main():
 
     V, H, T, B = cfg["V"], cfg["H"], cfg["T"], cfg["B"]
     ws = synthetic.make_weights(cfg["cell"], V, H, seed=0)
-    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, comm=comm, seed=rank, tc=args.tc)
+    vp = (args.vocab_parallel == 1 or (args.vocab_parallel < 0 and args.config.startswith("cfg4"))) and world > 1 \
+        and V % world == 0
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, comm=comm, seed=rank, tc=args.tc, vocab_parallel=vp)
     hot.set_optimizer("adagrad", lr=0.01, epsilon=1e-8, clipnorm=1.0)
     hot.dropout_out = args.dropout
     n_batches = 4
@@ -436,10 +440,11 @@ def main():
                   "bf16": "bf16 logits GEMMs, fp32 accumulate; fp32 elsewhere", "off": "f32"}[hot.tc_mode],
         "data": "synthetic",
         "config": {"workload": args.config, "cell": cfg["cell"], "act": cfg["act"], "V": V, "H": H, "T": T,
-                   "B_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "B_per_gpu": B, "global_batch": world * B,
+                   "parallelism": ("dp%d x vocab-parallel logits (W_out column-sharded)" % world) if vp else "dp%d" % world,
                    "l2": "256 MiB memset between timed steps (outside the events)", "dropout": args.dropout,
                    "optimizer": "adagrad lr=0.01 eps=1e-8 clipnorm=1",
-                   "cuda_graph": bool(hot.use_graphs and world == 1)},
+                   "cuda_graph": bool(hot.use_graphs and not vp and (world == 1 or hot.graph_collectives))},
         "clocks": clk,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * B * T * 4, "d2h_bytes_per_step": 4,

@@ -621,6 +621,7 @@ class HotPath:
         w = self.work(int(B), int(T))
         st = self.stream
         comm = self.comm
+        self._mark("ingest")
         self._stage(w, ids, tgt, x_dense)
         n_valid = w.n_valid_i.to(torch.float32)
         comm.all_reduce_sum(n_valid)
@@ -630,12 +631,17 @@ class HotPath:
         loss = wg.loss_sum * self.inv_nvalid      # identical on every rank: the sum runs over all ranks' tokens
         # ---- backward: dW_out / db_out of the shard are complete locally; dh is summed over the item shards
         self.flat_g.zero_()
+        self._mark("ce_bwd")
         self._backward_ce(wg)
+        self._mark("allreduce")
         comm.reduce_scatter_sum(w.dh.view(w.N, self.H), wg.dh.view(wg.N, self.H))
         if w.hscale is not None:
             w.dh.view(w.N, self.H).mul_(w.hscale)
+        self._mark("rnn_bwd")
         self._rnn_backward(w)
+        self._mark("rnn_wgrad")
         self._rnn_weight_grad(w)
+        self._mark("scatter")
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
         comm.all_reduce_sum(self.flat_g[:head])   # replicated recurrent parameters
@@ -649,6 +655,7 @@ class HotPath:
         # ---- global norm: replicated gradients count once, the sharded ones are summed over ranks
         o = self.opt
         max_rows = min(self.F, w.N * comm.world)
+        self._mark("optim")
         self.sumsq.zero_()
         if o["clipnorm"] > 0:
             call("seqrec_sumsq", ptr(self.flat_g[head:]), self.flat_g.numel() - head, ptr(self.sumsq), st)
@@ -661,6 +668,7 @@ class HotPath:
         call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows), ptr(self.n_rows),
              ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
         self._w_version += 1
+        self._mark("end")
         return loss
 
     def _segments(self):

@@ -44,7 +44,10 @@ def main():
             ref_losses = [float(ref.train_batch(i, t).item()) for i, t in steps]
             errs = [rel(a, b) for a, b in zip(mine, ref.get_weights())]
             lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
-            good = max(errs) < 2e-5 and lerr < 1e-5
+            # post-Adagrad weights: exact-fp32 kernels agree to 2e-5; with the 3-pass split GEMMs (x3) the 2^-16 product
+            # error differs between the sharded and the single-GPU reduction orders and Adagrad's g/sqrt(sum g^2) is
+            # sign-like on the first steps, so the stated x3 bound for weights applies (5e-4)
+            good = max(errs) < (2e-5 if tc == "off" else 1e-4) and lerr < 1e-5
             print("DP world=%d V=%d %s tc=%s vocab_parallel=%s: loss err %.2e, weight errs %s -> %s" % (
                 comm.world, V, cell, tc, vp, lerr, ["%.1e" % e for e in errs], "OK" if good else "MISMATCH"), flush=True)
             ok = ok and good
