@@ -183,6 +183,39 @@ struct Share {
 // CTA that owns work item w
 __device__ __forceinline__ int cta_of(int64_t w, int64_t total) { return (int)(((w + 1) * gridDim.x - 1) / total); }
 
+// Wave-synchronous partition for problems whose streamed operand does not fit the L2 (ce_tc_backward_ts_kernel).
+// With the contiguous split above the G CTAs sit at G different positions of the streamed operand at any instant, so
+// every streamed tile is fetched from HBM by almost every CTA that needs it (ncu, cfg3: 46 GB of DRAM reads for 0.3 GB
+// of operands).  Here CTA c takes the WHOLE outer tiles c, c+G, c+2G, ... and walks the inner (streamed) index from 0
+// in each of them: all CTAs stream the same tiles at the same time and the L2 serves G-1 of every G reads.  Only the
+// n_outer % G outer tiles of the last, partial wave are split stream-K style so that no SM idles.
+// Same interface as Share, over a CTA-local item index w in [w0 = 0, w1).
+struct WaveShare {
+  int w0, w1, n_inner;
+  int full_items;          // items of the full waves owned by this CTA = rounds * n_inner
+  int tail_o0;             // first outer tile of the partial wave
+  int t0, t1;              // this CTA's contiguous share of the partial wave's (outer, inner) pairs
+  __device__ __forceinline__ WaveShare(int n_outer, int n_inner_) : n_inner(n_inner_) {
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    const int rounds = n_outer / G;
+    full_items = rounds * n_inner;
+    tail_o0 = rounds * G;
+    const int64_t tail_total = (int64_t)(n_outer - tail_o0) * n_inner;
+    t0 = (int)(tail_total * c / G);
+    t1 = (int)(tail_total * (c + 1) / G);
+    w0 = 0;
+    w1 = full_items + (t1 - t0);
+  }
+  __device__ __forceinline__ int outer(int w) const {
+    return w < full_items ? (w / n_inner) * (int)gridDim.x + (int)blockIdx.x : tail_o0 + (t0 + (w - full_items)) / n_inner;
+  }
+  __device__ __forceinline__ int inner(int w) const {
+    return w < full_items ? w % n_inner : (t0 + (w - full_items)) % n_inner;
+  }
+  __device__ __forceinline__ bool seg_first(int w) const { return w == full_items || inner(w) == 0; }
+  __device__ __forceinline__ bool seg_last(int w) const { return w + 1 == w1 || inner(w) == n_inner - 1; }
+};
+
 // ================================================================================================================
 // forward: per-row (max, sum-exp) partials of logits = A . Bt^T
 //   A  = hout (optionally x dropout factors), [N, Hk] bf16 hi/lo     (tmA_*,  box 64 x 128)
@@ -1154,11 +1187,10 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   }
   const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
   const int n_ttiles = (int)((n_tokens + BM - 1) / BM);
-  const int64_t total = (int64_t)n_vtiles * n_ttiles;
-  const Share sh(total, ITEM_ST ? n_ttiles : n_vtiles);
+  const WaveShare sh(ITEM_ST ? n_vtiles : n_ttiles, ITEM_ST ? n_ttiles : n_vtiles);
   // first row of the stationary / streamed operand of work item w
-  auto p_row0 = [&](int64_t w) { return ITEM_ST ? v_begin + sh.outer(w) * BN : sh.outer(w) * BM; };
-  auto q_row0 = [&](int64_t w) { return ITEM_ST ? sh.inner(w) * BM : v_begin + sh.inner(w) * BN; };
+  auto p_row0 = [&](int w) { return ITEM_ST ? v_begin + sh.outer(w) * BN : sh.outer(w) * BM; };
+  auto q_row0 = [&](int w) { return ITEM_ST ? sh.inner(w) * BM : v_begin + sh.inner(w) * BN; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
@@ -1190,7 +1222,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       if (lane == 0) { ptx::prefetch_tmap(&tmX_hi); ptx::prefetch_tmap(&tmY_hi); ptx::prefetch_tmap(&tmZ_hi); }
       Pipe p;
       int seg = 0;
-      auto load_s_operands = [&](int64_t w) {
+      auto load_s_operands = [&](int w) {
         if (sh.seg_first(w)) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
           const int row0 = p_row0(w);
@@ -1215,7 +1247,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           p.advance(NS);
         }
       };
-      auto load_z = [&](int64_t w) {
+      auto load_z = [&](int w) {
         const int q0 = q_row0(w);
         for (int j = 0; j < NJ; ++j)
           for (int c = 0; c < NC; ++c) {
@@ -1230,7 +1262,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           }
       };
       load_s_operands(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+      for (int w = sh.w0; w < sh.w1; ++w) {
         if (w + 1 < sh.w1) load_s_operands(w + 1);
         load_z(w);
       }
@@ -1241,7 +1273,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
       Pipe p;
       int seg_s = -1, tc_s = 0, seg_d = -1, tc_d = 0;
-      auto issue_s = [&](int64_t w) {
+      auto issue_s = [&](int w) {
         if (sh.seg_first(w)) {
           ++seg_s;
           ptx::mbar_wait(bar_a, seg_s & 1);
@@ -1264,7 +1296,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         ++tc_s;
       };
       issue_s(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
+      for (int w = sh.w0; w < sh.w1; ++w) {
         if (w + 1 < sh.w1) issue_s(w + 1);
         const bool first = sh.seg_first(w);
         if (first) {
@@ -1324,7 +1356,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       }
       epi_bar_sync();
     }
-    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+    for (int w = sh.w0; w < sh.w1; ++w, ++tc) {
       const int buf = tc % SBUF;
       if (sh.seg_first(w)) {
         ++seg;
