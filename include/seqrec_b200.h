@@ -163,6 +163,14 @@ int seqrec_predict_probs(const float* hout, const float* W_out, const float* b_o
 int seqrec_topk(const float* hout, const float* W_out, const float* b_out, const float* m, const float* s,
                 int32_t* topk_ids, float* topk_p, int64_t n_rows, int H, int V, int k, void* stream);
 
+/* top-k on the tcgen05 tensor cores (csrc/ce_tc.cu): logits tiles as in seqrec_ce_tc_forward; every epilogue thread
+ * keeps a private top-k list of its (row, column-half) stream, a second kernel merges the lists of a row (value
+ * descending, lower item id first on ties).  ws_v / ws_i: seqrec_ce_tc_partials(n_rows, 0, V) * n_rows * k elements.
+ * k <= 32. */
+int seqrec_topk_tc(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                   const float* b_out, const float* m, const float* s, float* ws_v, int32_t* ws_i, int32_t* topk_ids,
+                   float* topk_p, int64_t n_rows, int Hk, int V, int k, int x3, void* stream);
+
 /* ---- K8: global-norm clip + Adagrad (experiments_methods.py:41) -------------------------------------------------
  * sumsq[0] (double, pre-zeroed) += sum g^2 */
 int seqrec_sumsq(const float* g, int64_t n, double* sumsq, void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "seqrec_target_logit": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_predict_probs": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "seqrec_topk": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p],
+    "seqrec_topk_tc": [_p] * 11 + [_l, _i, _i, _i, _i, _p],
     "seqrec_sumsq": [_p, _l, _p, _p],
     "seqrec_sumsq_rows": [_p, _p, _p, _i, _i, _p, _p],
     "seqrec_adagrad": [_p, _p, _p, _l, _f, _f, _f, _p, _p],

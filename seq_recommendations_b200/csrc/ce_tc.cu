@@ -618,6 +618,248 @@ ce_tc_forward_atm_kernel(const uint16_t* __restrict__ A_hi, const uint16_t* __re
   }
 }
 
+// ================================================================================================================
+// K9 on the tensor cores: top-k next items per token row, never materialising the (N,V) logits.
+// Same MMA pipeline as ce_tc_forward_atm_kernel (token tile in TMEM, W_out^T streamed by TMA); the epilogue thread that
+// owns (row, 64-column half) keeps a private, descending top-k list in shared memory ([k][thread] -> conflict free)
+// and a register threshold = its current k-th value.  A 64-column slab is skipped after ONE comparison of its maximum
+// with the threshold; an insertion is rare (k.ln(n/k) per stream).  Items reach a thread in ascending id order and an
+// insertion goes BEHIND equal values, so ties are won by the lower item id (the stable-argsort order of the oracle).
+// Every (token tile, CTA, half) stream leaves one list; topk_merge_kernel merges the lists of a row.
+constexpr int TOPK_MAX = 32;
+
+__device__ __noinline__ float topk_insert(float* lv, int32_t* li, int k, float z, int32_t id) {
+  int i = k - 1;
+  while (i > 0 && lv[(i - 1) * 256] < z) {
+    lv[i * 256] = lv[(i - 1) * 256];
+    li[i * 256] = li[(i - 1) * 256];
+    --i;
+  }
+  lv[i * 256] = z;
+  li[i * 256] = id;
+  return lv[(k - 1) * 256];
+}
+
+template <int KB, int NS, bool X3, bool BIAS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ce_tc_topk_kernel(const uint16_t* __restrict__ A_hi, const uint16_t* __restrict__ A_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const float* __restrict__ b_out, float* __restrict__ cand_v, int32_t* __restrict__ cand_i,
+                  int64_t n_tokens, int v_begin, int v_end, int max_slots, int k) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int HK = KB * KBLK;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;                                  // [NS][NP][TILE_B]
+  const uint32_t sL = sB + NS * NP * TILE_B;                 // lists: values [TOPK_MAX][256], ids [TOPK_MAX][256]
+  const uint32_t sBar = sL + 2 * TOPK_MAX * 256 * 4;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
+                 tmem_slot = bar_afree + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
+  const Share sh(total, n_vtiles);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
+    ptx::mbar_init(bar_a, N_EPI_WARPS);
+    ptx::mbar_init(bar_afree, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_a = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    if (lane == 0) ptx::prefetch_tmap(&tmB_hi);
+    Pipe p;
+    for (int64_t w = sh.w0; w < sh.w1; ++w) {
+      const int v0 = v_begin + sh.inner(w) * BN;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+          const uint32_t dst = sB + p.stage * NP * TILE_B;
+          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
+          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+        }
+        p.advance(NS);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+    Pipe p;
+    int seg = -1, tc = 0;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      if (sh.seg_first(w)) {
+        ++seg;
+        ptx::mbar_wait(bar_a, seg & 1);
+        ptx::tc_fence_after_sync();
+      }
+      const int buf = tc & 1;
+      ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d = tmem_base + buf * BN;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t b = sB + p.stage * NP * TILE_B;
+        const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < KBLK / 16; ++kk) {
+            const uint32_t a_hi = tmem_a + kb * (KBLK / 2) + kk * 8, a_lo = a_hi + HK / 2;
+            const uint32_t acc = (kb == 0 && kk == 0) ? 0u : 1u;
+            if (X3) {
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, kk * 16), idesc, acc);
+              ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, kk * 16), idesc, 1u);
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, kk * 16), idesc, 1u);
+            } else {
+              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, kk * 16), idesc, acc);
+            }
+          }
+        }
+        __syncwarp();
+        commit_elect(bar_empty + 8 * p.stage);
+        p.advance(NS);
+      }
+      commit_elect(bar_tfull + 8 * buf);
+      if (sh.seg_last(w)) commit_elect(bar_afree);
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int e = threadIdx.x - 64;                          // 0..255
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float* lv = reinterpret_cast<float*>(smem_raw + (sL - ptx::smem_u32(smem_raw))) + e;
+    int32_t* li = reinterpret_cast<int32_t*>(smem_raw + (sL - ptx::smem_u32(smem_raw))) + TOPK_MAX * 256 + e;
+    float thr = -INFINITY;
+    int tc = 0, seg = -1;
+    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+      const int buf = tc & 1;
+      const int tt = sh.outer(w), vt = sh.inner(w);
+      if (sh.seg_first(w)) {
+        ++seg;
+        for (int j = 0; j < k; ++j) { lv[j * 256] = -INFINITY; li[j * 256] = 0x7fffffff; }
+        thr = -INFINITY;
+        if (seg > 0) {
+          ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int64_t n = (int64_t)tt * BM + row;
+        row_to_tmem(tmem_a + lane_off + half * (HK / 4), A_hi, n, HK, half * (HK / 2), HK / 64, n < n_tokens);
+        if (X3)
+          row_to_tmem(tmem_a + lane_off + HK / 2 + half * (HK / 4), A_lo, n, HK, half * (HK / 2), HK / 64,
+                      n < n_tokens);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_a);
+      }
+      const int vc0 = v_begin + vt * BN + half * 64;
+      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      float z[64];
+      load_half_tile(tmem_base + lane_off + buf * BN + half * 64, z);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
+      if (BIAS || vc0 + 64 > v_end) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int v = vc0 + j;
+          if (v < v_end) { if (BIAS) z[j] += __ldg(b_out + v); }
+          else z[j] = -INFINITY;
+        }
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        mx[0] = fmaxf(mx[0], z[j]); mx[1] = fmaxf(mx[1], z[j + 1]);
+        mx[2] = fmaxf(mx[2], z[j + 2]); mx[3] = fmaxf(mx[3], z[j + 3]);
+      }
+      if (fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) > thr) {     // rare after the first tiles
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (z[j] > thr) thr = topk_insert(lv, li, k, z[j], vc0 + j);
+      }
+      if (sh.seg_last(w)) {
+        const int64_t n = (int64_t)tt * BM + row;
+        if (n < n_tokens) {
+          const int slot = (int)blockIdx.x - cta_of((int64_t)tt * n_vtiles, total);
+          const int64_t o = (((int64_t)slot * 2 + half) * n_tokens + n) * k;
+          for (int j = 0; j < k; ++j) { cand_v[o + j] = lv[j * 256]; cand_i[o + j] = li[j * 256]; }
+          if (vt == n_vtiles - 1) {                          // last CTA of this token tile: blank the unused slots
+            for (int sl = slot + 1; sl < max_slots; ++sl) {
+              const int64_t ob = (((int64_t)sl * 2 + half) * n_tokens + n) * k;
+              for (int j = 0; j < k; ++j) { cand_v[ob + j] = -INFINITY; cand_i[ob + j] = 0x7fffffff; }
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// one warp per row: k rounds of (value descending, id ascending) selection over the row's n_lists * k candidates
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const float* __restrict__ cand_v, const int32_t* __restrict__ cand_i, int n_lists,
+                  const float* __restrict__ mrow, const float* __restrict__ srow, int32_t* __restrict__ topk_ids,
+                  float* __restrict__ topk_p, int64_t n_rows, int k) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_rows) return;
+  const int total = n_lists * k;
+  constexpr int PER = 12;                                    // candidates per lane (n_lists * k <= 384)
+  float v[PER];
+  int32_t id[PER];
+#pragma unroll
+  for (int c = 0; c < PER; ++c) {
+    const int x = c * 32 + lane;
+    v[c] = -INFINITY; id[c] = 0x7fffffff;
+    if (x < total) {
+      const int64_t o = ((int64_t)(x / k) * n_rows + n) * k + (x % k);
+      v[c] = cand_v[o]; id[c] = cand_i[o];
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    float bv = -INFINITY;
+    int32_t bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < PER; ++c)
+      if (v[c] > bv || (v[c] == bv && id[c] < bi)) { bv = v[c]; bi = id[c]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+#pragma unroll
+    for (int c = 0; c < PER; ++c)
+      if (id[c] == bi) { v[c] = -INFINITY; id[c] = 0x7fffffff; }   // ids are unique across the lists
+    if (lane == 0) {
+      topk_ids[n * k + j] = bi;
+      if (topk_p) topk_p[n * k + j] = (mrow && srow) ? expf(bv - mrow[n]) / srow[n] : bv;
+    }
+  }
+}
+
 // flush a [128 x ncols] fp32 TMEM accumulator slice owned by this warp (32 rows x `ncols` columns starting at
 // column col0) into global memory with vector reductions: dst_row points at this thread's row, column col0
 __device__ __forceinline__ void flush_acc_red(uint32_t taddr, int ncols, float* dst_row, int valid_cols, bool row_ok,
@@ -1551,7 +1793,59 @@ int launch_fwd_atm(const uint16_t* A_hi, const uint16_t* A_lo, const CUtensorMap
   return 0;
 }
 
+template <int KB, bool X3, bool BIAS>
+int launch_topk(const uint16_t* A_hi, const uint16_t* A_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                const float* b_out, float* cand_v, int32_t* cand_i, int64_t n_rows, int V, int k, cudaStream_t st) {
+  constexpr int NP = X3 ? 2 : 1;
+  constexpr int NS = X3 ? 4 : 8;
+  const size_t smem = 1024 + (size_t)NS * NP * TILE_B + 2 * TOPK_MAX * 256 * 4 + 256;
+  auto kern = ce_tc_topk_kernel<KB, NS, X3, BIAS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -(int)e;
+  const int64_t total = ((n_rows + BM - 1) / BM) * ceil_div(V, BN);
+  kern<<<persistent_grid(total), TC_THREADS, smem, st>>>(A_hi, A_lo, b_hi, b_lo, b_out, cand_v, cand_i, n_rows, 0, V,
+                                                         forward_slots(n_rows, 0, V), k);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace
+
+// top-k on the tensor cores: A / Bt operands as for seqrec_ce_tc_forward; ws_v / ws_i hold
+// seqrec_ce_tc_partials(n_rows, 0, V) * n_rows * k candidates.  k <= 32 and partials * k <= 384.
+extern "C" int seqrec_topk_tc(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                              const float* b_out, const float* m, const float* s, float* ws_v, int32_t* ws_i,
+                              int32_t* topk_ids, float* topk_p, int64_t n_rows, int Hk, int V, int k, int x3,
+                              void* stream) {
+  SEQREC_ARG(n_rows > 0 && V > 0 && k >= 1 && k <= TOPK_MAX && k <= V, 1);
+  SEQREC_ARG(Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256, 2);
+  SEQREC_ARG(A_hi && Bt_hi && (!x3 || (A_lo && Bt_lo)) && ws_v && ws_i && topk_ids, 3);
+  const int n_lists = 2 * forward_slots(n_rows, 0, V);
+  SEQREC_ARG(n_lists * k <= 384, 4);
+  CUtensorMap b_hi, b_lo;
+  int rc;
+  if ((rc = make_tmap(&b_hi, Bt_hi, V, Hk, Hk, BN))) return rc;
+  if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
+  cudaStream_t st = as_stream(stream);
+#define TK2(KB, X3V, BV) rc = launch_topk<KB, X3V, BV>(A_hi, x3 ? A_lo : A_hi, b_hi, b_lo, b_out, ws_v, ws_i, n_rows, V, k, st)
+#define TK(KB)                                                                   \
+  {                                                                              \
+    if (x3) { if (b_out) TK2(KB, true, true); else TK2(KB, true, false); }       \
+    else    { if (b_out) TK2(KB, false, true); else TK2(KB, false, false); }     \
+  }
+  switch (Hk / KBLK) {
+    case 1: TK(1) break;
+    case 2: TK(2) break;
+    case 3: TK(3) break;
+    default: TK(4) break;
+  }
+#undef TK2
+#undef TK
+  if (rc) return rc;
+  topk_merge_kernel<<<ceil_div(n_rows * 32, 256), 256, 0, st>>>(ws_v, ws_i, n_lists, m, s, topk_ids, topk_p, n_rows, k);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
 
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,

@@ -809,8 +809,18 @@ class HotPath:
             hrows, m, s, n = w.hout, w.m, w.s, w.N
         out_i = torch.empty((n, k), dtype=torch.int32, device=self.device)
         out_p = torch.empty((n, k), dtype=torch.float32, device=self.device)
-        call("seqrec_topk", ptr(hrows), ptr(self.W_out), ptr(self.b_out), ptr(m), ptr(s), ptr(out_i), ptr(out_p), n,
-             self.H, self.V, int(k), self.stream)
+        wt = wl if last_step_only else w
+        n_lists = wt.tc["splits"] if wt.tc["fwd"] else 0
+        if wt.tc["fwd"] and k <= 32 and n_lists * k <= 384 and os.environ.get("SEQREC_TOPK_TC", "1") != "0":
+            # tensor-core ranking: the bf16 hi/lo operands were staged by the statistics pass above
+            ws_v = torch.empty((n_lists, n, k), dtype=torch.float32, device=self.device)
+            ws_i = torch.empty((n_lists, n, k), dtype=torch.int32, device=self.device)
+            call("seqrec_topk_tc", ptr(wt.A_hi), ptr(wt.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out), ptr(m),
+                 ptr(s), ptr(ws_v), ptr(ws_i), ptr(out_i), ptr(out_p), n, self.Hk, self.V, int(k),
+                 1 if self.tc_x3 else 0, self.stream)
+        else:
+            call("seqrec_topk", ptr(hrows), ptr(self.W_out), ptr(self.b_out), ptr(m), ptr(s), ptr(out_i), ptr(out_p), n,
+                 self.H, self.V, int(k), self.stream)
         if last_step_only:
             return out_i, out_p
         return (out_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),

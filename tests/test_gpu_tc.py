@@ -187,3 +187,34 @@ def test_cfg2_full_size_properties():
         assert abs(float(torch.logsumexp(z, 0)) - float(lse[n])) <= 1e-4
     assert abs(losses["x3"][0] / losses["off"][0] - 1) <= 1e-5
     assert abs(losses["x3"][1] / losses["off"][1] - 1) <= 1e-4
+
+
+@pytest.mark.parametrize("V,H,T,B", [(5000, 128, 6, 160), (20011, 256, 4, 300), (1000, 64, 3, 130)])
+def test_tc_topk_matches_simt_topk_including_ties(V, H, T, B, monkeypatch):
+    """Tensor-core ranking (per-thread lists + merge) vs the SIMT top-k: identical ids in identical order, for the last
+    step and for every step.  Duplicated W_out columns produce exact ties: the lower item id must win in both."""
+    ws = synthetic.make_weights("GRU", V, H, seed=13)
+    ws[3] = ws[3] * 10.0
+    ws[3][:, 7] = ws[3][:, 3]                 # exact ties between items 3 and 7, 40 and 41
+    ws[3][:, 41] = ws[3][:, 40]
+    ws[3][:, [3, 7, 40, 41]] *= 3.0           # ... and make them likely to rank
+    ids, _ = synthetic.make_batch(V, T, B, seed=14)
+    hot = HotPath("GRU", "tanh", V, H, V, weights=ws, tc="x3")
+    k = 20
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SEQREC_TOPK_TC", flag)
+        last_i, last_p = hot.topk_batch(ids, k, last_step_only=True)
+        all_i, all_p = hot.topk_batch(ids, k, last_step_only=False)
+        res[flag] = [x.cpu().numpy() for x in (last_i, last_p, all_i, all_p)]
+    assert hot.work(B, 1).tc["fwd"]
+    assert np.array_equal(res["1"][0], res["0"][0])
+    assert np.array_equal(res["1"][2], res["0"][2])
+    assert np.abs(res["1"][1] / res["0"][1] - 1).max() <= 1e-4
+    assert np.abs(res["1"][3] / res["0"][3] - 1).max() <= 1e-4
+    # ties: whenever both items of a tied pair are listed, the lower id comes first
+    for a, b in ((3, 7), (40, 41)):
+        for r in res["1"][0]:
+            r = r.tolist()
+            if a in r and b in r:
+                assert r.index(a) + 1 == r.index(b)
