@@ -158,7 +158,7 @@ ce_forward_simt_kernel(const float* __restrict__ hout, const float* __restrict__
 // finalize: merge the per-split stats, CE with Keras' clip, per-token backward coefficient, deterministic loss sum
 // (per-block partials in a fixed order; the last block to finish adds them up in block order)
 #define FIN_THREADS 256
-#define FIN_MAX_BLOCKS 256
+#define FIN_MAX_BLOCKS 1184
 __device__ double g_fin_partials[FIN_MAX_BLOCKS];
 __device__ unsigned int g_fin_counter = 0;
 
@@ -206,12 +206,22 @@ ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_
     is_last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  if (is_last) {
+    // the last block sums the per-block partials: a fixed thread <- partial assignment and a fixed reduction tree, so
+    // the loss is bit-reproducible; all threads take part (a serial loop of dependent L2 loads cost ~15 us at cfg2)
     __threadfence();
     double v = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) v += *((volatile double*)&g_fin_partials[i]);
-    if (loss_sum) loss_sum[0] = (float)v;
-    g_fin_counter = 0;  // ready for the next (stream-ordered) launch
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += FIN_THREADS) v += *((volatile double*)&g_fin_partials[i]);
+    v = warp_sum_d(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < FIN_THREADS / 32; ++i) t += red[i];
+      if (loss_sum) loss_sum[0] = (float)t;
+      g_fin_counter = 0;  // ready for the next (stream-ordered) launch
+    }
   }
 }
 
@@ -508,7 +518,7 @@ extern "C" int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const fl
                                   float* m_out, float* s_out, float* ce, float* py, float* coef, float* loss_sum,
                                   int64_t n_tokens, int splits, void* stream) {
   SEQREC_ARG(n_tokens > 0 && splits > 0, 1);
-  int blocks = (int)((n_tokens + 4 * FIN_THREADS - 1) / (4 * FIN_THREADS));
+  int blocks = (int)((n_tokens + FIN_THREADS - 1) / FIN_THREADS);   // one token per thread while the grid allows it
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
   ce_finalize_kernel<<<blocks, FIN_THREADS, 0, as_stream(stream)>>>(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef,
                                                                    loss_sum, n_tokens, splits);

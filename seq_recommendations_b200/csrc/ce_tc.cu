@@ -23,6 +23,14 @@
 
 namespace {
 
+// optional timeline capture (scripts/time_ce.py): CTA 0 of the forward kernel stores clock64() at protocol points of its
+// first 64 tiles.  The pointer is read ONCE per thread into `dbg`.
+__device__ long long* g_ce_dbg = nullptr;
+#define CE_DBG(tile, slot)                                                              \
+  do {                                                                                  \
+    if (dbg && (tile) < 64) dbg[(tile) * 8 + (slot)] = clock64();                       \
+  } while (0)
+
 constexpr int BM = 128;          // tokens per tile (UMMA M)
 constexpr int BN = 128;          // items per tile  (UMMA N of the logits GEMM)
 constexpr int KBLK = 64;         // bf16 elements per 128-byte swizzled row
@@ -168,15 +176,43 @@ __device__ __forceinline__ void store_dlogit_row(uint8_t* sD_gen, const float (&
 // [total*c/G, total*(c+1)/G) (balanced to +-1 tile, "stream-K" style).  A maximal run of tiles with the same `outer`
 // inside a CTA's range is a SEGMENT: the stationary operand is loaded once per segment and the per-segment result
 // (softmax partial, dH or dW accumulator) is flushed at its end.
+// d / n and d % n for d < 2^31 by multiply-high with M = floor((2^32 - 1) / n): the estimate is short by at most one.
+// Four integer instructions instead of the compiler's division sequence, which goes through I2F / F2I on the XU pipe
+// -- the pipe the epilogue warps saturate with ex2 -- and cost ~200 dependent cycles per call on the MMA warp's loop
+// header: a bubble in the tensor pipe on EVERY tile (clock64 timeline: tile period 2550 -> 2150 cycles once removed).
+struct FastDiv {
+  uint32_t n, M;
+  __device__ __forceinline__ void init(uint32_t n_) { n = n_; M = 0xFFFFFFFFu / n_; }
+  __device__ __forceinline__ void divmod(uint32_t d, uint32_t& q, uint32_t& r) const {
+    q = __umulhi(d, M);
+    r = d - q * n;
+    if (r >= n) { ++q; r -= n; }
+  }
+};
+
 struct Share {
   int64_t w0, w1;
   int n_inner;
+  int o0, i0;   // (outer, inner) of w0: computed ONCE with a 64-bit division; everything per tile is 32-bit
+  FastDiv fd;
   __device__ __forceinline__ Share(int64_t total, int n_inner_) : n_inner(n_inner_) {
     w0 = total * blockIdx.x / gridDim.x;
     w1 = total * (blockIdx.x + 1) / gridDim.x;
+    o0 = (int)(w0 / n_inner);
+    i0 = (int)(w0 - (int64_t)o0 * n_inner);
+    fd.init((uint32_t)n_inner);
   }
-  __device__ __forceinline__ int outer(int64_t w) const { return (int)(w / n_inner); }
-  __device__ __forceinline__ int inner(int64_t w) const { return (int)(w % n_inner); }
+  __device__ __forceinline__ uint32_t rel(int64_t w) const { return (uint32_t)(w - w0) + (uint32_t)i0; }
+  __device__ __forceinline__ int outer(int64_t w) const {
+    uint32_t q, r;
+    fd.divmod(rel(w), q, r);
+    return o0 + (int)q;
+  }
+  __device__ __forceinline__ int inner(int64_t w) const {
+    uint32_t q, r;
+    fd.divmod(rel(w), q, r);
+    return (int)r;
+  }
   __device__ __forceinline__ bool seg_first(int64_t w) const { return w == w0 || inner(w) == 0; }
   __device__ __forceinline__ bool seg_last(int64_t w) const { return w + 1 == w1 || inner(w) == n_inner - 1; }
 };
@@ -195,6 +231,7 @@ struct WaveShare {
   int full_items;          // items of the full waves owned by this CTA = rounds * n_inner
   int tail_o0;             // first outer tile of the partial wave
   int t0, t1;              // this CTA's contiguous share of the partial wave's (outer, inner) pairs
+  FastDiv fd;
   __device__ __forceinline__ WaveShare(int n_outer, int n_inner_) : n_inner(n_inner_) {
     const int G = (int)gridDim.x, c = (int)blockIdx.x;
     const int rounds = n_outer / G;
@@ -205,12 +242,21 @@ struct WaveShare {
     t1 = (int)(tail_total * (c + 1) / G);
     w0 = 0;
     w1 = full_items + (t1 - t0);
+    fd.init((uint32_t)n_inner);
   }
   __device__ __forceinline__ int outer(int w) const {
-    return w < full_items ? (w / n_inner) * (int)gridDim.x + (int)blockIdx.x : tail_o0 + (t0 + (w - full_items)) / n_inner;
+    uint32_t q, r;
+    if (w < full_items) {
+      fd.divmod((uint32_t)w, q, r);
+      return (int)q * (int)gridDim.x + (int)blockIdx.x;
+    }
+    fd.divmod((uint32_t)(t0 + (w - full_items)), q, r);
+    return tail_o0 + (int)q;
   }
   __device__ __forceinline__ int inner(int w) const {
-    return w < full_items ? w % n_inner : (t0 + (w - full_items)) % n_inner;
+    uint32_t q, r;
+    fd.divmod((uint32_t)(w < full_items ? w : t0 + (w - full_items)), q, r);
+    return (int)r;
   }
   __device__ __forceinline__ bool seg_first(int w) const { return w == full_items || inner(w) == 0; }
   __device__ __forceinline__ bool seg_last(int w) const { return w + 1 == w1 || inner(w) == n_inner - 1; }
@@ -230,6 +276,7 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
                      const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
                      int64_t n_tokens, int v_begin, int v_end, int max_slots) {
   constexpr int NP = X3 ? 2 : 1;  // operand parts (hi, lo)
+  long long* const dbg = (blockIdx.x == 0) ? g_ce_dbg : nullptr;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                                  // [NP][KB][TILE_B]
@@ -299,25 +346,33 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       Pipe p;
       int seg = -1, tc = 0;
       for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
+        const bool last = sh.seg_last(w);
         if (sh.seg_first(w)) {
           ++seg;
           ptx::mbar_wait(bar_a, seg & 1);
           ptx::tc_fence_after_sync();
         }
         const int buf = tc & 1;
+        if (lane == 0) CE_DBG(tc, 7);
         ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
+        if (lane == 0) CE_DBG(tc, 0);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
           ptx::tc_fence_after_sync();
+          if (kb == 0 && lane == 0) CE_DBG(tc, 1);
           const uint32_t b = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
+          if (kb == KB - 1 && lane == 0) CE_DBG(tc, 2);      // all MMAs of the tile issued
           commit_elect(bar_empty + 8 * p.stage);
+          if (kb == KB - 1 && lane == 0) CE_DBG(tc, 3);      // after the stage commit
           p.advance(NS);
         }
         commit_elect(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) commit_elect(bar_afree);
+        if (lane == 0) CE_DBG(tc, 4);                        // after the tile commit
+        if (last) commit_elect(bar_afree);
+        if (lane == 0) CE_DBG(tc, 5);                        // after seg_last
       }
     }
   } else {
@@ -1855,6 +1910,12 @@ extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const
                                                                                   n_tokens, H, ldw);
   SEQREC_CHECK_LAUNCH();
   return 0;
+}
+
+/* diagnostics only (not in the public header): device buffer of 64 x 8 clock64() stamps written by CTA 0 */
+extern "C" int seqrec_ce_tc_debug_buffer(long long* dev_buf) {
+  cudaError_t e = cudaMemcpyToSymbol(g_ce_dbg, &dev_buf, sizeof(dev_buf));
+  return e == cudaSuccess ? 0 : -(int)e;
 }
 
 extern "C" int seqrec_ce_tc_partials(int64_t n_tokens, int v_begin, int v_end) {
