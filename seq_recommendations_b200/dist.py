@@ -41,6 +41,14 @@ class Comm:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
+    def all_gather_cat_async(self, t):
+        """Same, issued asynchronously: returns (out, handle); handle.wait() before `out` is read."""
+        if not self.enabled:
+            return t, None
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        h = dist.all_gather_into_tensor(out, t.contiguous(), group=self.group, async_op=True)
+        return out, h
+
     def reduce_scatter_sum(self, out, inp):
         """out (n, ...) = sum over ranks of this rank's block of inp (world*n, ...)."""
         if not self.enabled:

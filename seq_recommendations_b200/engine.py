@@ -527,12 +527,21 @@ class HotPath:
         comm = self.comm
         self._split_version = -1                  # a training step always follows a weight update: re-stage W_out
         n_valid = w.n_valid_i.to(torch.float32)
-        comm.all_reduce_sum(n_valid)
-        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        # data parallel: the ids of all ranks (union of touched rows for the dense dW_in exchange) travel behind the
+        # forward pass; n_valid and loss_sum are reduced together in ONE two-float all-reduce after it (the forward
+        # needs neither: 1/n_valid first enters in the logits backward)
+        dense_rows = (comm.enabled and w.x_dense is None and
+                      embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense")
+        all_ids, ids_handle = comm.all_gather_cat_async(w.ids.view(-1)) if dense_rows else (None, None)
         self._forward_hidden(w, training=True)
         self._forward_ce(w, training=True)
-        loss_sum = w.loss_sum
-        comm.all_reduce_sum(loss_sum)
+        if comm.enabled:
+            pair = torch.cat([n_valid, w.loss_sum])
+            comm.all_reduce_sum(pair)
+            n_valid, loss_sum = pair[0:1], pair[1:2]
+        else:
+            loss_sum = w.loss_sum
+        torch.reciprocal(n_valid, out=self.inv_nvalid)
         loss = loss_sum * self.inv_nvalid
 
         # ---- backward
@@ -553,11 +562,12 @@ class HotPath:
             if not comm.enabled:
                 call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                      ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
-            elif embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense":
+            elif dense_rows:
                 call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                      ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
                 pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
-                all_ids = comm.all_gather_cat(w.ids.view(-1))
+                if ids_handle is not None:
+                    ids_handle.wait()
                 call("seqrec_mark_rows", ptr(all_ids), None, ptr(self.touched), ptr(self.rows), ptr(self.n_rows),
                      all_ids.numel(), self.F, st)
             else:
