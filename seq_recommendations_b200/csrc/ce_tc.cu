@@ -1443,9 +1443,17 @@ template <int KB, bool X3>
 struct TsCfg {
   static constexpr int NP = X3 ? 2 : 1;
   static constexpr int NS_RAW = (224 * 1024 - NP * KB * TILE_B) / (NP * TILE_B);
-  static constexpr int NS = NS_RAW > 8 ? 8 : NS_RAW;
   static constexpr int HK = KB * KBLK;
   static constexpr int NC = (HK + 127) / 128;               // 128-wide hidden chunks of the second GEMM
+  // Two MMA-issuing warps (logits GEMMs on warp 1, gradient GEMMs on warp 2) when the shared-memory ring can be as long
+  // as its period KB + 2*NC: every slot then always carries the same kind of block, so each slot's full barrier has ONE
+  // waiting warp in lock-step with it.  (With a shorter ring the two warps alias on the barriers' phase parity: a warp
+  // that runs ahead sees "its" parity from a completion that belonged to the other warp.)  Hk <= 128 qualifies; at
+  // Hk = 256 the resident operand leaves room for 3 stages only and one warp issues both streams.
+  static constexpr bool TW = (KB <= 2);
+  static constexpr int NS = TW ? (KB + 2 * NC) : (NS_RAW > 8 ? 8 : NS_RAW);
+  static constexpr int THREADS = TW ? 352 : 320;
+  static constexpr int EPI0 = TW ? 3 : 2;                   // first epilogue warp
   static constexpr int ACC_COLS = NC * 128;
   static constexpr int SBUF = (2 * BN + ACC_COLS + BN <= 512) ? 2 : 1;
   static constexpr uint32_t TERMS_B = 128 * 16;             // per-token terms of one streamed tile (ITEM_ST)
@@ -1455,7 +1463,7 @@ struct TsCfg {
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int KB, bool X3, bool ITEM_ST>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(352, 1)
 ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                          const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                          const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant__ CUtensorMap tmZ_lo,
@@ -1564,7 +1572,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         load_z(w);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !C::TW) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
@@ -1635,12 +1643,94 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         ++tc_d;
       }
     }
-  } else {
+  } else if (warp == 1 && C::TW) {
+    // ------------------------------------------------------------------------------------------- MMA issuer, logits
+    // ring positions: S(0) | S(1) G(0) | S(2) G(1) | ... | S(n-1) G(n-2) | G(n-1)   (KB stages per S, NZ per G)
+    if (sh.w0 < sh.w1) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+      constexpr int NZ = NJ * NC;
+      Pipe p;
+      int seg_s = -1, tc_s = 0;
+      for (int w = sh.w0; w < sh.w1; ++w, ++tc_s) {
+        if (sh.seg_first(w)) {
+          ++seg_s;
+          ptx::mbar_wait(bar_a, seg_s & 1);
+          ptx::tc_fence_after_sync();
+        }
+        const int buf = tc_s % SBUF;
+        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s / SBUF) & 1) ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t bb = sB + p.stage * NP * TILE_B;
+          mma_kblock<X3>(d, sX + kb * TILE_B, sX + (KB + kb) * TILE_B, bb, bb + TILE_B, idesc, kb == 0);
+          commit_elect(bar_empty + 8 * p.stage);
+          p.advance(NS);
+        }
+        commit_elect(bar_tfull + 8 * buf);
+        if (sh.seg_last(w)) commit_elect(bar_afree);
+        if (w > sh.w0)                                      // the stages of G(w-1) follow S(w) in the ring
+          for (int i = 0; i < NZ; ++i) p.advance(NS);
+      }
+    }
+  } else if (warp == 2 && C::TW) {
+    // ------------------------------------------------------------------------------------------- MMA issuer, gradient
+    if (sh.w0 < sh.w1) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+      Pipe p;
+      for (int i = 0; i < KB; ++i) p.advance(NS);           // S(w0)
+      int seg_d = -1, tc_d = 0;
+      for (int w = sh.w0; w < sh.w1; ++w) {
+        if (w + 1 < sh.w1)
+          for (int i = 0; i < KB; ++i) p.advance(NS);       // S(w+1) precedes G(w) in the ring
+        const bool first = sh.seg_first(w);
+        if (first) {
+          if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
+            ptx::mbar_wait(bar_hempty, seg_d & 1);
+            ptx::tc_fence_after_sync();
+          }
+          ++seg_d;
+        }
+        ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in tensor memory
+        ptx::tc_fence_after_sync();
+        for (int j = 0; j < NJ; ++j)
+          for (int c = 0; c < NC; ++c) {
+            ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t bb = sB + p.stage * NP * TILE_B;
+            const uint64_t db_hi = ptx::umma_desc_k_sw128(bb), db_lo = ptx::umma_desc_k_sw128(bb + TILE_B);
+            const uint32_t d = tmem_acc + c * 128;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k) {
+                const uint32_t a_hi = tmem_ds + j * (KBLK / 2) + k * 8, a_lo = a_hi + BN / 2;
+                const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
+                if (X3) {
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc, acc);
+                  ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
+                } else {
+                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, acc);
+                }
+              }
+            }
+            __syncwarp();
+            commit_elect(bar_empty + 8 * p.stage);
+            p.advance(NS);
+          }
+        commit_elect(bar_dempty);                           // the dS columns may be overwritten
+        if (sh.seg_last(w)) commit_elect(bar_hfull);
+        ++tc_d;
+      }
+    }
+  } else if (warp >= C::EPI0) {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - C::EPI0) >> 2;
     const int row = q * 32 + lane;
-    const int e = threadIdx.x - 64;                          // 0..255 among the epilogue threads
+    const int e = threadIdx.x - 32 * C::EPI0;                // 0..255 among the epilogue threads
     const float inv = inv_nvalid[0];
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float4* sT_gen = reinterpret_cast<float4*>(smem_raw + (sT - ptx::smem_u32(smem_raw)));
@@ -1802,7 +1892,7 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
   auto k = ce_tc_backward_ts_kernel<KB, X3, ITEM_ST>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
-  k<<<grid, TC_THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
+  k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
                                     n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem);
   SEQREC_CHECK_LAUNCH();
   return 0;
@@ -1993,10 +2083,11 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
-  // Hk > 128: the unified kernel with dS in tensor memory (SEQREC_CE_BWD_TS=1 routes the narrow shapes there too, so
-  // the two implementations can be compared on the same problem)
-  static const bool force_ts = [] { const char* e = getenv("SEQREC_CE_BWD_TS"); return e && e[0] == '1'; }();
-  if (KB > 2 || force_ts) {
+  // The unified kernel with dS in tensor memory serves every width (for Hk <= 128 with two MMA-issuing warps: cfg2
+  // logits backward 0.292 -> 0.272 ms).  SEQREC_CE_BWD_TS=0 routes Hk <= 128 to the two older kernels below (dH with dS
+  // in TMEM, dW with dS in shared memory), so the implementations can be compared on the same problem.
+  static const bool legacy = [] { const char* e = getenv("SEQREC_CE_BWD_TS"); return e && e[0] == '0'; }();
+  if (KB > 2 || !legacy) {
     const int64_t total_ts = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
     const int grid_ts = persistent_grid(total_ts);
     if (dh) {

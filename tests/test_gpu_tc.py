@@ -133,10 +133,10 @@ def test_tc_hidden_256_backward_matches_simt_with_dropout_and_many_segments():
     assert rel_err(res["x3"][1], res["off"][1]) <= 1e-4
 
 
-def test_tc_unified_backward_kernel_on_narrow_hidden(monkeypatch):
-    """SEQREC_CE_BWD_TS=1 routes Hk <= 128 through the unified kernel too (double-buffered logits there): both
-    implementations must agree with the SIMT kernels on the same problem.  The switch is read once per process, so
-    this runs in a subprocess."""
+def test_tc_legacy_backward_kernels_on_narrow_hidden(monkeypatch):
+    """SEQREC_CE_BWD_TS=0 routes Hk <= 128 through the two older kernels (dH with dlogit in TMEM, dW with dlogit in
+    shared memory) instead of the unified one: both implementations must agree with the SIMT kernels on the same
+    problem.  The switch is read once per process, so this runs in a subprocess."""
     import os
     import subprocess
     import sys
@@ -157,7 +157,7 @@ def test_tc_unified_backward_kernel_on_narrow_hidden(monkeypatch):
         "    assert rel_err(res['x3'][1], res['off'][1]) <= 1e-4, rel_err(res['x3'][1], res['off'][1])\n"
         "print('ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SEQREC_CE_BWD_TS="1")
+    env = dict(os.environ, SEQREC_CE_BWD_TS="0")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
