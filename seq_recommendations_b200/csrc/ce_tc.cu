@@ -1445,19 +1445,19 @@ struct TsCfg {
   static constexpr int NS_RAW = (224 * 1024 - NP * KB * TILE_B) / (NP * TILE_B);
   static constexpr int HK = KB * KBLK;
   static constexpr int NC = (HK + 127) / 128;               // 128-wide hidden chunks of the second GEMM
-  // Two MMA-issuing warps (logits GEMMs on warp 1, gradient GEMMs on warp 2) when the shared-memory ring can be as long
-  // as its period KB + 2*NC: every slot then always carries the same kind of block, so each slot's full barrier has ONE
-  // waiting warp in lock-step with it.  (With a shorter ring the two warps alias on the barriers' phase parity: a warp
-  // that runs ahead sees "its" parity from a completion that belonged to the other warp.)  Hk <= 128 qualifies; at
-  // Hk = 256 the resident operand leaves room for 3 stages only and one warp issues both streams.
-  static constexpr bool TW = (KB <= 2);
-  static constexpr int NS = TW ? (KB + 2 * NC) : (NS_RAW > 8 ? 8 : NS_RAW);
+  // Two MMA-issuing warps: logits GEMMs on warp 1, gradient GEMMs on warp 2, both fed from ONE shared-memory ring.
+  // Each ring slot has TWO full barriers, one per kind of block (Y block for the logits GEMM, Z block for the gradient
+  // GEMM), so that every barrier has a single waiting warp in lock-step with it; a consumer tracks the parity of ITS
+  // barrier per slot in a bit mask.  (With one barrier per slot the two warps alias on the phase parity: the warp that
+  // runs ahead takes a completion that belonged to the other warp for its own.)
+  static constexpr bool TW = true;
+  static constexpr int NS = (KB <= 2) ? (KB + 2 * NC) : (NS_RAW > 8 ? 8 : NS_RAW);   // Hk <= 128: ring length = period
   static constexpr int THREADS = TW ? 352 : 320;
   static constexpr int EPI0 = TW ? 3 : 2;                   // first epilogue warp
   static constexpr int ACC_COLS = NC * 128;
   static constexpr int SBUF = (2 * BN + ACC_COLS + BN <= 512) ? 2 : 1;
   static constexpr uint32_t TERMS_B = 128 * 16;             // per-token terms of one streamed tile (ITEM_ST)
-  static constexpr uint32_t SMEM_NEED = NP * KB * TILE_B + NS * NP * TILE_B + TERMS_B + 256;
+  static constexpr uint32_t SMEM_NEED = NP * KB * TILE_B + NS * NP * TILE_B + TERMS_B + 384;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -1484,7 +1484,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
                  bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
                  bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
-                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
+                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8, bar_fullz = tmem_slot + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0 && base - ptx::smem_u32(smem_raw) + C::SMEM_NEED > smem_bytes) {
     printf("seqrec_b200: ce_tc_backward_ts shared-memory layout does not fit (%u needed)\n", C::SMEM_NEED);
@@ -1498,7 +1498,11 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   auto q_row0 = [&](int w) { return ITEM_ST ? sh.inner(w) * BM : v_begin + sh.inner(w) * BN; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(bar_full + 8 * i, 1);
+      ptx::mbar_init(bar_fullz + 8 * i, 1);
+      ptx::mbar_init(bar_empty + 8 * i, 1);
+    }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
     ptx::mbar_init(bar_afree, 1);
@@ -1558,10 +1562,11 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           for (int c = 0; c < NC; ++c) {
             ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
             if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // rows >= Hk arrive as zeros
+              const uint32_t fb = (C::TW ? bar_fullz : bar_full) + 8 * p.stage;
+              ptx::mbar_arrive_expect_tx(fb, NP * TILE_B);   // rows >= Hk arrive as zeros
               const uint32_t dst = sB + p.stage * NP * TILE_B;
-              ptx::tma_load_2d(dst, &tmZ_hi, bar_full + 8 * p.stage, q0 + j * KBLK, c * 128);
-              if (X3) ptx::tma_load_2d(dst + TILE_B, &tmZ_lo, bar_full + 8 * p.stage, q0 + j * KBLK, c * 128);
+              ptx::tma_load_2d(dst, &tmZ_hi, fb, q0 + j * KBLK, c * 128);
+              if (X3) ptx::tma_load_2d(dst + TILE_B, &tmZ_lo, fb, q0 + j * KBLK, c * 128);
             }
             p.advance(NS);
           }
@@ -1650,6 +1655,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
       constexpr int NZ = NJ * NC;
       Pipe p;
+      uint32_t ybits = 0;                                   // parity of the Y-block barrier, per slot
       int seg_s = -1, tc_s = 0;
       for (int w = sh.w0; w < sh.w1; ++w, ++tc_s) {
         if (sh.seg_first(w)) {
@@ -1662,7 +1668,8 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::mbar_wait(bar_full + 8 * p.stage, (ybits >> p.stage) & 1u);
+          ybits ^= 1u << p.stage;
           ptx::tc_fence_after_sync();
           const uint32_t bb = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, sX + kb * TILE_B, sX + (KB + kb) * TILE_B, bb, bb + TILE_B, idesc, kb == 0);
@@ -1680,6 +1687,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
       Pipe p;
+      uint32_t zbits = 0;                                   // parity of the Z-block barrier, per slot
       for (int i = 0; i < KB; ++i) p.advance(NS);           // S(w0)
       int seg_d = -1, tc_d = 0;
       for (int w = sh.w0; w < sh.w1; ++w) {
@@ -1697,7 +1705,8 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         ptx::tc_fence_after_sync();
         for (int j = 0; j < NJ; ++j)
           for (int c = 0; c < NC; ++c) {
-            ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+            ptx::mbar_wait(bar_fullz + 8 * p.stage, (zbits >> p.stage) & 1u);
+            zbits ^= 1u << p.stage;
             ptx::tc_fence_after_sync();
             const uint32_t bb = sB + p.stage * NP * TILE_B;
             const uint64_t db_hi = ptx::umma_desc_k_sw128(bb), db_lo = ptx::umma_desc_k_sw128(bb + TILE_B);
