@@ -36,6 +36,7 @@ constexpr int BN = 128;          // items per tile  (UMMA N of the logits GEMM)
 constexpr int KBLK = 64;         // bf16 elements per 128-byte swizzled row
 constexpr int TILE_B = 128 * 128;  // bytes of one [128 rows x 64 bf16] operand block
 constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int TCF_THREADS = 352; // forward: warps 1 and 2 issue alternate tiles, warps 3..10 epilogue
 constexpr int N_EPI_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -270,31 +271,42 @@ struct WaveShare {
 // Every segment writes one partial per 64-column half into ws[(slot*2 + half)][n], slot = position of the CTA among
 // the CTAs sharing that token tile; slots a token tile does not use are filled with (-inf, 0).
 template <int KB, int NS, bool X3, bool BIAS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCF_THREADS, 1)
 ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                      const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
                      int64_t n_tokens, int v_begin, int v_end, int max_slots) {
   constexpr int NP = X3 ? 2 : 1;  // operand parts (hi, lo)
-  long long* const dbg = (blockIdx.x == 0) ? g_ce_dbg : nullptr;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;                                  // [NP][KB][TILE_B]
   const uint32_t sB = sA + NP * KB * TILE_B;                 // [NS][NP][TILE_B]
   const uint32_t sBar = sB + NS * NP * TILE_B;               // barriers
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
-                 tmem_slot = bar_afree + 8;
+  // Two MMA-issuing warps take alternate tiles (warp 1 the even ones into logits buffer 0, warp 2 the odd ones into
+  // buffer 1): while one warp sits in the waits / fences / commits between two of its tiles, the other has MMAs queued,
+  // so the tensor pipe no longer drains once per tile (tile period 2330 -> ~1600 cycles for 1536 of MMA at Hk = 128).
+  // Each ring slot has one full barrier PER ISSUING WARP (a warp must never take the other's completion for its own:
+  // parity aliasing) and one "token tile no longer read" barrier per issuing warp, committed exactly once per segment
+  // (tcgen05.commit also when the warp owns no tile of a one-tile segment: commit arrivals of one thread complete in
+  // order, a plain arrive could overtake the commit of the previous segment).
+  const uint32_t bar_full = sBar, bar_empty = sBar + 16 * NS, bar_tfull = sBar + 24 * NS,
+                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,   // afree: one per MMA warp
+                 tmem_slot = bar_afree + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
   const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
   const Share sh(total, n_vtiles);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(bar_full + 8 * i, 1);                   // even tiles (warp 1)
+      ptx::mbar_init(bar_full + 8 * (NS + i), 1);            // odd tiles  (warp 2)
+      ptx::mbar_init(bar_empty + 8 * i, 1);
+    }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
     ptx::mbar_init(bar_a, 1);
     ptx::mbar_init(bar_afree, 1);
+    ptx::mbar_init(bar_afree + 8, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -315,7 +327,10 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       int seg = 0;
       for (int64_t w = sh.w0; w < sh.w1; ++w) {
         if (sh.seg_first(w)) {
-          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);   // the previous segment's MMAs have read sA
+          if (seg > 0) {                                           // the previous segment's MMAs have read sA
+            ptx::mbar_wait(bar_afree, (seg - 1) & 1);
+            ptx::mbar_wait(bar_afree + 8, (seg - 1) & 1);
+          }
           const int row0 = sh.outer(w) * BM;
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
@@ -327,58 +342,64 @@ ce_tc_forward_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           ++seg;
         }
         const int v0 = v_begin + sh.inner(w) * BN;
+        const int owner = (int)(w - sh.w0) & 1;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
+            const uint32_t fb = bar_full + 8 * (owner * NS + p.stage);
+            ptx::mbar_arrive_expect_tx(fb, NP * TILE_B);
             const uint32_t dst = sB + p.stage * NP * TILE_B;
-            ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
-            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
+            ptx::tma_load_2d(dst, &tmB_hi, fb, kb * KBLK, v0);
+            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, fb, kb * KBLK, v0);
           }
           p.advance(NS);
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------- MMA issuer
+  } else if (warp <= 2) {
+    // ------------------------------------------------------------------------------------------- MMA issuers
     {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      const int me = warp - 1;                               // 0: even tiles, 1: odd tiles
+      const uint32_t my_full = bar_full + 8 * (me * NS);
       Pipe p;
+      uint32_t bits = 0;                                     // parity of MY full barrier, per slot
       int seg = -1, tc = 0;
       for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
-        const bool last = sh.seg_last(w);
-        if (sh.seg_first(w)) {
-          ++seg;
+        const bool first = sh.seg_first(w), last = sh.seg_last(w);
+        if (first) ++seg;
+        if ((tc & 1) != me) {                                // the other warp's tile: only keep the ring position
+          for (int kb = 0; kb < KB; ++kb) p.advance(NS);
+          if (first && last) commit_elect(bar_afree + 8 * me);   // a one-tile segment I have no part in
+          continue;
+        }
+        // my first tile of this segment: the token tile must have landed
+        if (first || (w > sh.w0 && sh.seg_first(w - 1))) {
           ptx::mbar_wait(bar_a, seg & 1);
           ptx::tc_fence_after_sync();
         }
-        const int buf = tc & 1;
-        if (lane == 0) CE_DBG(tc, 7);
+        const int buf = me;
         ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
-        if (lane == 0) CE_DBG(tc, 0);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
+          ptx::mbar_wait(my_full + 8 * p.stage, (bits >> p.stage) & 1u);
+          bits ^= 1u << p.stage;
           ptx::tc_fence_after_sync();
-          if (kb == 0 && lane == 0) CE_DBG(tc, 1);
           const uint32_t b = sB + p.stage * NP * TILE_B;
           mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
-          if (kb == KB - 1 && lane == 0) CE_DBG(tc, 2);      // all MMAs of the tile issued
           commit_elect(bar_empty + 8 * p.stage);
-          if (kb == KB - 1 && lane == 0) CE_DBG(tc, 3);      // after the stage commit
           p.advance(NS);
         }
         commit_elect(bar_tfull + 8 * buf);
-        if (lane == 0) CE_DBG(tc, 4);                        // after the tile commit
-        if (last) commit_elect(bar_afree);
-        if (lane == 0) CE_DBG(tc, 5);                        // after seg_last
+        // my last tile of this segment (the segment's last tile, or the one before it): sA is no longer read by me
+        if (last || (w + 1 < sh.w1 && sh.seg_last(w + 1))) commit_elect(bar_afree + 8 * me);
       }
     }
   } else {
     // ------------------------------------------------------------------------------------------- epilogue
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;            // which 64-column half of the tile this warp owns
+    const int half = (warp - 3) >> 2;            // which 64-column half of the tile this warp owns
     const int row = q * 32 + lane;
     float m = -INFINITY, s = 0.f;
     int tc = 0;
@@ -1884,8 +1905,8 @@ int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorM
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
-  k<<<persistent_grid(total), TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin,
-                                                      v_end, forward_slots(n_tokens, v_begin, v_end));
+  k<<<persistent_grid(total), TCF_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin,
+                                                       v_end, forward_slots(n_tokens, v_begin, v_end));
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
