@@ -195,6 +195,11 @@ int seqrec_dropout_mask(float* out, int64_t n, float rate, uint64_t seed, uint64
 int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols,
                       int64_t ld_out, int transpose, void* stream);
 
+/* the same with BOTH layouts from one read of src: hi/lo (rows, cols; leading dimension ld_out) and hi_t/lo_t
+ * (cols, rows; leading dimension ld_t) */
+int seqrec_split_bf16_both(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, uint16_t* hi_t,
+                           uint16_t* lo_t, int64_t rows, int64_t cols, int64_t ld_out, int64_t ld_t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -207,6 +207,51 @@ __global__ void split_bf16_t_kernel(const float* __restrict__ src, const float* 
   }
 }
 
+// both layouts from ONE read of the source: out (rows, cols) with leading dimension ld_out AND out_t (cols, rows) with
+// leading dimension ld_t (32x32 tiles through shared memory)
+__global__ void split_bf16_both_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                       __nv_bfloat16* __restrict__ hi_t, __nv_bfloat16* __restrict__ lo_t,
+                                       int64_t rows, int64_t cols, int64_t ld_out, int64_t ld_t) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    float x = 0.f;
+    if (r < rows && c < cols) {
+      x = src[r * cols + c];
+      if (scale) x *= scale[r * cols + c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[r * ld_out + c] = h;
+      if (lo) lo[r * ld_out + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float x = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi_t[c * ld_t + r] = h;
+      if (lo_t) lo_t[c * ld_t + r] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+extern "C" int seqrec_split_bf16_both(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, uint16_t* hi_t,
+                                      uint16_t* lo_t, int64_t rows, int64_t cols, int64_t ld_out, int64_t ld_t,
+                                      void* stream) {
+  SEQREC_ARG(src && hi && hi_t && rows > 0 && cols > 0 && ld_out >= cols && ld_t >= rows, 1);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+  SEQREC_ARG(grid.y <= 65535, 2);
+  split_bf16_both_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      src, scale, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
+      reinterpret_cast<__nv_bfloat16*>(hi_t), reinterpret_cast<__nv_bfloat16*>(lo_t), rows, cols, ld_out, ld_t);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, int64_t rows,
                                  int64_t cols, int64_t ld_out, int transpose, void* stream) {
   SEQREC_ARG(rows > 0 && cols > 0 && ld_out > 0, 1);

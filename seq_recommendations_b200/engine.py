@@ -71,6 +71,7 @@ class _Work:
         self.graph_calls = 0
         self.graph_loss = None
         self.D_hi = self.D_lo = self.Hs_hi = self.Hs_lo = self.C_hi = self.C_lo = None   # bf16 operands of the dU GEMM
+        self.tc_operands_fresh = False         # A_hi / A_lo hold the split of the CURRENT hout
         # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
         self.tc = hp._tc_plan(N)
         if self.tc["fwd"]:
@@ -236,10 +237,9 @@ class HotPath:
                 self.Bt_lo = torch.zeros((self.V, self.Hk), dtype=bf, device=self.device)
                 self.Wb_lo = torch.zeros((self.Hk, self.Vp), dtype=bf, device=self.device)
         st = self.stream
-        call("seqrec_split_bf16", ptr(self.W_out), None, ptr(self.Bt_hi), ptr(self.Bt_lo), self.H, self.V, self.Hk, 1,
-             st)
-        call("seqrec_split_bf16", ptr(self.W_out), None, ptr(self.Wb_hi), ptr(self.Wb_lo), self.H, self.V, self.Vp, 0,
-             st)
+        # W (H, V; ld Vp) and W^T (V, H; ld Hk) from one read of W_out
+        call("seqrec_split_bf16_both", ptr(self.W_out), None, ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(self.Bt_hi),
+             ptr(self.Bt_lo), self.H, self.V, self.Vp, self.Hk, st)
         self._split_version = self._w_version
 
     def work(self, B, T):
@@ -365,6 +365,7 @@ class HotPath:
         st = self.stream
         w.in_scale = None
         w.hscale = None
+        w.tc_operands_fresh = False
         self._mark("gather")
         if w.x_dense is None:
             if training and self.dropout_in > 0:
@@ -414,11 +415,15 @@ class HotPath:
                     w.C_hi = torch.empty((w.N, self.H), dtype=bf, device=self.device)
                     w.C_lo = torch.empty((w.N, self.H), dtype=bf, device=self.device)
             call("seqrec_split_bf16", ptr(w.xg), None, ptr(w.D_hi), ptr(w.D_lo), w.N, self.GH, self.GH, 0, st)
-            call("seqrec_split_bf16", ptr(w.hout), None, ptr(w.Hs_hi), ptr(w.Hs_lo), w.N, self.H, self.H, 0, st)
+            hs_hi, hs_lo = w.Hs_hi, w.Hs_lo
+            if w.tc["fwd"] and self.tc_x3 and w.hscale is None and self.Hk == self.H and w.tc_operands_fresh:
+                hs_hi, hs_lo = w.A_hi, w.A_lo              # the logits kernels' operand IS bf16 hi/lo of hout
+            else:
+                call("seqrec_split_bf16", ptr(w.hout), None, ptr(w.Hs_hi), ptr(w.Hs_lo), w.N, self.H, self.H, 0, st)
             if self.cell == "GRU":
                 call("seqrec_split_bf16", ptr(w.cst), None, ptr(w.C_hi), ptr(w.C_lo), w.N, self.H, self.H, 0, st)
-            call("seqrec_rnn_weight_grad_tc", CELL[self.cell], ptr(w.xg), ptr(w.D_hi), ptr(w.D_lo), ptr(w.Hs_hi),
-                 ptr(w.Hs_lo), ptr(w.C_hi), ptr(w.C_lo), ptr(self.dU), ptr(self.db), w.T, w.B, self.H, st)
+            call("seqrec_rnn_weight_grad_tc", CELL[self.cell], ptr(w.xg), ptr(w.D_hi), ptr(w.D_lo), ptr(hs_hi),
+                 ptr(hs_lo), ptr(w.C_hi), ptr(w.C_lo), ptr(self.dU), ptr(self.db), w.T, w.B, self.H, st)
             return
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
@@ -434,11 +439,13 @@ class HotPath:
         if w.tc["fwd"]:
             self._mark("stage_operands")
             self._stage_weight_operands()
-            call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), w.N, self.H, self.Hk, 0,
-                 st)
             if training and w.tc["bwd"]:
-                call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.Ht_hi), ptr(w.Ht_lo), w.N, self.H, w.Np,
-                     1, st)
+                call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
+                     ptr(w.Ht_lo), w.N, self.H, self.Hk, w.Np, st)
+            else:
+                call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), w.N, self.H, self.Hk,
+                     0, st)
+            w.tc_operands_fresh = True
             self._mark("ce_fwd")
             if with_targets:
                 call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
