@@ -418,6 +418,8 @@ def main():
         # issued by the kernels: logits recompute + gradient GEMM in BOTH kernels (4 GEMMs for 2 algorithmic ones), each
         # product in 3 bf16 passes in x3 mode
         "mma_flops_issued": work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 2.0 if hot.work(B, T).tc["bwd"] else 1.5),
+        "issued_tflops": (work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 2.0 if hot.work(B, T).tc["bwd"] else 1.5)
+                          / (dom_ms * 1e-3) / 1e12) if dom_ms > 0 else 0.0,
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_sustained"], "traffic": load_traffic(args.config),
         "peak_source": peaks["src"] + " bf16 sustained",
