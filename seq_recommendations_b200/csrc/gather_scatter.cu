@@ -122,11 +122,20 @@ scatter_add_rows_kernel(const float* __restrict__ dxp, const int32_t* __restrict
                         const uint8_t* __restrict__ mask, const float* __restrict__ in_scale,
                         float* __restrict__ dW, int32_t* __restrict__ touched, int32_t* __restrict__ rows,
                         int32_t* __restrict__ n_rows, int64_t n_tokens, int GH) {
+  // Work item of a warp = (block of 32 tokens, slab of 128 columns): lane <-> one float4 of the slab (or one float in
+  // the scalar variant).  Splitting the row over several warps and batching FOUR id-groups per round keeps 4 x 512 B
+  // of independent loads in flight per warp; with one warp walking a whole row group by group the kernel sat at one
+  // dependent L2/HBM round trip per 512 B (cfg2: 46 us for 59 MB).
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool vec = (GH & 3) == 0;
-  for (int64_t base = warp_global * 32; base < n_tokens; base += n_warps * 32) {
+  const int units = vec ? (GH >> 2) : GH;                    // float4s (or floats) per row
+  const int slabs = (units + 31) >> 5;                       // 32-lane slabs per row
+  const int64_t n_blocks = (n_tokens + 31) >> 5;
+  for (int64_t item = warp_global; item < n_blocks * slabs; item += n_warps) {
+    const int64_t base = (item / slabs) * 32;
+    const int slab = (int)(item % slabs);
     const int64_t n = base + lane;
     int32_t id = -1;
     float sc = 1.0f;
@@ -136,51 +145,69 @@ scatter_add_rows_kernel(const float* __restrict__ dxp, const int32_t* __restrict
     }
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const bool leader = (id >= 0) && (lane == (__ffs(peers) - 1));
-    if (leader) {
+    if (leader && slab == 0) {                               // one warp per token block claims the rows
       if (atomicExch(touched + id, 1) == 0) {
         const int slot = atomicAdd(n_rows, 1);
         rows[slot] = id;
       }
     }
     unsigned leaders = __ballot_sync(0xffffffffu, leader);
+    const int c = slab * 32 + lane;
+    const bool on = c < units;
     while (leaders) {
-      const int l = __ffs(leaders) - 1;
-      leaders &= leaders - 1;
-      const unsigned grp = __shfl_sync(0xffffffffu, peers, l);
-      const int32_t gid = __shfl_sync(0xffffffffu, id, l);
-      float* dst = dW + (int64_t)gid * GH;
-      // uniform trip counts: every lane runs every iteration so the shuffles below stay convergent
+      // up to four groups per round: their first members' loads are independent and issued back to back
+      int gl[4];
+      unsigned grp[4];
+      int32_t gid[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        gl[k] = leaders ? (__ffs(leaders) - 1) : -1;
+        if (leaders) leaders &= leaders - 1;
+        const int src = gl[k] < 0 ? 0 : gl[k];
+        grp[k] = __shfl_sync(0xffffffffu, peers, src);
+        gid[k] = __shfl_sync(0xffffffffu, id, src);
+      }
       if (vec) {
-        const int chunks = GH >> 2;
-        for (int c0 = 0; c0 < chunks; c0 += 32) {
-          const int c = c0 + lane;
-          const bool on = c < chunks;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          unsigned g = grp;
-          while (g) {
-            const int m = __ffs(g) - 1;
-            g &= g - 1;
-            const float s = __shfl_sync(0xffffffffu, sc, m);
+        float4 acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gl[k] >= 0) {                                  // first member = the leader itself
+            const float s0 = __shfl_sync(0xffffffffu, sc, gl[k]);
             if (on) {
-              const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(dxp + (base + m) * GH) + c);
-              acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
+              const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(dxp + (base + gl[k]) * GH) + c);
+              acc[k] = make_float4(s0 * v.x, s0 * v.y, s0 * v.z, s0 * v.w);
             }
           }
-          if (on) red_add_f4(dst + 4 * c, acc);
         }
-      } else {
-        for (int c0 = 0; c0 < GH; c0 += 32) {
-          const int c = c0 + lane;
-          const bool on = c < GH;
-          float acc = 0.f;
-          unsigned g = grp;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (gl[k] < 0) continue;                           // warp-uniform
+          unsigned g = grp[k] & (grp[k] - 1);                // remaining members (duplicates of the id)
           while (g) {
             const int m = __ffs(g) - 1;
             g &= g - 1;
-            const float s = __shfl_sync(0xffffffffu, sc, m);
-            if (on) acc += s * dxp[(base + m) * GH + c];
+            const float s1 = __shfl_sync(0xffffffffu, sc, m);
+            if (on) {
+              const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(dxp + (base + m) * GH) + c);
+              acc[k].x += s1 * v.x; acc[k].y += s1 * v.y; acc[k].z += s1 * v.z; acc[k].w += s1 * v.w;
+            }
           }
-          if (on) atomicAdd(dst + c, acc);
+          if (on) red_add_f4(dW + (int64_t)gid[k] * GH + 4 * c, acc[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (gl[k] < 0) continue;
+          float acc = 0.f;
+          unsigned g = grp[k];
+          while (g) {
+            const int m = __ffs(g) - 1;
+            g &= g - 1;
+            const float s1 = __shfl_sync(0xffffffffu, sc, m);
+            if (on) acc += s1 * dxp[(base + m) * GH + c];
+          }
+          if (on) atomicAdd(dW + (int64_t)gid[k] * GH + c, acc);
         }
       }
     }
@@ -191,11 +218,12 @@ extern "C" int seqrec_scatter_add_rows(const float* dxp, const int32_t* ids, con
                                        const float* in_scale, float* dW_in, int32_t* touched, int32_t* rows,
                                        int32_t* n_rows, int64_t n_tokens, int V, int GH, void* stream) {
   SEQREC_ARG(n_tokens > 0 && V > 0 && GH > 0, 1);
-  const int64_t warps = (n_tokens + 31) / 32;
-  int blocks = (int)((warps + 7) / 8);
+  const int units = (GH & 3) == 0 ? GH / 4 : GH;
+  const int64_t warps = ((n_tokens + 31) / 32) * ((units + 31) / 32);   // (token block, column slab) items
+  int64_t blocks = (warps + 7) / 8;
   const int cap = SEQREC_NUM_SMS * 16;
   if (blocks > cap) blocks = cap;
-  scatter_add_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dxp, ids, mask, in_scale, dW_in, touched, rows,
+  scatter_add_rows_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(dxp, ids, mask, in_scale, dW_in, touched, rows,
                                                                  n_rows, n_tokens, GH);
   SEQREC_CHECK_LAUNCH();
   return 0;
