@@ -41,7 +41,15 @@ sumsq_rows_kernel(const float* __restrict__ g, const int32_t* __restrict__ rows,
   double acc = 0.0;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nr; w += (gridDim.x * blockDim.x) >> 5) {
     const float* row = g + (size_t)rows[w] * GH;
-    for (int c = lane; c < GH; c += 32) acc += (double)(row[c] * row[c]);
+    if ((GH & 3) == 0) {
+      const float4* r4 = reinterpret_cast<const float4*>(row);
+      for (int c = lane; c < (GH >> 2); c += 32) {
+        const float4 v = r4[c];
+        acc += (double)(v.x * v.x) + (double)(v.y * v.y) + (double)(v.z * v.z) + (double)(v.w * v.w);
+      }
+    } else {
+      for (int c = lane; c < GH; c += 32) acc += (double)(row[c] * row[c]);
+    }
   }
   acc = warp_sum_d(acc);
   if (lane == 0) red[threadIdx.x >> 5] = acc;
@@ -64,7 +72,24 @@ adagrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __rest
                float eps, float clipnorm, const double* __restrict__ sumsq) {
   const float sc = clip_scale(sumsq, clipnorm);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(a)) & 15) == 0;
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* a4 = reinterpret_cast<float4*>(a);
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 gv = g4[i], av = a4[i], pv = p4[i];
+    gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+    av.x += gv.x * gv.x; av.y += gv.y * gv.y; av.z += gv.z * gv.z; av.w += gv.w * gv.w;
+    pv.x -= lr * gv.x / (sqrtf(av.x) + eps);
+    pv.y -= lr * gv.y / (sqrtf(av.y) + eps);
+    pv.z -= lr * gv.z / (sqrtf(av.z) + eps);
+    pv.w -= lr * gv.w / (sqrtf(av.w) + eps);
+    a4[i] = av;
+    p4[i] = pv;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
     const float gv = g[i] * sc;
     const float av = a[i] + gv * gv;
     a[i] = av;
@@ -83,12 +108,30 @@ adagrad_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nr; w += (gridDim.x * blockDim.x) >> 5) {
     const int32_t row = rows[w];
     const size_t off = (size_t)row * GH;
-    for (int c = lane; c < GH; c += 32) {
-      const float gv = g[off + c] * sc;
-      const float av = a[off + c] + gv * gv;
-      a[off + c] = av;
-      p[off + c] = p[off + c] - lr * gv / (sqrtf(av) + eps);
-      g[off + c] = 0.f;  // restore the all-zero invariant of the dense gradient buffer
+    if ((GH & 3) == 0) {                         // 128-bit accesses: 3 loads + 3 stores per 4 parameters
+      float4* p4 = reinterpret_cast<float4*>(p + off);
+      float4* g4 = reinterpret_cast<float4*>(g + off);
+      float4* a4 = reinterpret_cast<float4*>(a + off);
+      for (int c = lane; c < (GH >> 2); c += 32) {
+        float4 gv = g4[c], av = a4[c], pv = p4[c];
+        gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+        av.x += gv.x * gv.x; av.y += gv.y * gv.y; av.z += gv.z * gv.z; av.w += gv.w * gv.w;
+        pv.x -= lr * gv.x / (sqrtf(av.x) + eps);
+        pv.y -= lr * gv.y / (sqrtf(av.y) + eps);
+        pv.z -= lr * gv.z / (sqrtf(av.z) + eps);
+        pv.w -= lr * gv.w / (sqrtf(av.w) + eps);
+        a4[c] = av;
+        p4[c] = pv;
+        g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);  // restore the all-zero invariant of the dense gradient buffer
+      }
+    } else {
+      for (int c = lane; c < GH; c += 32) {
+        const float gv = g[off + c] * sc;
+        const float av = a[off + c] + gv * gv;
+        a[off + c] = av;
+        p[off + c] = p[off + c] - lr * gv / (sqrtf(av) + eps);
+        g[off + c] = 0.f;
+      }
     }
     if (lane == 0) touched[row] = 0;
   }
