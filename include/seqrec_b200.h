@@ -200,6 +200,11 @@ int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16
 int seqrec_split_bf16_both(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, uint16_t* hi_t,
                            uint16_t* lo_t, int64_t rows, int64_t cols, int64_t ld_out, int64_t ld_t, void* stream);
 
+/* split + column sums in one pass: hi/lo (rows, cols) and colsum[c] += sum_r src[r,c] (colsum pre-zeroed, may be NULL);
+ * feeds the dU GEMM (dxp operand) and db from one read of dxp */
+int seqrec_split_bf16_colsum(const float* src, uint16_t* hi, uint16_t* lo, float* colsum, int64_t rows, int cols,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

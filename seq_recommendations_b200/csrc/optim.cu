@@ -295,6 +295,40 @@ extern "C" int seqrec_split_bf16_both(const float* src, const float* scale, uint
   return 0;
 }
 
+// split + column sums in one pass over src (the dU GEMM's dxp operand and db = sum_n dxp[n,:] both come from it):
+// thread <-> column, blockIdx.y <-> a chunk of rows; partial column sums leave through atomicAdd
+__global__ void __launch_bounds__(256)
+split_bf16_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                         float* __restrict__ colsum, int64_t rows, int cols, int64_t rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = blockIdx.y * rows_per_block;
+  const int64_t r1 = rows < r0 + rows_per_block ? rows : r0 + rows_per_block;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const float x = src[r * cols + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[r * cols + c] = h;
+    lo[r * cols + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+    acc += x;
+  }
+  if (colsum) atomicAdd(colsum + c, acc);
+}
+
+extern "C" int seqrec_split_bf16_colsum(const float* src, uint16_t* hi, uint16_t* lo, float* colsum, int64_t rows,
+                                        int cols, void* stream) {
+  SEQREC_ARG(src && hi && lo && rows > 0 && cols > 0, 1);
+  const int64_t rpb = 32;
+  dim3 grid((unsigned)((cols + 255) / 256), (unsigned)((rows + rpb - 1) / rpb));
+  if (grid.y > 65535) return -1003;
+  split_bf16_colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                reinterpret_cast<__nv_bfloat16*>(lo), colsum, rows, cols,
+                                                                rpb);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int seqrec_split_bf16(const float* src, const float* scale, uint16_t* hi, uint16_t* lo, int64_t rows,
                                  int64_t cols, int64_t ld_out, int transpose, void* stream) {
   SEQREC_ARG(rows > 0 && cols > 0 && ld_out > 0, 1);

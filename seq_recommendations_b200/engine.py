@@ -414,7 +414,12 @@ class HotPath:
                 if self.cell == "GRU":
                     w.C_hi = torch.empty((w.N, self.H), dtype=bf, device=self.device)
                     w.C_lo = torch.empty((w.N, self.H), dtype=bf, device=self.device)
-            call("seqrec_split_bf16", ptr(w.xg), None, ptr(w.D_hi), ptr(w.D_lo), w.N, self.GH, self.GH, 0, st)
+            # dxp -> bf16 hi/lo and db = column sums, one pass (rows chunked over blockIdx.y: 65535 * 32 rows at most)
+            fused_db = w.N <= 65535 * 32
+            if fused_db:
+                call("seqrec_split_bf16_colsum", ptr(w.xg), ptr(w.D_hi), ptr(w.D_lo), ptr(self.db), w.N, self.GH, st)
+            else:
+                call("seqrec_split_bf16", ptr(w.xg), None, ptr(w.D_hi), ptr(w.D_lo), w.N, self.GH, self.GH, 0, st)
             hs_hi, hs_lo = w.Hs_hi, w.Hs_lo
             if w.tc["fwd"] and self.tc_x3 and w.hscale is None and self.Hk == self.H and w.tc_operands_fresh:
                 hs_hi, hs_lo = w.A_hi, w.A_lo              # the logits kernels' operand IS bf16 hi/lo of hout
@@ -423,7 +428,8 @@ class HotPath:
             if self.cell == "GRU":
                 call("seqrec_split_bf16", ptr(w.cst), None, ptr(w.C_hi), ptr(w.C_lo), w.N, self.H, self.H, 0, st)
             call("seqrec_rnn_weight_grad_tc", CELL[self.cell], ptr(w.xg), ptr(w.D_hi), ptr(w.D_lo), ptr(hs_hi),
-                 ptr(hs_lo), ptr(w.C_hi), ptr(w.C_lo), ptr(self.dU), ptr(self.db), w.T, w.B, self.H, st)
+                 ptr(hs_lo), ptr(w.C_hi), ptr(w.C_lo), ptr(self.dU), None if fused_db else ptr(self.db), w.T, w.B,
+                 self.H, st)
             return
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
