@@ -16,6 +16,18 @@ namespace {
 
 constexpr int KS = 4;  // K-slices
 
+// tanh through ex2.approx / fast division (absolute error ~2e-7): tanhf costs ~5x more and sits on the sequential path
+template <int ACT>
+__device__ __forceinline__ float act_fast(float a) {
+  if (ACT == SEQREC_ACT_TANH) {
+    a = fminf(fmaxf(a, -15.f), 15.f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * 2.8853900817779268f));
+    return 1.f - __fdividef(2.f, e + 1.f);
+  }
+  return act_f<ACT>(a);
+}
+
 template <int CELL>
 struct Gates { static constexpr int G = (CELL == SEQREC_CELL_GRU) ? 3 : 1; };
 
@@ -79,7 +91,11 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
   const int tid = threadIdx.x;
   const int s = tid / CG, c = tid - s * CG;
   const int b0 = blockIdx.x * RB;
-  const bool owner = (s == 0) && (c < H);      // does the gate math of hidden unit c
+  // elementwise work (gate math, stores, prefetch) of hidden unit c is spread over the K-slice threads: thread (s, c)
+  // with s < RB owns batch row s -- with one owner per unit looping over the rows, 12 of the 16 warps sat in the
+  // barrier behind 4 (ncu: 45 % of the samples were stall_barrier)
+  const bool owner = (s < RB) && (c < H);
+  const int orow = s;                          // the row this thread owns when `owner`
 
   float u[G][KPT];
 #pragma unroll
@@ -93,13 +109,12 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
 
   auto prefetch_x = [&](int t) {               // owners: xp of step t -> x_s[t & 1]
     if (owner && t < T) {
+      const int r = orow;
+      if (b0 + r < B) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r)
-        if (b0 + r < B) {
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            cp_async4(x_s + (((t & 1) * RB + r) * G + g) * CG + c, xg + ((size_t)t * B + b0 + r) * GH + g * H + c);
-        }
+        for (int g = 0; g < G; ++g)
+          cp_async4(x_s + (((t & 1) * RB + r) * G + g) * CG + c, xg + ((size_t)t * B + b0 + r) * GH + g * H + c);
+      }
     }
     cp_async_commit();
   };
@@ -135,19 +150,17 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
     __syncthreads();
     if constexpr (CELL == SEQREC_CELL_GRU) {
       if (owner) {
+        const int r = orow;
+        float az = xc[(r * G + 0) * CG + c], ar = xc[(r * G + 1) * CG + c];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          float az = xc[(r * G + 0) * CG + c], ar = xc[(r * G + 1) * CG + c];
-#pragma unroll
-          for (int q = 0; q < KS; ++q) {
-            az += part_s[((q * RB + r) * G + 0) * CG + c];
-            ar += part_s[((q * RB + r) * G + 1) * CG + c];
-          }
-          const float z = hard_sigmoid_f(az), rr = hard_sigmoid_f(ar);
-          zr_s[(r * 2 + 0) * CG + c] = z;
-          zr_s[(r * 2 + 1) * CG + c] = rr;
-          rh_s[r * KP + c] = rr * h_s[r * KP + c];
+        for (int q = 0; q < KS; ++q) {
+          az += part_s[((q * RB + r) * G + 0) * CG + c];
+          ar += part_s[((q * RB + r) * G + 1) * CG + c];
         }
+        const float z = hard_sigmoid_f(az), rr = hard_sigmoid_f(ar);
+        zr_s[(r * 2 + 0) * CG + c] = z;
+        zr_s[(r * 2 + 1) * CG + c] = rr;
+        rh_s[r * KP + c] = rr * h_s[r * KP + c];
       }
       __syncthreads();
       // ---- phase 2: candidate, (r*h).U_h
@@ -160,34 +173,31 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
       __syncthreads();
     }
     // ---- phase 3: gate math, state update under the mask, stores
-    if (owner) {
+    if (owner && b0 + orow < B) {
+      const int r = orow;
+      const size_t tok = tok0 + r;
+      const bool m = m_s[(t & 1) * RB + r] != 0;
+      const float hp = h_s[r * KP + c];
+      float hn;
+      float* gp = xg + tok * GH;
+      if constexpr (CELL == SEQREC_CELL_GRU) {
+        float ah = xc[(r * G + 2) * CG + c];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (b0 + r >= B) continue;
-        const size_t tok = tok0 + r;
-        const bool m = m_s[(t & 1) * RB + r] != 0;
-        const float hp = h_s[r * KP + c];
-        float hn;
-        float* gp = xg + tok * GH;
-        if constexpr (CELL == SEQREC_CELL_GRU) {
-          float ah = xc[(r * G + 2) * CG + c];
+        for (int q = 0; q < KS; ++q) ah += part_s[((q * RB + r) * G + 2) * CG + c];
+        const float hh = act_fast<ACT>(ah);
+        const float z = zr_s[(r * 2 + 0) * CG + c], rr = zr_s[(r * 2 + 1) * CG + c];
+        hn = z * hp + (1.0f - z) * hh;
+        gp[c] = z; gp[H + c] = rr; gp[2 * H + c] = hh;
+      } else {
+        float a = xc[(r * G + 0) * CG + c];
 #pragma unroll
-          for (int q = 0; q < KS; ++q) ah += part_s[((q * RB + r) * G + 2) * CG + c];
-          const float hh = act_f<ACT>(ah);
-          const float z = zr_s[(r * 2 + 0) * CG + c], rr = zr_s[(r * 2 + 1) * CG + c];
-          hn = z * hp + (1.0f - z) * hh;
-          gp[c] = z; gp[H + c] = rr; gp[2 * H + c] = hh;
-        } else {
-          float a = xc[(r * G + 0) * CG + c];
-#pragma unroll
-          for (int q = 0; q < KS; ++q) a += part_s[((q * RB + r) * G + 0) * CG + c];
-          hn = act_f<ACT>(a);
-          gp[c] = hn;
-        }
-        const float hv = m ? hn : hp;
-        h_s[r * KP + c] = hv;
-        hout[tok * H + c] = hv;
+        for (int q = 0; q < KS; ++q) a += part_s[((q * RB + r) * G + 0) * CG + c];
+        hn = act_fast<ACT>(a);
+        gp[c] = hn;
       }
+      const float hv = m ? hn : hp;
+      h_s[r * KP + c] = hv;
+      hout[tok * H + c] = hv;
     }
     if (tid < RB) {
       m_s[((t + 1) & 1) * RB + tid] = m1;
@@ -222,7 +232,8 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
   const int tid = threadIdx.x;
   const int s = tid / CG, c = tid - s * CG;
   const int b0 = blockIdx.x * RB;
-  const bool owner = (s == 0) && (c < H);
+  const bool owner = (s < RB) && (c < H);      // thread (s, c), s < RB, owns batch row s of unit c (see the forward)
+  const int orow = s;
 
   float u[G][KPT];
 #pragma unroll
@@ -239,19 +250,18 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
   auto prefetch_in = [&](int t) {
     if (owner && t >= 0) {
       float* dst = in_s + (size_t)(t & 1) * RB * NI * CG;
+      const int r = orow;
+      if (b0 + r < B) {
+        const size_t tok = (size_t)t * B + b0 + r;
+        cp_async4(dst + (r * NI + 0) * CG + c, dhout + tok * H + c);
+        if (CELL == SEQREC_CELL_GRU) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r)
-        if (b0 + r < B) {
-          const size_t tok = (size_t)t * B + b0 + r;
-          cp_async4(dst + (r * NI + 0) * CG + c, dhout + tok * H + c);
-          if (CELL == SEQREC_CELL_GRU) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) cp_async4(dst + (r * NI + 1 + g) * CG + c, xg + tok * GH + g * H + c);
-            if (t > 0) cp_async4(dst + (r * NI + 4) * CG + c, hout + (tok - B) * H + c);
-          } else {
-            cp_async4(dst + (r * NI + 1) * CG + c, hout + tok * H + c);
-          }
+          for (int g = 0; g < 3; ++g) cp_async4(dst + (r * NI + 1 + g) * CG + c, xg + tok * GH + g * H + c);
+          if (t > 0) cp_async4(dst + (r * NI + 4) * CG + c, hout + (tok - B) * H + c);
+        } else {
+          cp_async4(dst + (r * NI + 1) * CG + c, hout + tok * H + c);
         }
+      }
     }
     cp_async_commit();
   };
@@ -271,31 +281,26 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
     prefetch_in(t - 1);
     cp_async_wait<1>();                        // this step's inputs (own elements) have landed
     // ---- phase 1 (owners): elementwise gate gradients
-    if (owner) {
+    if (owner && b0 + orow < B) {
+      const int r = orow;
+      const size_t tok = tok0 + r;
+      const bool m = m_s[(t & 1) * RB + r] != 0;
+      const float dh = ic[(r * NI + 0) * CG + c] + dc_s[r * CG + c];
+      if (!m) {
+        dd_s[r * CG + c] = dh;                 // masked step: h_t = h_{t-1}, no gate gradient
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (b0 + r >= B) continue;
-        const size_t tok = tok0 + r;
-        const bool m = m_s[(t & 1) * RB + r] != 0;
-        const float dh = ic[(r * NI + 0) * CG + c] + dc_s[r * CG + c];
-        if (!m) {
-          dd_s[r * CG + c] = dh;               // masked step: h_t = h_{t-1}, no gate gradient
-#pragma unroll
-          for (int g = 0; g < G; ++g) da_s[(g * RB + r) * KP + c] = 0.f;
-          if (CELL == SEQREC_CELL_GRU) cst[tok * H + c] = 0.f;
-          continue;
-        }
-        if (CELL == SEQREC_CELL_GRU) {
-          const float z = ic[(r * NI + 1) * CG + c], rg = ic[(r * NI + 2) * CG + c], hh = ic[(r * NI + 3) * CG + c];
-          const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
-          da_s[(0 * RB + r) * KP + c] = dh * (hprev - hh) * hard_sigmoid_grad_from_y(z);
-          da_s[(2 * RB + r) * KP + c] = dh * (1.0f - z) * act_grad_from_y<ACT>(hh);
-          dd_s[r * CG + c] = dh * z;
-          cst[tok * H + c] = rg * hprev;       // operand of dU's candidate block
-        } else {
-          da_s[(0 * RB + r) * KP + c] = dh * act_grad_from_y<ACT>(ic[(r * NI + 1) * CG + c]);
-          dd_s[r * CG + c] = 0.f;
-        }
+        for (int g = 0; g < G; ++g) da_s[(g * RB + r) * KP + c] = 0.f;
+        if (CELL == SEQREC_CELL_GRU) cst[tok * H + c] = 0.f;
+      } else if (CELL == SEQREC_CELL_GRU) {
+        const float z = ic[(r * NI + 1) * CG + c], rg = ic[(r * NI + 2) * CG + c], hh = ic[(r * NI + 3) * CG + c];
+        const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
+        da_s[(0 * RB + r) * KP + c] = dh * (hprev - hh) * hard_sigmoid_grad_from_y(z);
+        da_s[(2 * RB + r) * KP + c] = dh * (1.0f - z) * act_grad_from_y<ACT>(hh);
+        dd_s[r * CG + c] = dh * z;
+        cst[tok * H + c] = rg * hprev;         // operand of dU's candidate block
+      } else {
+        da_s[(0 * RB + r) * KP + c] = dh * act_grad_from_y<ACT>(ic[(r * NI + 1) * CG + c]);
+        dd_s[r * CG + c] = 0.f;
       }
     }
     __syncthreads();
@@ -310,18 +315,15 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
         for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[0][r];
       }
       __syncthreads();
-      if (owner) {
+      if (owner && b0 + orow < B && m_s[(t & 1) * RB + orow] != 0) {
+        const int r = orow;
+        float d_rh = 0.f;
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          if (b0 + r >= B || m_s[(t & 1) * RB + r] == 0) continue;
-          float d_rh = 0.f;
-#pragma unroll
-          for (int q = 0; q < KS; ++q) d_rh += part_s[(q * RB + r) * CG + c];
-          const float rg = ic[(r * NI + 2) * CG + c];
-          const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
-          da_s[(1 * RB + r) * KP + c] = d_rh * hprev * hard_sigmoid_grad_from_y(rg);
-          dd_s[r * CG + c] += d_rh * rg;
-        }
+        for (int q = 0; q < KS; ++q) d_rh += part_s[(q * RB + r) * CG + c];
+        const float rg = ic[(r * NI + 2) * CG + c];
+        const float hprev = (t > 0) ? ic[(r * NI + 4) * CG + c] : 0.f;
+        da_s[(1 * RB + r) * KP + c] = d_rh * hprev * hard_sigmoid_grad_from_y(rg);
+        dd_s[r * CG + c] += d_rh * rg;
       }
       __syncthreads();
     }
@@ -337,19 +339,16 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
       for (int r = 0; r < RB; ++r) part_s[(s * RB + r) * CG + c] = acc[0][r];
     }
     __syncthreads();
-    if (owner) {
+    if (owner && b0 + orow < B) {
+      const int r = orow;
+      float v = dd_s[r * CG + c];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (b0 + r >= B) continue;
-        float v = dd_s[r * CG + c];
+      for (int q = 0; q < KS; ++q) v += part_s[(q * RB + r) * CG + c];
+      dc_s[r * CG + c] = v;
+      // dxp[t] = da (overwrites the saved gates, already copied to shared memory by the prefetch)
+      float* gp = xg + (tok0 + r) * GH;
 #pragma unroll
-        for (int q = 0; q < KS; ++q) v += part_s[(q * RB + r) * CG + c];
-        dc_s[r * CG + c] = v;
-        // dxp[t] = da (overwrites the saved gates, already copied to shared memory by the prefetch)
-        float* gp = xg + (tok0 + r) * GH;
-#pragma unroll
-        for (int g = 0; g < G; ++g) gp[g * H + c] = da_s[(g * RB + r) * KP + c];
-      }
+      for (int g = 0; g < G; ++g) gp[g * H + c] = da_s[(g * RB + r) * KP + c];
     }
     if (tid < RB) {
       m_s[((t - 1) & 1) * RB + tid] = m1;
