@@ -403,6 +403,28 @@ def main():
     e2e_ms = float(t.item())
     clk = clocks.stop() if clocks is not None else None
 
+    # ---- the same workload through the reference-facing surface: RNNFullModel.fit_model on host id arrays (numpy in,
+    #      History out), one epoch of 32 batches; N = 1 only (the Keras surface drives one process)
+    plugin = None
+    if world == 1:
+        from seq_recommendations_b200.model import RNNFullModel
+        from seq_recommendations_b200.optimizers import Adagrad
+        nb = 32
+        big_i, big_t = synthetic.make_batch(V, T, B * nb, seed=7)
+        mdl = RNNFullModel(T, V, V, z_dim=H, rnn_type=cfg["cell"], z_to_z_activation=cfg["act"], y_to_y=False,
+                           x_to_y=False, seed=0)
+        mdl.compile_model(loss="categorical_crossentropy", metrics=[],
+                          optimizer=Adagrad(lr=0.01, epsilon=1e-08, decay=0.0, clipnorm=1.))
+        mdl.fit_model(big_i[:4 * B], big_t[:4 * B], n_epochs=1, batch_size=B, verbose=0)       # warm-up / graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist = mdl.fit_model(big_i, big_t, n_epochs=1, batch_size=B, verbose=0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        plugin = {"value": B * nb / dt, "unit": "sequences/sec", "ms_per_step": dt / nb * 1e3,
+                  "api": "RNNFullModel.fit_model(ids (N,T) int32 numpy, targets, n_epochs=1, batch_size=%d) -> History" % B,
+                  "epoch_loss": float(hist.history["loss"][-1])}
+
     if rank != 0:
         return
     peaks = load_peaks()
@@ -451,6 +473,7 @@ def main():
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "sequences/sec", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * B * T * 4, "d2h_bytes_per_step": 4,
                 "api": "HotPath.train_batch(pinned host ids, targets) -> loss.item()"},
+        "e2e_plugin": plugin,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),

@@ -13,7 +13,8 @@ from gpu_util import as_t, make_pair, rel_err
 pytestmark = pytest.mark.gpu
 
 # (cell, act, H, T, B): ragged last cluster (B % 64 != 0), one and several clusters, both cluster sizes (H/32 = 4, 8)
-CASES = [("LSTM", "tanh", 256, 12, 70), ("LSTM", "relu", 256, 7, 64), ("GRU", "tanh", 256, 9, 130),
+CASES = [("LSTM", "tanh", 256, 1, 70), ("GRU", "tanh", 256, 1, 9), ("GRU", "tanh", 128, 2, 64),
+         ("LSTM", "tanh", 256, 12, 70), ("LSTM", "relu", 256, 7, 64), ("GRU", "tanh", 256, 9, 130),
          ("GRU", "relu", 256, 5, 33), ("LSTM", "tanh", 128, 10, 96), ("GRU", "tanh", 128, 11, 50)]
 
 
@@ -46,7 +47,7 @@ def test_tc_scan_matches_simt_scan(cell, act, H, T, B):
     assert np.all(out[True][0][pad & (np.cumsum(~pad, axis=1) == 0)] == 0.0)
 
 
-@pytest.mark.parametrize("cell,act,H,T,B", CASES[:4])
+@pytest.mark.parametrize("cell,act,H,T,B", CASES[:7])
 def test_tc_scan_loss_and_gradients_match_oracle(cell, act, H, T, B):
     V = 400
     hot, ora, _ = make_pair(cell, act, V, H, seed=5, bias_scale=0.1, tc="off")
