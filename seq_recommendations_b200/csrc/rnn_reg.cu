@@ -16,30 +16,6 @@ namespace {
 
 constexpr int KS = 4;  // K-slices
 
-// tanh through ex2.approx / fast division (absolute error ~2e-7): tanhf costs ~5x more and sits on the sequential path
-template <int ACT>
-__device__ __forceinline__ float act_fast(float a) {
-  if (ACT == SEQREC_ACT_TANH) {
-    a = fminf(fmaxf(a, -15.f), 15.f);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * 2.8853900817779268f));
-    return 1.f - __fdividef(2.f, e + 1.f);
-  }
-  return act_f<ACT>(a);
-}
-
-template <int CELL>
-struct Gates { static constexpr int G = (CELL == SEQREC_CELL_GRU) ? 3 : 1; };
-
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // acc[g][r] += sum_i vec[r*ldv + k0 + i] * u[g0 + g][i] for NG gates sharing the same vector; the float4 loads of the
 // next quad are issued before the FFMAs of the current one (software pipelined, fully unrolled)
 template <int RB, int KPT, int NG, int GT>
@@ -184,7 +160,7 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
         float ah = xc[(r * G + 2) * CG + c];
 #pragma unroll
         for (int q = 0; q < KS; ++q) ah += part_s[((q * RB + r) * G + 2) * CG + c];
-        const float hh = act_fast<ACT>(ah);
+        const float hh = act_f<ACT>(ah);
         const float z = zr_s[(r * 2 + 0) * CG + c], rr = zr_s[(r * 2 + 1) * CG + c];
         hn = z * hp + (1.0f - z) * hh;
         gp[c] = z; gp[H + c] = rr; gp[2 * H + c] = hh;
@@ -192,7 +168,7 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
         float a = xc[(r * G + 0) * CG + c];
 #pragma unroll
         for (int q = 0; q < KS; ++q) a += part_s[((q * RB + r) * G + 0) * CG + c];
-        hn = act_fast<ACT>(a);
+        hn = act_f<ACT>(a);
         gp[c] = hn;
       }
       const float hv = m ? hn : hp;
