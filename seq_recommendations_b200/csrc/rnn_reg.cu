@@ -16,6 +16,18 @@ namespace {
 
 constexpr int KS = 4;  // K-slices
 
+template <int CELL>
+struct Gates { static constexpr int G = (CELL == SEQREC_CELL_GRU) ? 3 : 1; };
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // acc[g][r] += sum_i vec[r*ldv + k0 + i] * u[g0 + g][i] for NG gates sharing the same vector; the float4 loads of the
 // next quad are issued before the FFMAs of the current one (software pipelined, fully unrolled)
 template <int RB, int KPT, int NG, int GT>
