@@ -741,6 +741,62 @@ class HotPath:
                      o["eps"], o["clipnorm"], ptr(self.sumsq), st)
             self.dW_in.zero_()
 
+    def _rank_rows(self, wt, hrows, m, s, n, k):
+        """Top-k of n rows against THIS rank's items (ids are local item indices), probabilities from (m, s)."""
+        out_i = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        out_p = torch.empty((n, k), dtype=torch.float32, device=self.device)
+        n_lists = wt.tc["splits"] if wt.tc["fwd"] else 0
+        if wt.tc["fwd"] and k <= 32 and n_lists * k <= 384 and os.environ.get("SEQREC_TOPK_TC", "1") != "0":
+            # tensor-core ranking: the bf16 hi/lo operands were staged by the statistics pass
+            ws_v = torch.empty((n_lists, n, k), dtype=torch.float32, device=self.device)
+            ws_i = torch.empty((n_lists, n, k), dtype=torch.int32, device=self.device)
+            call("seqrec_topk_tc", ptr(wt.A_hi), ptr(wt.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out), ptr(m),
+                 ptr(s), ptr(ws_v), ptr(ws_i), ptr(out_i), ptr(out_p), n, self.Hk, self.V, int(k),
+                 1 if self.tc_x3 else 0, self.stream)
+        else:
+            call("seqrec_topk", ptr(hrows), ptr(self.W_out), ptr(self.b_out), ptr(m), ptr(s), ptr(out_i), ptr(out_p), n,
+                 self.H, self.V, int(k), self.stream)
+        return out_i, out_p
+
+    def _topk_vp(self, w, k, last_step_only):
+        """Vocabulary-parallel ranking: all-gather the rows to score, every rank ranks them against its
+        item shard with the catalog-wide softmax statistics, the P*k candidates of a row are gathered back and merged
+        (probability descending, lower item id first on ties)."""
+        comm = self.comm
+        if k > self.V:
+            raise ValueError("k must not exceed the items of one shard (%d)" % self.V)
+        if last_step_only:
+            rows, msk, nb, nt = w.hout[w.T - 1], w.mask[w.T - 1], w.B, 1
+        else:
+            rows, msk, nb, nt = w.hout.view(w.N, self.H), w.mask.view(-1), w.B, w.T
+        n_loc = rows.shape[0]
+        wg = self.work(nb * comm.world, nt)
+        wg.hout.view(wg.N, self.H).copy_(comm.all_gather_cat(rows.contiguous()))
+        wg.mask.view(-1).copy_(comm.all_gather_cat(msk.contiguous().view(-1)))
+        wg.hscale = None
+        n_splits = self._ce_partials(wg, False, False)
+        call("seqrec_ce_finalize", ptr(wg.ws_m), ptr(wg.ws_s), None, None, ptr(wg.m), ptr(wg.s), None, None, None, None,
+             wg.N, n_splits, self.stream)
+        m_all = comm.all_gather_cat(wg.m)
+        s_all = comm.all_gather_cat(wg.s)
+        self._finalize_ce(wg, m_all, s_all, comm.world, False)          # catalog-wide (m, s) of every gathered row
+        loc_i, loc_p = self._rank_rows(wg, wg.hout.view(wg.N, self.H), wg.m, wg.s, wg.N, k)
+        loc_i = loc_i + self.v_lo                                        # global item ids
+        all_i = comm.all_gather_cat(loc_i.view(1, wg.N, k))              # (P shards, P*n_loc rows, k)
+        all_p = comm.all_gather_cat(loc_p.view(1, wg.N, k))
+        lo = comm.rank * n_loc
+        ci = all_i[:, lo:lo + n_loc].permute(1, 0, 2).reshape(n_loc, comm.world * k)
+        cp = all_p[:, lo:lo + n_loc].permute(1, 0, 2).reshape(n_loc, comm.world * k)
+        order = torch.argsort(ci, dim=1, stable=True)                    # ids ascending ...
+        ci, cp = torch.gather(ci, 1, order), torch.gather(cp, 1, order)
+        order = torch.argsort(cp, dim=1, descending=True, stable=True)   # ... then probability descending, stable
+        top_i = torch.gather(ci, 1, order)[:, :k].contiguous()
+        top_p = torch.gather(cp, 1, order)[:, :k].contiguous()
+        if last_step_only:
+            return top_i, top_p
+        return (top_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),
+                top_p.view(w.T, w.B, k).permute(1, 0, 2).contiguous())
+
     # ------------------------------------------------------------------------------------------------ gradients only
     def grad_batch(self, ids, tgt, x_dense=None):
         """fwd + bwd WITHOUT the update (parity tests): returns loss and the raw (unclipped) gradients as numpy arrays
@@ -789,7 +845,8 @@ class HotPath:
     def predict_batch(self, ids, x_dense=None):
         """model.predict: (B,T,V) float32 softmax probabilities on the device."""
         if self.vocab_parallel:
-            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
+            raise NotImplementedError("a vocabulary-parallel model never materialises (B,T,V): use topk_batch / "
+                                      "target_prob_batch, or gather the weights into a replicated model")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)
@@ -802,23 +859,26 @@ class HotPath:
 
     def target_prob_batch(self, ids, tgt, x_dense=None):
         """p(true next item) per step, clipped to [1e-7, 1-1e-7] like model.py:108-110; (B,T) device tensor."""
-        if self.vocab_parallel:
-            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, tgt, x_dense)
         self._forward_hidden(w, training=False)
+        if self.vocab_parallel:
+            # every rank scores all ranks' tokens against its item shard; the merged statistics cover the whole catalog
+            wg = self._vp_forward(w, training=False)
+            lo = self.comm.rank * w.N
+            return wg.py[lo:lo + w.N].view(w.T, w.B).t().contiguous()
         self._forward_ce(w)
         return w.py.view(w.T, w.B).t().contiguous()
 
     def topk_batch(self, ids, k, last_step_only=True, x_dense=None):
         """Top-k next items: (B,k) ids and probabilities for the last step, or (B,T,k) for every step."""
-        if self.vocab_parallel:
-            raise NotImplementedError("scoring with a vocabulary-parallel model is not built yet (gather the weights)")
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)
         self._forward_hidden(w, training=False)
+        if self.vocab_parallel:
+            return self._topk_vp(w, int(k), last_step_only)
         if last_step_only:
             # softmax statistics of the last step only: a (B, 1) problem over the rows hout[T-1]
             wl = self.work(int(B), 1)
@@ -830,20 +890,7 @@ class HotPath:
         else:
             self._forward_ce(w, with_targets=False)
             hrows, m, s, n = w.hout, w.m, w.s, w.N
-        out_i = torch.empty((n, k), dtype=torch.int32, device=self.device)
-        out_p = torch.empty((n, k), dtype=torch.float32, device=self.device)
-        wt = wl if last_step_only else w
-        n_lists = wt.tc["splits"] if wt.tc["fwd"] else 0
-        if wt.tc["fwd"] and k <= 32 and n_lists * k <= 384 and os.environ.get("SEQREC_TOPK_TC", "1") != "0":
-            # tensor-core ranking: the bf16 hi/lo operands were staged by the statistics pass above
-            ws_v = torch.empty((n_lists, n, k), dtype=torch.float32, device=self.device)
-            ws_i = torch.empty((n_lists, n, k), dtype=torch.int32, device=self.device)
-            call("seqrec_topk_tc", ptr(wt.A_hi), ptr(wt.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out), ptr(m),
-                 ptr(s), ptr(ws_v), ptr(ws_i), ptr(out_i), ptr(out_p), n, self.Hk, self.V, int(k),
-                 1 if self.tc_x3 else 0, self.stream)
-        else:
-            call("seqrec_topk", ptr(hrows), ptr(self.W_out), ptr(self.b_out), ptr(m), ptr(s), ptr(out_i), ptr(out_p), n,
-                 self.H, self.V, int(k), self.stream)
+        out_i, out_p = self._rank_rows(wl if last_step_only else w, hrows, m, s, n, int(k))
         if last_step_only:
             return out_i, out_p
         return (out_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),

@@ -36,6 +36,26 @@ def main():
         lo, hi = dist.shard_rows(B, comm.rank, comm.world)
         losses = [float(hot.train_batch(i[lo:hi], t[lo:hi]).item()) for i, t in steps]
         mine = hot.get_weights()
+        if vp:
+            # scoring with the column-sharded model (collective calls: every rank takes part) vs a replicated model that
+            # holds the gathered weights, on this rank's rows
+            k = 5
+            si, st = steps[0]
+            vi, vpr = hot.topk_batch(si[lo:hi], k, last_step_only=True)
+            ai, apr = hot.topk_batch(si[lo:hi], k, last_step_only=False)
+            py = hot.target_prob_batch(si[lo:hi], st[lo:hi])
+            solo_s = dist.Comm.__new__(dist.Comm)
+            solo_s.enabled, solo_s.group, solo_s.rank, solo_s.world = False, None, 0, 1
+            rep = HotPath(cell, act, V, H, V, weights=mine, comm=solo_s, tc=tc)
+            ri, rpr = rep.topk_batch(si[lo:hi], k, last_step_only=True)
+            qi, qpr = rep.topk_batch(si[lo:hi], k, last_step_only=False)
+            rpy = rep.target_prob_batch(si[lo:hi], st[lo:hi])
+            same = (torch.equal(vi.cpu(), ri.cpu()) and torch.equal(ai.cpu(), qi.cpu())
+                    and float((vpr / rpr - 1).abs().max()) < 1e-4 and float((apr / qpr - 1).abs().max()) < 1e-4
+                    and float((py / rpy - 1).abs().max()) < 1e-4)
+            print("rank %d: vocabulary-parallel scoring V=%d %s -> %s" % (comm.rank, V, cell, "OK" if same else "MISMATCH"),
+                  flush=True)
+            ok = ok and same
         if comm.rank == 0:
             solo = dist.Comm.__new__(dist.Comm)
             solo.enabled, solo.group, solo.rank, solo.world = False, None, 0, 1
