@@ -33,6 +33,13 @@ int seqrec_abi_version(void);
 /* number of kernels this library has launched since load (or since the last call with reset != 0) */
 int seqrec_launch_count(int reset);
 
+/* ---- batch formatting on the device (the step before the hot path; preprocessor.py:67-94 + Keras pad_sequences with
+ * padding='pre', truncating='pre').  Ragged input: items (flat int32) and offsets (n_seqs+1, int64); sequence i of length
+ * L gives the pairs (s[j], s[j+1]); its last min(L-1, T) pairs fill the right end of row i of ids_bt / tgt_bt (n_seqs, T),
+ * the rest is pad = -1.  No (N,T,V) one-hot ever exists. */
+int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets, int32_t* ids_bt, int32_t* tgt_bt, int64_t n_seqs,
+                         int T, void* stream);
+
 /* ---- batch format (preprocessor.py:67-94, model.py:335 Masking) ------------------------------------------------
  * (B,T) batch-major ids/targets (pad = negative) -> time-major ids/targets/mask; counts valid tokens into
  * n_valid[0] (int32, must be zeroed by the caller). */

@@ -51,6 +51,42 @@ extern "C" int seqrec_format_batch(const int32_t* ids_bt, const int32_t* tgt_bt,
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Ragged sequences -> the (B,T) id / target batch of FullModelPreprocessor (preprocessor.py:67-94 with Keras'
+// pad_sequences(padding='pre', truncating='pre')): sequence i = items[offs[i] .. offs[i+1]) of length L gives the
+// L-1 pairs (s[j], s[j+1]); the LAST min(L-1, T) pairs fill the right end of row i, the rest is pad (-1).
+__global__ void __launch_bounds__(256)
+pad_sequences_kernel(const int32_t* __restrict__ items, const int64_t* __restrict__ offs, int32_t* __restrict__ ids_bt,
+                     int32_t* __restrict__ tgt_bt, int64_t n_seqs, int T) {
+  const int64_t total = n_seqs * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / T;
+    const int t = (int)(i - b * T);
+    const int64_t start = offs[b], len = offs[b + 1] - start;
+    const int64_t pairs = len > 0 ? len - 1 : 0;
+    const int64_t keep = pairs < T ? pairs : T;                // pairs that fit after left truncation
+    const int64_t j = t - (T - keep);                          // index among the kept pairs
+    int32_t vi = -1, vt = -1;
+    if (j >= 0) {
+      const int64_t src = start + (pairs - keep) + j;
+      vi = items[src];
+      vt = items[src + 1];
+    }
+    ids_bt[i] = vi;
+    if (tgt_bt) tgt_bt[i] = vt;
+  }
+}
+
+extern "C" int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets, int32_t* ids_bt, int32_t* tgt_bt,
+                                    int64_t n_seqs, int T, void* stream) {
+  SEQREC_ARG(items && offsets && ids_bt && n_seqs > 0 && T > 0, 1);
+  int64_t blocks = (n_seqs * T + 255) / 256;
+  if (blocks > SEQREC_NUM_SMS * 16) blocks = SEQREC_NUM_SMS * 16;
+  pad_sequences_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(items, offsets, ids_bt, tgt_bt, n_seqs, T);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // K1: xp[n,:] = (mask ? scale*W_in[id,:] : 0) + b.   One thread per float4 of the output, consecutive threads on
 // consecutive 16-byte chunks of one row (coalesced reads of the table row and coalesced streaming stores).
 template <bool VEC4>

@@ -109,6 +109,41 @@ class FullModelPreprocessor(Preprocessor):
         return x[:, :, 0], y[:, :, 0]
 
 
+def ragged(sequences):
+    """List of item-id sequences -> (flat int32 items, int64 offsets of length n+1)."""
+    lens = np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences))
+    offs = np.zeros(len(sequences) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    flat = np.fromiter((int(v) for s in sequences for v in s), dtype=np.int32, count=int(offs[-1]))
+    return flat, offs
+
+
+def transform_ids_device(sequences, seq_length=None, device=None):
+    """`FullModelPreprocessor.transform_ids` on the GPU: the ragged corpus goes to HBM once as
+    (items, offsets) and the left-padded / left-truncated (N,T) int32 id and target batches are built by
+    `seqrec_pad_sequences` -- bit-identical to the host path, no Python loop over sequences, no one-hot.
+    `sequences` is a list of id sequences or an (items, offsets) pair.  Returns device tensors (ids, targets)."""
+    import ctypes
+    import torch
+    from ._lib import call, ptr
+    flat, offs = sequences if isinstance(sequences, tuple) else ragged(sequences)
+    n = len(offs) - 1
+    lens = np.diff(offs)
+    T = int(seq_length) if seq_length is not None else int(max(int(lens.max(initial=1)) - 1, 0))
+    if n == 0 or T <= 0:
+        raise ValueError("need at least one sequence and a positive sequence length")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    d_items = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.int32)).to(dev)
+    if d_items.numel() == 0:
+        d_items = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_offs = torch.from_numpy(np.ascontiguousarray(offs, dtype=np.int64)).to(dev)
+    ids = torch.empty((n, T), dtype=torch.int32, device=dev)
+    tgt = torch.empty((n, T), dtype=torch.int32, device=dev)
+    call("seqrec_pad_sequences", ptr(d_items), ptr(d_offs), ptr(ids), ptr(tgt), n, T,
+         ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    return ids, tgt
+
+
 def to_id_batch(a, n_classes=None):
     """Any accepted batch encoding -> (ids int32 (N,T) with pad=-1).
 
