@@ -142,8 +142,8 @@ int seqrec_ce_backward(const float* hout, const float* hscale, const float* W_ou
  *   Ht = hs^T          (Hk, Np)  Np = N padded to a multiple of 8
  *   Bt = W_out^T       (V, Hk)
  *   W  = W_out         (Hk, Vp)  Vp = V padded to a multiple of 8
- * x3 != 0 selects the 3-pass split product (fp32-grade, ~2^-16 relative); forward supports Hk <= 256, backward
- * Hk <= 128 and no output bias.  dh is overwritten unless accumulate_dh != 0; dW_out must be pre-zeroed (both leave
+ * x3 != 0 selects the 3-pass split product (fp32-grade, ~2^-16 relative); Hk <= 256.  b_out (V, may be NULL) is the
+ * output bias, db_out (V, pre-zeroed, may be NULL) receives its gradient.  dh is overwritten unless accumulate_dh != 0; dW_out must be pre-zeroed (both leave
  * the SM through vector reductions).  ws_m / ws_s as in seqrec_ce_forward; the target logit comes from
  * seqrec_target_logit (exact fp32 dot product). */
 int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
@@ -158,7 +158,7 @@ int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint
                           const int32_t* tgt, const float* m, const float* s, const float* coef,
                           const float* inv_nvalid, const float* hscale, float* dh, float* dW_out, int64_t n_tokens,
                           int H, int Hk, int V, int Vp, int64_t Np, int v_begin, int v_end, int ldw,
-                          int accumulate_dh, int x3, void* stream);
+                          int accumulate_dh, int x3, const float* b_out, float* db_out, void* stream);
 int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
                         const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream);
 

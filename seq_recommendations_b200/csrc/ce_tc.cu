@@ -1492,7 +1492,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
                          const float* __restrict__ srow, const float* __restrict__ coef,
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
                          float* __restrict__ out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
-                         uint32_t smem_bytes) {
+                         uint32_t smem_bytes, const float* __restrict__ b_out, float* __restrict__ db_out) {
   using C = TsCfg<KB, X3>;
   constexpr int NP = C::NP, NS = C::NS, NC = C::NC, SBUF = C::SBUF;
   constexpr int NJ = BN / KBLK;                             // 64-wide K blocks of the second GEMM per tile
@@ -1765,6 +1765,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float4* sT_gen = reinterpret_cast<float4*>(smem_raw + (sT - ptx::smem_u32(smem_raw)));
     RowTerms rt;                                             // !ITEM_ST: this thread's token row; ITEM_ST: prefetch
+    float bias_v = 0.f, db_acc = 0.f;                        // ITEM_ST: b_out of this thread's item, its dL/db partial
     int tc = 0, seg = -1;
     if (ITEM_ST && sh.w0 < sh.w1) {
       if (e < 128) {
@@ -1778,6 +1779,11 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       if (sh.seg_first(w)) {
         ++seg;
         if (!ITEM_ST) rt = load_row_terms((int64_t)sh.outer(w) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+        if (ITEM_ST) {
+          const int v = v_begin + sh.outer(w) * BN + row;
+          bias_v = (b_out && v < v_end) ? b_out[v] : 0.f;
+          db_acc = 0.f;
+        }
       }
       if (ITEM_ST && e < 128 && w + 1 < sh.w1)               // next tile's token terms, behind this tile's math
         rt = load_row_terms((int64_t)sh.inner(w + 1) * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
@@ -1789,16 +1795,23 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
       if (!ITEM_ST) {
-        dlogit_half_tile(z, rt, v_begin + sh.inner(w) * BN + half * 64, v_end);
+        const int vc0 = v_begin + sh.inner(w) * BN + half * 64;
+        if (b_out) {                                         // warp-uniform: output bias of the items in the columns
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (vc0 + j < v_end) z[j] += __ldg(b_out + vc0 + j);
+        }
+        dlogit_half_tile(z, rt, vc0, v_end);
       } else {
         const int v = v_begin + sh.outer(w) * BN + row;      // this thread's item
         const bool row_ok = v < v_end;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
           const float4 t = sT_gen[half * 64 + j];            // {-m.log2e, coef/s, coef, target} of token column j
-          float x = ptx::ex2_approx(fmaf(z[j], LOG2E, t.x)) * t.y;
+          float x = ptx::ex2_approx(fmaf(z[j] + bias_v, LOG2E, t.x)) * t.y;
           if (__float_as_int(t.w) == v) x -= t.z;
           z[j] = row_ok ? x : 0.f;
+          db_acc += z[j];                                    // dL/db_out[v] = sum over tokens of dlogit
         }
       }
       ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);              // the previous tile's second GEMM has consumed dS
@@ -1836,6 +1849,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         } else {
           const int v = v_begin + sh.outer(w) * BN + row;
           const bool row_ok = v < v_end;
+          if (db_out && row_ok) atomicAdd(db_out + v, db_acc);
 #pragma unroll 1
           for (int c = 0; c < C::ACC_COLS / 2; c += 32) {
             uint32_t r[32];
@@ -1915,7 +1929,8 @@ template <int KB, bool X3, bool ITEM_ST>
 int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
                   const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo, const int32_t* tgt,
                   const float* m, const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
-                  float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw, cudaStream_t st) {
+                  float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw, const float* b_out,
+                  float* db_out, cudaStream_t st) {
   using C = TsCfg<KB, X3>;
   size_t smem = (size_t)C::SMEM_NEED + 1024;                 // slack for the 1024-byte alignment of the tiles
   if (smem > 227 * 1024) smem = 227 * 1024;                  // (the kernel traps if the aligned layout does not fit)
@@ -1923,7 +1938,7 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
-                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem);
+                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -1932,10 +1947,10 @@ int launch_ts(int KB, bool x3, bool item_st, int grid, const CUtensorMap& x_hi, 
               const CUtensorMap& y_hi, const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo,
               const int32_t* tgt, const float* m, const float* s, const float* coef, const float* inv_nvalid,
               const float* hscale, float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
-              cudaStream_t st) {
+              const float* b_out, float* db_out, cudaStream_t st) {
 #define TS3(KBV, X3V, ISV)                                                                                         \
   return launch_ts_one<KBV, X3V, ISV>(grid, x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, \
-                                      out, n_tokens, H, v_begin, v_end, ldw, st)
+                                      out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)
 #define TS2(KBV)                                                         \
   {                                                                      \
     if (x3) { if (item_st) TS3(KBV, true, true); else TS3(KBV, true, false); }     \
@@ -2100,7 +2115,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
                                      const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
                                      float* dh, float* dW_out, int64_t n_tokens, int H, int Hk, int V, int Vp,
                                      int64_t Np, int v_begin, int v_end, int ldw, int accumulate_dh, int x3,
-                                     void* stream) {
+                                     const float* b_out, float* db_out, void* stream) {
   SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
   SEQREC_ARG((Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256) && H <= Hk, 2);
   SEQREC_ARG(Vp >= V && Vp % 8 == 0 && Np >= n_tokens && Np % 8 == 0 && ldw >= v_end, 3);
@@ -2117,7 +2132,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   // logits backward 0.292 -> 0.272 ms).  SEQREC_CE_BWD_TS=0 routes Hk <= 128 to the two older kernels below (dH with dS
   // in TMEM, dW with dS in shared memory), so the implementations can be compared on the same problem.
   static const bool legacy = [] { const char* e = getenv("SEQREC_CE_BWD_TS"); return e && e[0] == '0'; }();
-  if (KB > 2 || !legacy) {
+  if (KB > 2 || !legacy || b_out) {                        // (the legacy kernels have no output-bias path)
     const int64_t total_ts = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
     const int grid_ts = persistent_grid(total_ts);
     if (dh) {
@@ -2128,14 +2143,14 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
       if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
       if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
       if ((rc = launch_ts(KB, x3 != 0, false, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
-                          hscale, dh, n_tokens, H, v_begin, v_end, ldw, st)))
+                          hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, st)))
         return rc;
     }
     if (dW_out) {
       if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
       if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
       if ((rc = launch_ts(KB, x3 != 0, true, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
-                          nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, st)))
+                          nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)))
         return rc;
     }
     return 0;

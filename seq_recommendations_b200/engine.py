@@ -221,7 +221,7 @@ class HotPath:
     def _tc_plan(self, N):
         """Which logits kernels serve a batch of N tokens."""
         fwd = (self.tc_mode != "off" and self.Hk <= 256 and self.V >= 256 and N >= 128)
-        bwd = fwd and not self.out_bias
+        bwd = fwd
         splits = _lib.load().seqrec_ce_tc_partials(N, 0, self.V) if fwd else 0   # partial rows the TC forward writes
         return dict(fwd=fwd, bwd=bwd, splits=splits)
 
@@ -478,7 +478,7 @@ class HotPath:
             call("seqrec_ce_tc_backward", ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), ptr(self.Bt_hi),
                  ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(w.tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
                  ptr(self.inv_nvalid), ptr(w.hscale), ptr(w.dh), ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
-                 self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, st)
+                 self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, ptr(self.b_out), ptr(self.db_out), st)
         else:
             call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
                  ptr(w.m), ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out),

@@ -218,3 +218,20 @@ def test_tc_topk_matches_simt_topk_including_ties(V, H, T, B, monkeypatch):
             r = r.tolist()
             if a in r and b in r:
                 assert r.index(a) + 1 == r.index(b)
+
+
+@pytest.mark.parametrize("cell,act,V,H,T,B", [("GRU", "tanh", 2000, 128, 9, 41), ("LSTM", "relu", 1501, 256, 6, 70),
+                                              ("simpleRNN", "relu", 900, 64, 5, 90)])
+def test_tc_output_bias_forward_and_backward_match_oracle(cell, act, V, H, T, B):
+    """`RNNBaseline`'s logits layer has a bias (model.py:254-257): the tensor-core kernels add b_out to the logits tile in
+    both passes and the item-stationary backward kernel accumulates dL/db_out."""
+    hot, ora, _ = make_pair(cell, act, V, H, seed=21, out_bias=True, bias_scale=0.3, tc="x3")
+    ids, tgt = synthetic.make_batch(V, T, B, seed=22, min_len=1)
+    w = hot.work(B, T)
+    assert w.tc["fwd"] and w.tc["bwd"]
+    loss, grads, _ = hot.grad_batch(ids, tgt)
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+    assert abs(loss - float(rl)) <= 1e-4 * abs(float(rl))
+    assert len(grads) == 5
+    for name, g, r in zip(["W_in", "U", "b", "W_out", "b_out"], grads, rg):
+        assert rel_err(g, r.numpy()) <= 1e-4, (name, rel_err(g, r.numpy()))
