@@ -8,7 +8,7 @@
 // (RB x H).(H x G*H), far too small and too latency-bound for the tensor pipe at the batch sizes of the named configs.
 #include "common.cuh"
 
-#define RNN_THREADS 256
+#define RNN_THREADS 512
 
 // acc[r] += sum_{k in [k0,k1)} vec[r*ldv + k] * mat[k*ldm + col]      (vec in shared memory, mat shared or global)
 template <int RB>
