@@ -38,14 +38,18 @@ def load_peaks():
         return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
-def load_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the committed ncu --set full
-    capture of this workload (profiles/traffic.json, written by scripts/summarize_ncu.py); None when not captured."""
+def load_traffic(workload, prefix="ce_tc_backward"):
+    """(bytes, detail): dram__bytes_read.sum + dram__bytes_write.sum of the dominant phase -- the kernels whose name starts
+    with `prefix`, one launch each per call of seqrec_ce_tc_backward -- from the committed ncu --set full capture of this
+    workload (profiles/traffic.json, written by scripts/summarize_ncu.py), and the per-kernel entries behind the sum;
+    (None, None) when the workload was not captured."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            detail = json.load(f).get(workload)
+        dom = [v["dram_bytes_per_launch"] for k, v in detail.items() if k.startswith(prefix)]
+        return (float(sum(dom)) if dom else None), detail
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
@@ -431,6 +435,7 @@ def main():
     N = B * T
     work = algorithmic_work(cfg, N)
     per_step = {k: v / args.steps for k, v in phases.items()}
+    traffic, traffic_detail = load_traffic(args.config)
     dom_ms = per_step.get("ce_bwd", 0.0)
     achieved = work["ce_bwd_flops"] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     roofline = {
@@ -443,7 +448,8 @@ def main():
         "issued_tflops": (work["ce_bwd_flops"] * ((3 if hot.tc_x3 else 1) * 2.0 if hot.work(B, T).tc["bwd"] else 1.5)
                           / (dom_ms * 1e-3) / 1e12) if dom_ms > 0 else 0.0,
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_sustained"], "traffic": load_traffic(args.config),
+        "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+        "traffic_detail": traffic_detail,
         "peak_source": peaks["src"] + " bf16 sustained",
         "ms_per_launch": dom_ms,
         "others": {

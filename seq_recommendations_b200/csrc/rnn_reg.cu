@@ -223,14 +223,26 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
   const bool owner = (s < RB) && (c < H);      // thread (s, c), s < RB, owns batch row s of unit c (see the forward)
   const int orow = s;
 
+  // U rows into registers through a per-warp 32 x 33 transpose tile: lane l reads element l of the K-slice of one row
+  // (one 128-byte line per load), then picks its own row out of shared memory.  Reading U[c][...] directly is one line
+  // per LANE -- 96 loads x 32 tags per warp, which ncu showed as 18 % of the kernel (stall_lg_throttle) at cfg2.
   float u[G][KPT];
+  {
+    float* tile = smem + (size_t)(tid >> 5) * (32 * 33);    // aliases da_s.. (initialised after the barrier below)
+    const int lane = tid & 31, c0 = c - lane;              // CG is a multiple of 32: a warp has one s, 32 rows
 #pragma unroll
-  for (int g = 0; g < G; ++g)
+    for (int g = 0; g < G; ++g) {
+      const int j = s * KPT + lane;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr)
+        tile[rr * 33 + lane] = (lane < KPT && j < H && c0 + rr < H) ? U[(size_t)(c0 + rr) * GH + g * H + j] : 0.f;
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const int j = s * KPT + i;
-      u[g][i] = (j < H && c < H) ? U[(size_t)c * GH + g * H + j] : 0.f;
+      for (int i = 0; i < KPT; ++i) u[g][i] = tile[lane * 33 + i];
+      __syncwarp();
     }
+  }
+  __syncthreads();
   for (int i = tid; i < G * RB * KP; i += blockDim.x) da_s[i] = 0.f;
   for (int i = tid; i < 2 * RB * CG; i += blockDim.x) dd_s[i] = 0.f;   // dd_s and dc_s
 
@@ -367,8 +379,10 @@ int launch_pair(bool fwd, float* xg, const float* U, const uint8_t* mask, float*
     }
     k<<<grid, threads, smem, st>>>(xg, U, mask, hout, T, B, H);
   } else {
-    const size_t smem = sizeof(float) * (size_t)(G * RB * KP + KS * RB * CG + 2 * RB * NI * CG + 2 * RB * CG) +
-                        sizeof(int) * 2 * RB;
+    const size_t smem_step = sizeof(float) * (size_t)(G * RB * KP + KS * RB * CG + 2 * RB * NI * CG + 2 * RB * CG) +
+                             sizeof(int) * 2 * RB;
+    const size_t smem_load = sizeof(float) * (size_t)(threads / 32) * 32 * 33;   // prologue transpose tiles
+    const size_t smem = smem_step > smem_load ? smem_step : smem_load;
     auto k = rnn_backward_reg_kernel<CELL, ACT, RB, KPT>;
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
