@@ -67,7 +67,7 @@ rnn_forward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, cons
   constexpr int G = Gates<CELL>::G;
   constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;   // gates whose recurrent product uses h_{t-1} itself
   constexpr int KP = KS * KPT;                 // padded hidden size seen by the dot products
-  const int CG = blockDim.x / KS;
+  constexpr int CG = KP;                       // blockDim.x / KS: H rounded up to 32 == KS * KPT (dispatch_kpt)
   const int GH = G * H;
   extern __shared__ __align__(16) float smem[];
   float* h_s = smem;                           // [RB][KP]        h_{t-1}
@@ -208,7 +208,7 @@ rnn_backward_reg_kernel(float* __restrict__ xg, const float* __restrict__ U, con
   constexpr int G1 = (CELL == SEQREC_CELL_GRU) ? 2 : 1;
   constexpr int NI = (CELL == SEQREC_CELL_GRU) ? 5 : 2;   // prefetched per-step inputs: dh, gates..., h_{t-1}
   constexpr int KP = KS * KPT;
-  const int CG = blockDim.x / KS;
+  constexpr int CG = KP;                       // blockDim.x / KS: H rounded up to 32 == KS * KPT (dispatch_kpt)
   const int GH = G * H;
   extern __shared__ __align__(16) float smem[];
   float* da_s = smem;                          // [G][RB][KP]      pre-activation gradients of this step
