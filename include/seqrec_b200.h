@@ -125,6 +125,12 @@ int seqrec_ce_forward(const float* hout, const float* hscale, const float* W_out
 int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
                        float* s_out, float* ce, float* py, float* coef, float* loss_sum, int64_t n_tokens,
                        int splits, void* stream);
+/* seqrec_ce_finalize plus the masked mean Keras reports (weighted loss / number of unmasked steps, training.py
+ * `_weighted_masked_objective` as used by model.py:397): n_valid[0] = unmasked tokens (int32, device);
+ * inv_nvalid[0] = 1 / n_valid (the factor the backward pass scales with), loss_mean[0] = loss_sum * inv_nvalid. */
+int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
+                            float* s_out, float* ce, float* py, float* coef, float* loss_sum, const int32_t* n_valid,
+                            float* inv_nvalid, float* loss_mean, int64_t n_tokens, int splits, void* stream);
 
 /* ---- K6: backward of K5 with recomputed logits ------------------------------------------------------------------
  * dlogit[n,v] = (exp(z-m)/s - [v==tgt]) * coef[n] * inv_nvalid[0];

@@ -47,7 +47,8 @@ class _Work:
         self.ids = torch.empty((T, B), dtype=i32, device=dev)
         self.tgt = torch.empty((T, B), dtype=i32, device=dev)
         self.mask = torch.empty((T, B), dtype=torch.uint8, device=dev)
-        self.n_valid_i = torch.zeros(1, dtype=i32, device=dev)
+        self.n_valid_i = hp.scal[0:1]               # shared per-step scalar block (HotPath.scal)
+        self.loss_mean = torch.zeros(1, dtype=f32, device=dev)
         self.xg = torch.empty((T, B, hp.GH), dtype=f32, device=dev)
         self.hout = torch.empty((T, B, hp.H), dtype=f32, device=dev)
         self.cst = torch.empty((T, B, hp.H), dtype=f32, device=dev)
@@ -137,7 +138,11 @@ class HotPath:
             o += _align(s)
         self._seg = list(zip(offs, sizes))
         self.flat_p = torch.zeros(o, dtype=f32, device=dev)
-        self.flat_g = torch.zeros(o, dtype=f32, device=dev)
+        # gradients and the per-step scalars share one allocation, so a training step clears both with ONE fill:
+        # scal[0] unmasked tokens (int32), [1] touched-row count (int32), [2:4] squared gradient norm (float64)
+        self._grads_and_scal = torch.zeros(o + 4, dtype=f32, device=dev)   # o is a multiple of 64 floats
+        self.flat_g = self._grads_and_scal[:o]
+        self.scal = self._grads_and_scal[o:o + 4].view(torch.int32)
         self.flat_a = torch.zeros(o, dtype=f32, device=dev)
 
         def views(flat):
@@ -170,8 +175,8 @@ class HotPath:
             self.U_lo = torch.empty((self.H, self.GH), dtype=torch.bfloat16, device=dev)
         self.touched = torch.zeros(self.F, dtype=torch.int32, device=dev)
         self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
-        self.n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.n_rows = self.scal[1:2]
+        self.sumsq = self.scal[2:4].view(torch.float64)
         self.inv_nvalid = torch.ones(1, dtype=f32, device=dev)
         self.trainable = {"W_in": True, "U": True, "b": True, "W_out": True, "b_out": True}
         self.opt = None
@@ -296,13 +301,18 @@ class HotPath:
         self.reset_optimizer_state()
 
     # ------------------------------------------------------------------------------------------------ batch ingest
-    def _format(self, w, have_t=True):
+    def _zero_step_scalars(self, grads=False):
+        """n_valid, n_rows and sumsq start every step at zero; staging a batch is the start of a step.  grads: a
+        training step -- the flat gradient buffer (dense, accumulated into by the backward kernels) goes with them."""
+        (self._grads_and_scal if grads else self.scal).zero_()
+
+    def _format(self, w, have_t=True, grads=False):
         """(B,T) device ids/targets -> time-major ids/targets/mask + valid-token count (the in-graph part of ingest)."""
-        w.n_valid_i.zero_()
+        self._zero_step_scalars(grads)
         call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
              ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, self.stream)
 
-    def _stage(self, w, ids, tgt, x_dense=None, format_now=True):
+    def _stage(self, w, ids, tgt, x_dense=None, format_now=True, grads=False):
         """Host (numpy / pinned torch) or device batch -> time-major device buffers.  ids (B,T) int32, pad < 0."""
         st = self.stream
 
@@ -336,9 +346,9 @@ class HotPath:
                 w.pin_dirty = False
             if not format_now:
                 return
-            self._format(w, have_t)
+            self._format(w, have_t, grads)
         else:
-            w.n_valid_i.zero_()
+            self._zero_step_scalars(grads)
             # dense-feature input (RNNBaseline): x_dense (B,T,F) float; mask = any(x != 0) (model.py:246)
             xd = x_dense if isinstance(x_dense, torch.Tensor) else torch.from_numpy(
                 np.ascontiguousarray(x_dense, dtype=np.float32))
@@ -434,9 +444,9 @@ class HotPath:
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
 
-    def _forward_ce(self, w, with_targets=True, training=False):
+    def _forward_ce(self, w, with_targets=True, training=False, mean=False):
         n_splits = self._ce_partials(w, with_targets, training)
-        self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets)
+        self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets, mean)
 
     def _ce_partials(self, w, with_targets=True, training=False):
         """Logits kernels only: per-token partial (max, sum-exp) rows in w.ws_m / w.ws_s and the target logit in w.zy.
@@ -467,9 +477,16 @@ class HotPath:
                  self.V, self.V, n_splits, 0, st)
         return n_splits
 
-    def _finalize_ce(self, w, ws_m, ws_s, n_splits, with_targets=True):
-        call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
-             ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
+    def _finalize_ce(self, w, ws_m, ws_s, n_splits, with_targets=True, mean=False):
+        """mean: this rank's tokens are the whole batch -- the kernel also writes 1/n_valid (self.inv_nvalid) and the
+        masked-mean loss (w.loss_mean), which saves three one-element launches between the logits passes."""
+        if mean:
+            call("seqrec_ce_finalize_mean", ptr(ws_m), ptr(ws_s), ptr(w.zy), ptr(w.mask), ptr(w.m), ptr(w.s), ptr(w.ce),
+                 ptr(w.py), ptr(w.coef), ptr(w.loss_sum), ptr(w.n_valid_i), ptr(self.inv_nvalid), ptr(w.loss_mean),
+                 w.N, n_splits, self.stream)
+        else:
+            call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
+                 ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
         self._mark("misc")
 
     def _backward_ce(self, w):
@@ -513,7 +530,7 @@ class HotPath:
                      (not self.comm.enabled or self.graph_collectives) and
                      self.dropout_in == 0 and self.dropout_out == 0)
         if not graphable:
-            self._stage(w, ids, tgt, x_dense)
+            self._stage(w, ids, tgt, x_dense, grads=True)
             return self._train_core(w)
         # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~45 short launches of a step are
         # submitted as one graph, which removes the launch gaps between them.  The first step of a (B,T) shape runs
@@ -522,12 +539,12 @@ class HotPath:
         if w.graph is None:
             w.graph_calls += 1
             if w.graph_calls < 2:
-                self._format(w)
+                self._format(w, grads=True)
                 return self._train_core(w)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._format(w)
+                self._format(w, grads=True)
                 w.graph_loss = self._train_core(w)
             w.graph = g
         w.graph.replay()
@@ -539,7 +556,6 @@ class HotPath:
         st = self.stream
         comm = self.comm
         self._split_version = -1                  # a training step always follows a weight update: re-stage W_out
-        n_valid = w.n_valid_i.to(torch.float32)
         # data parallel: the ids of all ranks (union of touched rows for the dense dW_in exchange) travel behind the
         # forward pass; n_valid and loss_sum are reduced together in ONE two-float all-reduce after it (the forward
         # needs neither: 1/n_valid first enters in the logits backward)
@@ -547,18 +563,18 @@ class HotPath:
                       embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense")
         all_ids, ids_handle = comm.all_gather_cat_async(w.ids.view(-1)) if dense_rows else (None, None)
         self._forward_hidden(w, training=True)
-        self._forward_ce(w, training=True)
+        self._forward_ce(w, training=True, mean=not comm.enabled)
         if comm.enabled:
-            pair = torch.cat([n_valid, w.loss_sum])
+            pair = torch.cat([w.n_valid_i.to(torch.float32), w.loss_sum])
             comm.all_reduce_sum(pair)
-            n_valid, loss_sum = pair[0:1], pair[1:2]
+            torch.reciprocal(pair[0:1], out=self.inv_nvalid)
+            loss = pair[1:2] * self.inv_nvalid
         else:
-            loss_sum = w.loss_sum
-        torch.reciprocal(n_valid, out=self.inv_nvalid)
-        loss = loss_sum * self.inv_nvalid
+            # written with inv_nvalid by the finalize kernel; a graph replay hands out the static buffer (as it always
+            # did), an eager step a private copy
+            loss = w.loss_mean if torch.cuda.is_current_stream_capturing() else w.loss_mean.clone()
 
-        # ---- backward
-        self.flat_g.zero_()
+        # ---- backward (flat_g was cleared with the step scalars when the batch was staged)
         self._mark("ce_bwd")
         self._backward_ce(w)
         # data parallel: dW_out / db_out are final here -- their all-reduce runs on NCCL's stream behind the recurrent
@@ -570,8 +586,7 @@ class HotPath:
         self._rnn_backward(w)
         # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs
         self._mark("scatter")
-        self.n_rows.zero_()
-        if w.x_dense is None:
+        if w.x_dense is None:                     # (n_rows and sumsq were cleared when the batch was staged)
             if not comm.enabled:
                 call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                      ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
@@ -607,7 +622,7 @@ class HotPath:
             if h is not None:
                 h.wait()
         self._mark("optim")
-        self._apply_update(w)
+        self._apply_update(w, scalars_clean=True)
         self._w_version += 1
         self._mark("end")
         return loss
@@ -698,10 +713,11 @@ class HotPath:
         names = ["U", "b", "W_out", "b_out"]
         return [(n, o, s) for n, (o, s) in zip(names, self._seg) if s > 0]
 
-    def _apply_update(self, w):
+    def _apply_update(self, w, scalars_clean=False):
         st = self.stream
         o = self.opt
-        self.sumsq.zero_()
+        if not scalars_clean:
+            self.sumsq.zero_()
         segs = self._segments()
         all_dense = all(self.trainable[n] for n, _, _ in segs)
         max_rows = min(self.F, w.N * self.comm.world)
