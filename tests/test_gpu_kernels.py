@@ -252,3 +252,44 @@ def test_dense_feature_inputs_match_oracle():
     assert abs(loss - float(rl)) <= TOL * abs(float(rl))
     for g, r in zip(grads, rg):
         assert rel_err(g, r.numpy()) <= TOL
+
+
+@pytest.mark.parametrize("N,splits", [(1, 1), (777, 3), (12800, 5)])
+def test_finalize_mean_matches_finalize_and_numpy(N, splits):
+    """seqrec_ce_finalize_mean = seqrec_ce_finalize + (1/n_valid, masked mean): same per-token outputs bit for bit, and
+    the two scalars against a float64 numpy restatement (Keras masked mean: sum of masked losses / unmasked steps)."""
+    rng = np.random.default_rng(N)
+    ws_m = torch.tensor(rng.standard_normal((splits, N)).astype(np.float32)).cuda()
+    ws_s = torch.tensor((rng.random((splits, N)) * 50 + 1).astype(np.float32)).cuda()
+    zy = torch.tensor(rng.standard_normal(N).astype(np.float32)).cuda()
+    mask_h = (rng.random(N) > 0.3).astype(np.uint8)
+    mask_h[0] = 1
+    mask = torch.tensor(mask_h).cuda()
+    n_valid = torch.tensor([int(mask_h.sum())], dtype=torch.int32).cuda()
+    outs = []
+    for mean in (False, True):
+        m, s, ce, py, coef = (torch.empty(N, dtype=torch.float32, device="cuda") for _ in range(5))
+        loss_sum = torch.zeros(1, dtype=torch.float32, device="cuda")
+        inv, lm = torch.zeros(1, dtype=torch.float32, device="cuda"), torch.zeros(1, dtype=torch.float32, device="cuda")
+        if mean:
+            call("seqrec_ce_finalize_mean", ptr(ws_m), ptr(ws_s), ptr(zy), ptr(mask), ptr(m), ptr(s), ptr(ce), ptr(py),
+                 ptr(coef), ptr(loss_sum), ptr(n_valid), ptr(inv), ptr(lm), N, splits, stream())
+        else:
+            call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(zy), ptr(mask), ptr(m), ptr(s), ptr(ce), ptr(py),
+                 ptr(coef), ptr(loss_sum), N, splits, stream())
+        torch.cuda.synchronize()
+        outs.append([t.cpu() for t in (m, s, ce, py, coef, loss_sum, inv, lm)])
+    for a, b in zip(outs[0][:6], outs[1][:6]):
+        assert torch.equal(a, b)
+    nv = float(mask_h.sum())
+    assert outs[1][6].item() == np.float32(1.0) / np.float32(nv)
+    ref_mean = outs[1][2].double().numpy().sum() / nv
+    assert abs(outs[1][7].item() - ref_mean) <= 1e-6 * abs(ref_mean)
+    # and the per-token losses against numpy: merged (m, s) -> -log(clip(exp(zy - m) / s))
+    mm = ws_m.cpu().double().numpy()
+    ss = ws_s.cpu().double().numpy()
+    gm = mm.max(axis=0)
+    gs = (ss * np.exp(mm - gm)).sum(axis=0)
+    p = np.clip(np.exp(zy.cpu().double().numpy() - gm) / gs, 1e-7, 1 - 1e-7)
+    ref_ce = np.where(mask_h != 0, -np.log(p), 0.0)
+    assert rel_err(outs[1][2].numpy(), ref_ce) < TOL
