@@ -15,6 +15,7 @@ HBM layout (all fp32 unless noted; token n = t*B + b, time-major):
   per batch ids/tgt int32 [T][B], mask u8 [T][B], xg [T][B][G*H] (xp -> gates -> dxp in place),
             hout [T][B][H], cst [T][B][H], dh [T][B][H], per-token stats m,s,zy,ce,py,coef [N], ws [splits][N]
 """
+import contextlib
 import ctypes
 import math
 import os
@@ -182,6 +183,11 @@ class HotPath:
         self.opt = None
         self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
         self.use_graphs = os.environ.get("SEQREC_GRAPHS", "1") == "1"
+        # independent short kernels of a step (operand staging | scan, target logit | logits pass, scatter-add | dU
+        # GEMMs, dense | row-sparse optimiser halves) run as parallel branches: a second stream, forked and joined with
+        # events -- under CUDA-graph capture these become parallel branches of the step graph
+        self.overlap = os.environ.get("SEQREC_OVERLAP", "1") == "1"
+        self._side_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self.graph_collectives = os.environ.get("SEQREC_GRAPH_COLLECTIVES", "1") == "1"   # capture NCCL calls too
         # tensor-core logits path: 'x3' = 3-pass bf16 split products (fp32-grade, the default), 'bf16' = single pass,
         # 'off' = exact-fp32 SIMT kernels.  SEQREC_TC overrides.  Small / odd problems always take the SIMT kernels.
@@ -216,6 +222,24 @@ class HotPath:
     @property
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @contextlib.contextmanager
+    def _branch(self):
+        """Work issued inside runs on the side stream, after everything queued on the current stream so far; the caller
+        MUST `_join()` before anything consumes its results (and before the step ends).  Serial (a plain pass-through)
+        while bench.py profiles phases, so that every phase is timed alone."""
+        if not self.overlap or self.prof is not None or self._side_stream is None:
+            yield
+            return
+        self._side_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._side_stream):
+            yield
+        self._branched = True
+
+    def _join(self):
+        if getattr(self, "_branched", False):
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
+            self._branched = False
 
     def _ce_splits(self, N):
         tiles = (N + 63) // 64
@@ -462,12 +486,15 @@ class HotPath:
                 call("seqrec_split_bf16", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), w.N, self.H, self.Hk,
                      0, st)
             w.tc_operands_fresh = True
+            self._join()                          # W_out operands staged on the branch by _train_core
             self._mark("ce_fwd")
-            if with_targets:
-                call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
-                     ptr(w.zy), w.N, self.H, self.V, st)
+            if with_targets:                      # the target logit is not needed before the finalize kernel
+                with self._branch():
+                    call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
+                         ptr(w.tgt), ptr(w.zy), w.N, self.H, self.V, self.stream)
             call("seqrec_ce_tc_forward", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out),
                  ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, 1 if self.tc_x3 else 0, st)
+            self._join()
             n_splits = w.tc["splits"]
         else:
             self._mark("ce_fwd")
@@ -562,6 +589,10 @@ class HotPath:
         dense_rows = (comm.enabled and w.x_dense is None and
                       embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense")
         all_ids, ids_handle = comm.all_gather_cat_async(w.ids.view(-1)) if dense_rows else (None, None)
+        if w.tc["fwd"]:
+            self._mark("stage_operands")
+            with self._branch():                  # bf16 operands of the updated W_out, behind gather + scan
+                self._stage_weight_operands()
         self._forward_hidden(w, training=True)
         self._forward_ce(w, training=True, mean=not comm.enabled)
         if comm.enabled:
@@ -584,7 +615,12 @@ class HotPath:
         pending = [comm.all_reduce_sum(self.flat_g[head:], async_op=True)] if comm.enabled else []
         self._mark("rnn_bwd")
         self._rnn_backward(w)
-        # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs
+        # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs, which run
+        #      as a parallel branch (both only read dxp)
+        branch_wgrad = self.overlap and self.prof is None
+        if branch_wgrad:
+            with self._branch():
+                self._rnn_weight_grad(w)
         self._mark("scatter")
         if w.x_dense is None:                     # (n_rows and sumsq were cleared when the batch was staged)
             if not comm.enabled:
@@ -612,7 +648,10 @@ class HotPath:
             if comm.enabled:
                 pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
         self._mark("rnn_wgrad")
-        self._rnn_weight_grad(w)
+        if branch_wgrad:
+            self._join()
+        else:
+            self._rnn_weight_grad(w)
         self._mark("allreduce")
         if comm.enabled:
             pending.append(comm.all_reduce_sum(self.flat_g[:head], async_op=True))
@@ -721,19 +760,37 @@ class HotPath:
         segs = self._segments()
         all_dense = all(self.trainable[n] for n, _, _ in segs)
         max_rows = min(self.F, w.N * self.comm.world)
+        # the W_in half (row-sparse or dense) runs as a parallel branch of the flat-buffer half
         if o["clipnorm"] > 0:
+            if self.trainable["W_in"]:
+                with self._branch():
+                    if w.x_dense is None:
+                        call("seqrec_sumsq_rows", ptr(self.dW_in), ptr(self.rows), ptr(self.n_rows), self.GH, max_rows,
+                             ptr(self.sumsq), self.stream)
+                    else:
+                        call("seqrec_sumsq", ptr(self.dW_in), self.dW_in.numel(), ptr(self.sumsq), self.stream)
             if all_dense:
                 call("seqrec_sumsq", ptr(self.flat_g), self.flat_g.numel(), ptr(self.sumsq), st)
             else:
                 for n, off, sz in segs:
                     if self.trainable[n]:
                         call("seqrec_sumsq", ptr(self.flat_g[off:off + sz]), sz, ptr(self.sumsq), st)
-            if self.trainable["W_in"]:
-                if w.x_dense is None:
-                    call("seqrec_sumsq_rows", ptr(self.dW_in), ptr(self.rows), ptr(self.n_rows), self.GH, max_rows,
-                         ptr(self.sumsq), st)
+            self._join()
+        with self._branch():
+            if w.x_dense is None:
+                if self.trainable["W_in"]:
+                    # also re-zeroes the touched rows of dW_in and their flags (zero invariant of the dense buffer)
+                    call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows),
+                         ptr(self.n_rows), ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"],
+                         ptr(self.sumsq), self.stream)
                 else:
-                    call("seqrec_sumsq", ptr(self.dW_in), self.dW_in.numel(), ptr(self.sumsq), st)
+                    self.dW_in.zero_()
+                    self.touched.zero_()
+            else:
+                if self.trainable["W_in"]:
+                    call("seqrec_adagrad", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), self.W_in.numel(), o["lr"],
+                         o["eps"], o["clipnorm"], ptr(self.sumsq), self.stream)
+                self.dW_in.zero_()
         if all_dense:
             call("seqrec_adagrad", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_a), self.flat_p.numel(), o["lr"],
                  o["eps"], o["clipnorm"], ptr(self.sumsq), st)
@@ -742,20 +799,7 @@ class HotPath:
                 if self.trainable[n]:
                     call("seqrec_adagrad", ptr(self.flat_p[off:off + sz]), ptr(self.flat_g[off:off + sz]),
                          ptr(self.flat_a[off:off + sz]), sz, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
-        if w.x_dense is None:
-            if self.trainable["W_in"]:
-                # also re-zeroes the touched rows of dW_in and their flags (zero invariant of the dense buffer)
-                call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows),
-                     ptr(self.n_rows), ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"],
-                     ptr(self.sumsq), st)
-            else:
-                self.dW_in.zero_()
-                self.touched.zero_()
-        else:
-            if self.trainable["W_in"]:
-                call("seqrec_adagrad", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), self.W_in.numel(), o["lr"],
-                     o["eps"], o["clipnorm"], ptr(self.sumsq), st)
-            self.dW_in.zero_()
+        self._join()
 
     def _rank_rows(self, wt, hrows, m, s, n, k):
         """Top-k of n rows against THIS rank's items (ids are local item indices), probabilities from (m, s)."""
