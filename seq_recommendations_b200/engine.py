@@ -10,7 +10,8 @@ libseqrec_b200.so.  There is no CPU path: constructing a HotPath without CUDA or
 
 HBM layout (all fp32 unless noted; token n = t*B + b, time-major):
   weights   W_in (F,G*H) | flat[U (H,G*H) | b (G*H) | W_out (H,V) | b_out (V)]         Keras layouts, row-major
-  grads     dW_in (F,G*H) zero-invariant + touched flags + row list | flat like the weights
+  grads     dW_in (F,G*H) zero-invariant + touched flags + row list | flat like the weights, with the per-step
+            scalars (n_valid, touched-row count, squared gradient norm) in its tail: one fill clears both
   accum     Adagrad accumulators, same shapes
   per batch ids/tgt int32 [T][B], mask u8 [T][B], xg [T][B][G*H] (xp -> gates -> dxp in place),
             hout [T][B][H], cst [T][B][H], dh [T][B][H], per-token stats m,s,zy,ce,py,coef [N], ws [splits][N]
@@ -559,7 +560,7 @@ class HotPath:
         if not graphable:
             self._stage(w, ids, tgt, x_dense, grads=True)
             return self._train_core(w)
-        # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~45 short launches of a step are
+        # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~22 launches of a step are
         # submitted as one graph, which removes the launch gaps between them.  The first step of a (B,T) shape runs
         # eagerly, the second one captures.
         self._stage(w, ids, tgt, None, format_now=False)
