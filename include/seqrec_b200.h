@@ -201,6 +201,10 @@ int seqrec_adagrad_rows(float* p, float* g, float* a, const int32_t* rows, const
 /* ---- Dropout (model.py:362-363, :371-372): inverted-dropout factors from a counter-based RNG ---------------------
  * out[i] = (u_i >= rate) ? 1/(1-rate) : 0 */
 int seqrec_dropout_mask(float* out, int64_t n, float rate, uint64_t seed, uint64_t offset, void* stream);
+/* the same factors with the stream position on the device: state[0] = offset of the next draw (advanced by n when the
+ * launch completes), state[1] = internal ticket (0 between launches).  Lets a captured training step draw new factors
+ * at every graph replay. */
+int seqrec_dropout_mask_dev(float* out, int64_t n, float rate, uint64_t seed, uint64_t* state, void* stream);
 
 /* ---- bf16 hi/lo operand staging for the tensor-core logits kernels ----------------------------------------------
  * src (rows, cols) fp32 (optionally times scale (rows, cols)) -> hi, lo bf16 with hi+lo ~= src to 16 mantissa bits.

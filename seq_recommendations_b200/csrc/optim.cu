@@ -198,6 +198,41 @@ dropout_mask_kernel(float* __restrict__ out, int64_t n, float rate, uint64_t see
   }
 }
 
+// Same factors with the stream position held on the device: state[0] = offset of the next draw, state[1] = block ticket.
+// Every block reads the offset when it starts and takes a ticket when it is done; the last one advances the offset by n
+// and clears the ticket -- so a launch captured in a CUDA graph draws fresh factors at every replay.
+__global__ void __launch_bounds__(256)
+dropout_mask_dev_kernel(float* __restrict__ out, int64_t n, float rate, uint64_t seed,
+                        unsigned long long* __restrict__ state) {
+  const uint64_t offset = *((volatile unsigned long long*)state);
+  const float keep = 1.0f / (1.0f - rate);
+  const uint64_t key = splitmix64(seed);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = splitmix64(key ^ (offset + (uint64_t)i));
+    const float u = (float)(r >> 40) * (1.0f / 16777216.0f);
+    out[i] = (u >= rate) ? keep : 0.f;
+  }
+  __syncthreads();                             // every thread of the block has read the offset
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(state + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+      state[0] = offset + (uint64_t)n;
+      state[1] = 0ull;
+    }
+  }
+}
+
+extern "C" int seqrec_dropout_mask_dev(float* out, int64_t n, float rate, uint64_t seed, uint64_t* state,
+                                       void* stream) {
+  SEQREC_ARG(n > 0 && rate >= 0.f && rate < 1.f, 1);
+  SEQREC_ARG(state != nullptr, 5);
+  dropout_mask_dev_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(
+      out, n, rate, seed, reinterpret_cast<unsigned long long*>(state));
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int seqrec_dropout_mask(float* out, int64_t n, float rate, uint64_t seed, uint64_t offset, void* stream) {
   SEQREC_ARG(n > 0 && rate >= 0.f && rate < 1.f, 1);
   dropout_mask_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(out, n, rate, seed, offset);

@@ -71,6 +71,7 @@ class _Work:
         self.pin_event = None
         self.pin_dirty = False
         self.graph = None
+        self.graph_key = None
         self.graph_calls = 0
         self.graph_loss = None
         self.D_hi = self.D_lo = self.Hs_hi = self.Hs_lo = self.C_hi = self.C_lo = None   # bf16 operands of the dU GEMM
@@ -128,7 +129,9 @@ class HotPath:
         self.dropout_in = 0.0
         self.dropout_out = 0.0
         self.seed = int(seed)
-        self._rng_offset = 0
+        # dropout stream position, on the device ([0] next offset, [1] kernel-internal ticket): a captured step draws
+        # fresh factors at every replay
+        self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._work = {}
         f32 = torch.float32
         dev = self.device
@@ -391,8 +394,7 @@ class HotPath:
     def _dropout(self, shape, rate):
         t = torch.empty(shape, dtype=torch.float32, device=self.device)
         n = t.numel()
-        call("seqrec_dropout_mask", ptr(t), n, float(rate), self.seed, self._rng_offset, self.stream)
-        self._rng_offset += n
+        call("seqrec_dropout_mask_dev", ptr(t), n, float(rate), self.seed, ptr(self.rng_state), self.stream)
         return t
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -555,8 +557,7 @@ class HotPath:
         w = self.work(int(B), int(T))
         self._mark("ingest")
         graphable = (self.use_graphs and x_dense is None and self.prof is None and
-                     (not self.comm.enabled or self.graph_collectives) and
-                     self.dropout_in == 0 and self.dropout_out == 0)
+                     (not self.comm.enabled or self.graph_collectives))
         if not graphable:
             self._stage(w, ids, tgt, x_dense, grads=True)
             return self._train_core(w)
@@ -564,6 +565,9 @@ class HotPath:
         # submitted as one graph, which removes the launch gaps between them.  The first step of a (B,T) shape runs
         # eagerly, the second one captures.
         self._stage(w, ids, tgt, None, format_now=False)
+        key = self._graph_key()
+        if w.graph is not None and w.graph_key != key:
+            w.graph, w.graph_calls = None, 1      # host state baked into the captured launches changed: re-capture
         if w.graph is None:
             w.graph_calls += 1
             if w.graph_calls < 2:
@@ -574,10 +578,16 @@ class HotPath:
             with torch.cuda.graph(g):
                 self._format(w, grads=True)
                 w.graph_loss = self._train_core(w)
-            w.graph = g
+            w.graph, w.graph_key = g, key
         w.graph.replay()
         self._w_version += 1
         return w.graph_loss
+
+    def _graph_key(self):
+        """Everything a captured step bakes in BY VALUE (kernel arguments and which kernels are launched at all)."""
+        o = self.opt
+        return (o["lr"], o["eps"], o["clipnorm"], tuple(sorted(self.trainable.items())), self.dropout_in,
+                self.dropout_out, self.overlap, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
 
     def _train_core(self, w):
         """forward + backward + exchange + update on the staged batch (everything after the host->device copy)."""

@@ -293,3 +293,51 @@ def test_finalize_mean_matches_finalize_and_numpy(N, splits):
     p = np.clip(np.exp(zy.cpu().double().numpy() - gm) / gs, 1e-7, 1 - 1e-7)
     ref_ce = np.where(mask_h != 0, -np.log(p), 0.0)
     assert rel_err(outs[1][2].numpy(), ref_ce) < TOL
+
+
+def test_dropout_device_state_matches_host_offsets():
+    """seqrec_dropout_mask_dev draws the factors of seqrec_dropout_mask at the offset held on the device and advances
+    it by n when the launch completes (several blocks: the last one to finish moves the offset)."""
+    n, rate, seed = 300_001, 0.25, 77
+    state = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for step in range(3):
+        a = torch.empty(n, dtype=torch.float32, device="cuda")
+        b = torch.empty(n, dtype=torch.float32, device="cuda")
+        call("seqrec_dropout_mask_dev", ptr(a), n, rate, seed, ptr(state), stream())
+        call("seqrec_dropout_mask", ptr(b), n, rate, seed, step * n, stream())
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        assert state.cpu().tolist() == [(step + 1) * n, 0]
+
+
+def test_graph_replayed_step_draws_new_dropout_factors_and_follows_host_state():
+    """A training step with z->y dropout replays as a CUDA graph: every replay draws new factors (device-side stream
+    position), and a change of the host state baked into the capture (dropout rate, learning rate) re-captures."""
+    V, H, T, B = 300, 32, 6, 16
+    hot, _, _ = make_pair("GRU", "tanh", V, H, seed=5)
+    hot.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
+    hot.dropout_out = 0.3
+    ids, tgt = synthetic.make_batch(V, T, B, seed=6)
+    w = hot.work(B, T)
+    masks, losses = [], []
+    for _ in range(5):
+        losses.append(float(hot.train_batch(ids, tgt).item()))
+        masks.append(w.hscale.clone())
+    assert w.graph is not None                                           # steps 2.. were replays
+    assert all(np.isfinite(losses))
+    for a, b in zip(masks[:-1], masks[1:]):
+        assert not torch.equal(a, b)
+    zero_frac = float(torch.stack(masks).eq(0).float().mean().item())
+    assert abs(zero_frac - 0.3) < 0.03
+    assert int(hot.rng_state[0].item()) == 5 * T * B * H
+    g0 = w.graph
+    hot.dropout_out = 0.0
+    hot.train_batch(ids, tgt)
+    assert w.graph is not g0 and w.hscale is None                        # re-captured without the dropout launches
+    g1 = w.graph
+    before = hot.weight_list()[3].clone()
+    hot.opt["lr"] = 0.0                                                  # baked into the Adagrad launch by value
+    hot.train_batch(ids, tgt)
+    torch.cuda.synchronize()
+    assert w.graph is not g1
+    assert torch.equal(hot.weight_list()[3], before)
