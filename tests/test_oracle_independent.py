@@ -147,7 +147,7 @@ def test_one_model_step_equals_torch_modules_end_to_end(monkeypatch):
     h, _ = lstm(emb(ids))
     ref = torch.nn.functional.cross_entropy(out(h).reshape(-1, V), tgt.reshape(-1), reduction="mean")
     ref.backward()
-    assert abs(float(loss) - float(ref)) <= 1e-12 * abs(float(ref))
+    assert abs(float(loss) - float(ref.detach())) <= 1e-12 * abs(float(ref.detach()))
     assert torch.allclose(grads[0], emb.weight.grad, rtol=1e-9, atol=1e-13)
     assert torch.allclose(grads[1], lstm.weight_hh_l0.grad.t(), rtol=1e-9, atol=1e-13)
     assert torch.allclose(grads[2], lstm.bias_ih_l0.grad, rtol=1e-9, atol=1e-13)
