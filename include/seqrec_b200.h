@@ -42,9 +42,12 @@ int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets, int32_t* 
 
 /* ---- batch format (preprocessor.py:67-94, model.py:335 Masking) ------------------------------------------------
  * (B,T) batch-major ids/targets (pad = negative) -> time-major ids/targets/mask; counts valid tokens into
- * n_valid[0] (int32, must be zeroed by the caller). */
+ * n_valid[0] (int32, must be zeroed by the caller).  Range check: an input id >= n_in, or a target outside [0, n_items)
+ * on a valid step, turns the token into a pad and sets bit 0 / bit 1 of err[0] (int32, may be NULL; the reference raises
+ * IndexError in np_utils.to_categorical, preprocessor.py:75-78) -- no kernel ever indexes a table with such an id. */
 int seqrec_format_batch(const int32_t* ids_bt, const int32_t* tgt_bt, int32_t* ids_tb, int32_t* tgt_tb,
-                        uint8_t* mask_tb, int32_t* n_valid, int B, int T, void* stream);
+                        uint8_t* mask_tb, int32_t* n_valid, int B, int T, int n_in, int n_items, int32_t* err,
+                        void* stream);
 
 /* ---- K1: one-hot x input-kernel == row gather (model.py:360-364 LSTM on the masked one-hot input) ---------------
  * xp[n,:] = (mask[n] ? in_scale[n]*W_in[ids[n],:] : 0) + b.   in_scale may be NULL (no y->z dropout). */
@@ -98,6 +101,9 @@ int seqrec_rnn_tc_forward(int cell, int act, float* xg, const uint16_t* Ut_hi, c
 int seqrec_rnn_tc_backward(int cell, int act, float* xg, const uint16_t* U_hi, const uint16_t* U_lo,
                            const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T, int B, int H,
                            void* stream);
+/* diagnostics (scripts/time_rnn.py): device buffer of 64 x 8 clock64() stamps written by CTA 0 of the tensor-core scans
+ * at their protocol points; NULL switches the capture off (the default) */
+int seqrec_rnn_tc_debug_buffer(long long* dev_buf);
 /* dU (H,G*H) += sum_t hprev_t^T . dxp_t (GRU candidate block uses cst = r*hprev);  db (G*H) += sum_n dxp[n,:].
  * dU and db must be pre-zeroed. */
 int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* hout, const float* cst, float* dU, float* db,
@@ -119,7 +125,7 @@ int seqrec_transpose(const float* in, float* out, int rows, int cols, void* stre
  * hscale: optional inverted-dropout factors (N,H) applied to hout (z->y Dropout, model.py:371-372). */
 int seqrec_ce_forward(const float* hout, const float* hscale, const float* W_out, const float* b_out,
                       const int32_t* tgt, float* ws_m, float* ws_s, float* zy, int64_t n_tokens, int H, int V,
-                      int v_begin, int v_end, int ldw, int splits, int use_tensor_cores, void* stream);
+                      int v_begin, int v_end, int ldw, int splits, void* stream);
 /* merge partial stats; ce[n] = -log(clip(exp(zy-m)/s, 1e-7, 1-1e-7))*mask; py[n] = clipped prob (model.py:108-110);
  * coef[n] = mask * [clip inactive] (to be scaled by 1/n_valid); loss_sum[0] = sum ce (deterministic single block) */
 int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
@@ -127,10 +133,11 @@ int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const float* zy, co
                        int splits, void* stream);
 /* seqrec_ce_finalize plus the masked mean Keras reports (weighted loss / number of unmasked steps, training.py
  * `_weighted_masked_objective` as used by model.py:397): n_valid[0] = unmasked tokens (int32, device);
- * inv_nvalid[0] = 1 / n_valid (the factor the backward pass scales with), loss_mean[0] = loss_sum * inv_nvalid. */
+ * n_valid_f[0] = (float)n_valid (the denominator the optimiser divides the un-normalised gradients by -- summed over
+ * ranks in a data-parallel step), loss_mean[0] = loss_sum / n_valid. */
 int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
                             float* s_out, float* ce, float* py, float* coef, float* loss_sum, const int32_t* n_valid,
-                            float* inv_nvalid, float* loss_mean, int64_t n_tokens, int splits, void* stream);
+                            float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits, void* stream);
 
 /* ---- K6: backward of K5 with recomputed logits ------------------------------------------------------------------
  * dlogit[n,v] = (exp(z-m)/s - [v==tgt]) * coef[n] * inv_nvalid[0];
@@ -139,8 +146,7 @@ int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* z
 int seqrec_ce_backward(const float* hout, const float* hscale, const float* W_out, const float* b_out,
                        const int32_t* tgt, const float* m, const float* s, const float* coef,
                        const float* inv_nvalid, float* dh, float* dW_out, float* db_out, int64_t n_tokens, int H,
-                       int V, int v_begin, int v_end, int ldw, int accumulate_dh, int use_tensor_cores,
-                       void* stream);
+                       int V, int v_begin, int v_end, int ldw, int accumulate_dh, void* stream);
 
 /* ---- K5/K6 on the tcgen05 tensor cores (csrc/ce_tc.cu) ----------------------------------------------------------
  * Operands are bf16 hi/lo pairs staged by seqrec_split_bf16 (lo pointers may be NULL when x3 == 0 = single-pass bf16):
@@ -184,19 +190,27 @@ int seqrec_topk_tc(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B
                    const float* b_out, const float* m, const float* s, float* ws_v, int32_t* ws_i, int32_t* topk_ids,
                    float* topk_p, int64_t n_rows, int Hk, int V, int k, int x3, void* stream);
 
+/* merge of n_lists candidate lists per row -- cand_v / cand_i [n_lists][.][k] with `list_stride` elements between the
+ * lists of a row -- into the row's top k: value descending, lower item id first on ties (the stable-argsort order of
+ * the oracle).  Ends the vocabulary-parallel ranking (one list per item shard).  n_lists * k <= 384. */
+int seqrec_topk_merge(const float* cand_v, const int32_t* cand_i, int n_lists, int64_t list_stride,
+                      int32_t* topk_ids, float* topk_p, int64_t n_rows, int k, void* stream);
+
 /* ---- K8: global-norm clip + Adagrad (experiments_methods.py:41) -------------------------------------------------
  * sumsq[0] (double, pre-zeroed) += sum g^2 */
 int seqrec_sumsq(const float* g, int64_t n, double* sumsq, void* stream);
 int seqrec_sumsq_rows(const float* g, const int32_t* rows, const int32_t* n_rows, int GH, int max_rows,
                       double* sumsq, void* stream);
-/* scale = (norm >= clipnorm) ? clipnorm/norm : 1 (clipnorm <= 0: no clip); a += (g*scale)^2;
- * p -= lr*g*scale/(sqrt(a)+eps) */
+/* The stored gradient g may be UN-normalised (a sum over tokens): gdenom[0] (device float, NULL = 1) is the global number
+ * of unmasked steps the Keras objective divides by.  g' = g / gdenom; norm = sqrt(sumsq) / gdenom;
+ * scale = (norm >= clipnorm) ? clipnorm/norm : 1 (clipnorm <= 0: no clip); a += (g'*scale)^2;
+ * p -= lr*g'*scale/(sqrt(a)+eps) */
 int seqrec_adagrad(float* p, const float* g, float* a, int64_t n, float lr, float eps, float clipnorm,
-                   const double* sumsq, void* stream);
+                   const double* sumsq, const float* gdenom, void* stream);
 /* row-sparse variant over the touched rows; also re-zeroes those rows of g and their touched flags */
 int seqrec_adagrad_rows(float* p, float* g, float* a, const int32_t* rows, const int32_t* n_rows, int32_t* touched,
                         int GH, int max_rows, float lr, float eps, float clipnorm, const double* sumsq,
-                        void* stream);
+                        const float* gdenom, void* stream);
 
 /* ---- Dropout (model.py:362-363, :371-372): inverted-dropout factors from a counter-based RNG ---------------------
  * out[i] = (u_i >= rate) ? 1/(1-rate) : 0 */

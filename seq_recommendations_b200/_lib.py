@@ -23,7 +23,7 @@ SIGNATURES = {
     "seqrec_abi_version": [],
     "seqrec_launch_count": [_i],
     "seqrec_pad_sequences": [_p, _p, _p, _p, _l, _i, _p],
-    "seqrec_format_batch": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "seqrec_format_batch": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
     "seqrec_gather_rows": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_scatter_add_rows": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_mark_rows": [_p, _p, _p, _p, _p, _l, _i, _p],
@@ -35,13 +35,14 @@ SIGNATURES = {
     "seqrec_rnn_tc_applicable": [_i, _i],
     "seqrec_rnn_tc_forward": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_tc_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_tc_debug_buffer": [_p],
     "seqrec_rnn_weight_grad": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_weight_grad_tc": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_transpose": [_p, _p, _i, _i, _p],
-    "seqrec_ce_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
+    "seqrec_ce_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_finalize": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
     "seqrec_ce_finalize_mean": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
-    "seqrec_ce_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
+    "seqrec_ce_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_tc_forward": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_tc_partials": [_l, _i, _i],
     "seqrec_ce_tc_backward": [_p] * 16 + [_l, _i, _i, _i, _i, _l, _i, _i, _i, _i, _i, _p, _p, _p],
@@ -49,10 +50,11 @@ SIGNATURES = {
     "seqrec_predict_probs": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "seqrec_topk": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p],
     "seqrec_topk_tc": [_p] * 11 + [_l, _i, _i, _i, _i, _p],
+    "seqrec_topk_merge": [_p, _p, _i, _l, _p, _p, _l, _i, _p],
     "seqrec_sumsq": [_p, _l, _p, _p],
     "seqrec_sumsq_rows": [_p, _p, _p, _i, _i, _p, _p],
-    "seqrec_adagrad": [_p, _p, _p, _l, _f, _f, _f, _p, _p],
-    "seqrec_adagrad_rows": [_p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p],
+    "seqrec_adagrad": [_p, _p, _p, _l, _f, _f, _f, _p, _p, _p],
+    "seqrec_adagrad_rows": [_p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p],
     "seqrec_dropout_mask": [_p, _l, _f, _u64, _u64, _p],
     "seqrec_dropout_mask_dev": [_p, _l, _f, _u64, _p, _p],
     "seqrec_split_bf16": [_p, _p, _p, _p, _l, _l, _l, _i, _p],

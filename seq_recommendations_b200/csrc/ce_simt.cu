@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
 ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_s, const float* __restrict__ zy,
                    const uint8_t* __restrict__ mask, float* __restrict__ m_out, float* __restrict__ s_out,
                    float* __restrict__ ce, float* __restrict__ py, float* __restrict__ coef,
-                   float* __restrict__ loss_sum, const int32_t* __restrict__ n_valid, float* __restrict__ inv_nvalid,
+                   float* __restrict__ loss_sum, const int32_t* __restrict__ n_valid, float* __restrict__ n_valid_f,
                    float* __restrict__ loss_mean, int64_t n_tokens, int splits) {
   __shared__ double red[FIN_THREADS / 32];
   __shared__ bool is_last;
@@ -221,10 +221,10 @@ ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_
       double t = 0.0;
       for (int i = 0; i < FIN_THREADS / 32; ++i) t += red[i];
       if (loss_sum) loss_sum[0] = (float)t;
-      if (n_valid) {                          // masked mean and the 1/n_valid the backward pass scales with
-        const float inv = 1.0f / (float)n_valid[0];
-        if (inv_nvalid) inv_nvalid[0] = inv;
-        if (loss_mean) loss_mean[0] = (float)t * inv;
+      if (n_valid) {                          // masked mean, and the count as the float the optimiser divides by
+        const float nv = (float)n_valid[0];
+        if (n_valid_f) n_valid_f[0] = nv;
+        if (loss_mean) loss_mean[0] = (float)t / nv;
       }
       g_fin_counter = 0;  // ready for the next (stream-ordered) launch
     }
@@ -252,7 +252,7 @@ ce_backward_dh_simt_kernel(const float* __restrict__ hout, const float* __restri
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t n0 = (int64_t)blockIdx.x * CT;
   load_token_tile(sm.A_s, hout, hscale, n0, n_tokens, H);
-  const float inv = inv_nvalid[0];
+  const float inv = inv_nvalid ? inv_nvalid[0] : 1.0f;   // NULL: un-normalised gradients (the optimiser divides)
   float m[4], s[4], cf[4];
   int32_t tg[4];
 #pragma unroll
@@ -340,7 +340,7 @@ ce_backward_dw_simt_kernel(const float* __restrict__ hout, const float* __restri
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int v0 = v_begin + blockIdx.x * CT;
   load_item_tile(sm.W_s, W_out, ldw, v0, v_end, H);
-  const float inv = inv_nvalid[0];
+  const float inv = inv_nvalid ? inv_nvalid[0] : 1.0f;   // NULL: un-normalised gradients (the optimiser divides)
   float bj[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -522,12 +522,12 @@ int ce_backward_simt(const float* hout, const float* hscale, const float* W_out,
 
 static int ce_finalize_launch(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
                               float* s_out, float* ce, float* py, float* coef, float* loss_sum, const int32_t* n_valid,
-                              float* inv_nvalid, float* loss_mean, int64_t n_tokens, int splits, void* stream) {
+                              float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits, void* stream) {
   SEQREC_ARG(n_tokens > 0 && splits > 0, 1);
   int blocks = (int)((n_tokens + FIN_THREADS - 1) / FIN_THREADS);   // one token per thread while the grid allows it
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
   ce_finalize_kernel<<<blocks, FIN_THREADS, 0, as_stream(stream)>>>(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef,
-                                                                   loss_sum, n_valid, inv_nvalid, loss_mean, n_tokens,
+                                                                   loss_sum, n_valid, n_valid_f, loss_mean, n_tokens,
                                                                    splits);
   SEQREC_CHECK_LAUNCH();
   return 0;
@@ -542,10 +542,10 @@ extern "C" int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const fl
 
 extern "C" int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask,
                                        float* m_out, float* s_out, float* ce, float* py, float* coef, float* loss_sum,
-                                       const int32_t* n_valid, float* inv_nvalid, float* loss_mean, int64_t n_tokens,
+                                       const int32_t* n_valid, float* n_valid_f, float* loss_mean, int64_t n_tokens,
                                        int splits, void* stream) {
   SEQREC_ARG(n_valid != nullptr, 11);
-  return ce_finalize_launch(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef, loss_sum, n_valid, inv_nvalid, loss_mean,
+  return ce_finalize_launch(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef, loss_sum, n_valid, n_valid_f, loss_mean,
                             n_tokens, splits, stream);
 }
 

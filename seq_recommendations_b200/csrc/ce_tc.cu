@@ -23,14 +23,6 @@
 
 namespace {
 
-// optional timeline capture (scripts/time_ce.py): CTA 0 of the forward kernel stores clock64() at protocol points of its
-// first 64 tiles.  The pointer is read ONCE per thread into `dbg`.
-__device__ long long* g_ce_dbg = nullptr;
-#define CE_DBG(tile, slot)                                                              \
-  do {                                                                                  \
-    if (dbg && (tile) < 64) dbg[(tile) * 8 + (slot)] = clock64();                       \
-  } while (0)
-
 constexpr int BM = 128;          // tokens per tile (UMMA M)
 constexpr int BN = 128;          // items per tile  (UMMA N of the logits GEMM)
 constexpr int KBLK = 64;         // bf16 elements per 128-byte swizzled row
@@ -92,13 +84,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// byte offset of element (row, col) inside a K-major 128-byte-swizzled operand whose 64-column blocks of `rows`
-// rows are laid one after another (block stride = rows*128 bytes)
-__device__ __forceinline__ uint32_t sw128_offset(int row, int col, int rows) {
-  const int blk = col >> 6, c = col & 63;
-  return (uint32_t)(blk * rows * 128 + row * 128 + ((((c >> 3) ^ (row & 7)) << 4) | ((c & 7) << 1)));
-}
-
 // ---- epilogue helpers (each epilogue warp owns 32 rows x 64 columns of a 128 x 128 logits tile) -------------------
 // load the warp's 64 accumulator columns (two 32-column tcgen05.ld in flight, one wait)
 __device__ __forceinline__ void load_half_tile(uint32_t taddr, float (&z)[64]) {
@@ -149,26 +134,6 @@ __device__ __forceinline__ void dlogit_half_tile(float (&z)[64], const RowTerms&
 #pragma unroll
     for (int j = 0; j < 64; ++j)
       if (j == tj) z[j] -= rt.cf;
-  }
-}
-
-// write this thread's row of 64 dlogits as bf16 hi (and lo) into the swizzled operand block `blk` (rows of 128 B)
-template <bool X3>
-__device__ __forceinline__ void store_dlogit_row(uint8_t* sD_gen, const float (&d)[64], int row, int blk,
-                                                 int lo_offset_bytes) {
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = d[g * 8 + 2 * e], x1 = d[g * 8 + 2 * e + 1];
-      const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
-      if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
-    }
-    const uint32_t off = (uint32_t)(blk * TILE_B + row * 128 + ((g ^ (row & 7)) << 4));
-    *reinterpret_cast<uint4*>(sD_gen + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (X3) *reinterpret_cast<uint4*>(sD_gen + lo_offset_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -501,200 +466,6 @@ __device__ __forceinline__ void row_to_tmem(uint32_t tcol, const uint16_t* __res
 }
 
 // ================================================================================================================
-// forward, A operand in TENSOR MEMORY.  An SS-mode M=128 x N=128 MMA reads 8 KB of shared memory per 64 tensor cycles
-// -- exactly the 128 B/clk the SM's shared memory delivers -- so with the TMA writes of the streamed operand on top
-// the SS kernel above is shared-memory bound (ncu: tensor pipe 57 % active).  Here the stationary token tile lives in
-// TMEM as the A operand (TS-mode MMA): only the streamed W_out^T blocks cross shared memory (64 B/clk), and the whole
-// shared memory is a deeper TMA ring.  The epilogue warps load the A rows from global memory at the start of a segment
-// (one thread = one token row) and tcgen05.st them as packed bf16 pairs.
-//   TMEM columns: [0, 256) logits double buffer | A hi (HK/2) | A lo (HK/2)
-template <int KB, int NS, bool X3, bool BIAS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-ce_tc_forward_atm_kernel(const uint16_t* __restrict__ A_hi, const uint16_t* __restrict__ A_lo,
-                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const float* __restrict__ b_out, float* __restrict__ ws_m, float* __restrict__ ws_s,
-                         int64_t n_tokens, int v_begin, int v_end, int max_slots) {
-  constexpr int NP = X3 ? 2 : 1;
-  constexpr int HK = KB * KBLK;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sB = base;                                  // [NS][NP][TILE_B]
-  const uint32_t sBar = sB + NS * NP * TILE_B;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
-                 tmem_slot = bar_afree + 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
-  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
-  const Share sh(total, n_vtiles);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
-    ptx::mbar_init(bar_a, N_EPI_WARPS);
-    ptx::mbar_init(bar_afree, 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tmem_a = tmem_base + 2 * BN;                // hi: HK/2 columns, lo: the next HK/2
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------- TMA producer
-    if (lane == 0) ptx::prefetch_tmap(&tmB_hi);
-    Pipe p;
-    for (int64_t w = sh.w0; w < sh.w1; ++w) {
-      const int v0 = v_begin + sh.inner(w) * BN;
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-          const uint32_t dst = sB + p.stage * NP * TILE_B;
-          ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
-          if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
-        }
-        p.advance(NS);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
-    Pipe p;
-    int seg = -1, tc = 0;
-    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
-      if (sh.seg_first(w)) {
-        ++seg;
-        ptx::mbar_wait(bar_a, seg & 1);                      // the epilogue warps have stored the token tile
-        ptx::tc_fence_after_sync();
-      }
-      const int buf = tc & 1;
-      ptx::mbar_wait(bar_tempty + 8 * buf, ((tc >> 1) & 1) ^ 1);
-      ptx::tc_fence_after_sync();
-      const uint32_t d = tmem_base + buf * BN;
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t b = sB + p.stage * NP * TILE_B;
-        const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < KBLK / 16; ++k) {
-            const uint32_t a_hi = tmem_a + kb * (KBLK / 2) + k * 8, a_lo = a_hi + HK / 2;
-            const uint32_t acc = (kb == 0 && k == 0) ? 0u : 1u;
-            if (X3) {
-              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc, acc);
-              ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
-              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
-            } else {
-              ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, acc);
-            }
-          }
-        }
-        __syncwarp();
-        commit_elect(bar_empty + 8 * p.stage);
-        p.advance(NS);
-      }
-      commit_elect(bar_tfull + 8 * buf);
-      if (sh.seg_last(w)) commit_elect(bar_afree);
-    }
-  } else {
-    // ------------------------------------------------------------------------------------------- epilogue
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float m = -INFINITY, s = 0.f;
-    int tc = 0, seg = -1;
-    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
-      const int buf = tc & 1;
-      const int tt = sh.outer(w), vt = sh.inner(w);
-      if (sh.seg_first(w)) {
-        ++seg;
-        m = -INFINITY; s = 0.f;
-        if (seg > 0) {                                       // the previous segment's MMAs have consumed the old tile
-          ptx::mbar_wait(bar_afree, (seg - 1) & 1);
-          ptx::tc_fence_after_sync();
-        }
-        const int64_t n = (int64_t)tt * BM + row;
-        // this warp's half of the K range: HK/2 elements = HK/4 packed columns per part
-        row_to_tmem(tmem_a + lane_off + half * (HK / 4), A_hi, n, HK, half * (HK / 2), HK / 64, n < n_tokens);
-        if (X3)
-          row_to_tmem(tmem_a + lane_off + HK / 2 + half * (HK / 4), A_lo, n, HK, half * (HK / 2), HK / 64,
-                      n < n_tokens);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_a);
-      }
-      const int vc0 = v_begin + vt * BN + half * 64;
-      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
-      ptx::tc_fence_after_sync();
-      float z[64];
-      load_half_tile(tmem_base + lane_off + buf * BN + half * 64, z);
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-      if (BIAS || vc0 + 64 > v_end) {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int v = vc0 + j;
-          if (v < v_end) { if (BIAS) z[j] += __ldg(b_out + v); }
-          else z[j] = -INFINITY;
-        }
-      }
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        mx[0] = fmaxf(mx[0], z[j]); mx[1] = fmaxf(mx[1], z[j + 1]);
-        mx[2] = fmaxf(mx[2], z[j + 2]); mx[3] = fmaxf(mx[3], z[j + 3]);
-      }
-      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      if (cmax > -INFINITY) {
-        const float mn = fmaxf(m, cmax);
-        const float nb = -mn * LOG2E;
-        float add[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          add[0] += ptx::ex2_approx(fmaf(z[j], LOG2E, nb));
-          add[1] += ptx::ex2_approx(fmaf(z[j + 1], LOG2E, nb));
-          add[2] += ptx::ex2_approx(fmaf(z[j + 2], LOG2E, nb));
-          add[3] += ptx::ex2_approx(fmaf(z[j + 3], LOG2E, nb));
-        }
-        s = s * ptx::ex2_approx(fmaf(m, LOG2E, nb)) + ((add[0] + add[1]) + (add[2] + add[3]));
-        m = mn;
-      }
-      if (sh.seg_last(w)) {
-        const int64_t n = (int64_t)tt * BM + row;
-        if (n < n_tokens) {
-          const int slot = (int)blockIdx.x - cta_of((int64_t)tt * n_vtiles, total);
-          ws_m[((int64_t)slot * 2 + half) * n_tokens + n] = m;
-          ws_s[((int64_t)slot * 2 + half) * n_tokens + n] = s;
-          if (vt == n_vtiles - 1) {
-            for (int k = slot + 1; k < max_slots; ++k) {
-              ws_m[((int64_t)k * 2 + half) * n_tokens + n] = -INFINITY;
-              ws_s[((int64_t)k * 2 + half) * n_tokens + n] = 0.f;
-            }
-          }
-        }
-      }
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ================================================================================================================
 // K9 on the tensor cores: top-k next items per token row, never materialising the (N,V) logits.
 // Same MMA pipeline as ce_tc_forward_atm_kernel (token tile in TMEM, W_out^T streamed by TMA); the epilogue thread that
 // owns (row, 64-column half) keeps a private, descending top-k list in shared memory ([k][thread] -> conflict free)
@@ -896,8 +667,8 @@ ce_tc_topk_kernel(const uint16_t* __restrict__ A_hi, const uint16_t* __restrict_
 // one warp per row: k rounds of (value descending, id ascending) selection over the row's n_lists * k candidates
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const float* __restrict__ cand_v, const int32_t* __restrict__ cand_i, int n_lists,
-                  const float* __restrict__ mrow, const float* __restrict__ srow, int32_t* __restrict__ topk_ids,
-                  float* __restrict__ topk_p, int64_t n_rows, int k) {
+                  int64_t list_stride, const float* __restrict__ mrow, const float* __restrict__ srow,
+                  int32_t* __restrict__ topk_ids, float* __restrict__ topk_p, int64_t n_rows, int k) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (n >= n_rows) return;
@@ -910,7 +681,7 @@ topk_merge_kernel(const float* __restrict__ cand_v, const int32_t* __restrict__ 
     const int x = c * 32 + lane;
     v[c] = -INFINITY; id[c] = 0x7fffffff;
     if (x < total) {
-      const int64_t o = ((int64_t)(x / k) * n_rows + n) * k + (x % k);
+      const int64_t o = (int64_t)(x / k) * list_stride + n * k + (x % k);
       v[c] = cand_v[o]; id[c] = cand_i[o];
     }
   }
@@ -966,487 +737,6 @@ __device__ __forceinline__ void flush_acc_red(uint32_t taddr, int ncols, float* 
 }
 
 // ================================================================================================================
-// backward, token-stationary: dh[n,:] += sum_v dlogit[n,v] * W_out[:,v]
-//   outer = token tile (A resident per segment), inner = item tile.  Per item tile:  S = A.Bt^T (TMEM, double
-//   buffered) -> epilogue writes dS (bf16 hi/lo, rows = tokens) to shared memory -> dH (TMEM accumulator of the
-//   segment) += dS . W^T with W = W_out [Hk, Vp] bf16 hi/lo (box 64 x Hk).  At the end of a segment the accumulator is
-//   red-added into the pre-zeroed dh.  The MMA stream is software pipelined across tiles AND segments:
-//   S(w+1) is issued before dH(w).  Needs Hk <= 128 (shared-memory budget).
-template <int KB, bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-ce_tc_backward_dh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                         const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
-                         const float* __restrict__ srow, const float* __restrict__ coef,
-                         const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
-                         float* __restrict__ dh, int64_t n_tokens, int H, int v_begin, int v_end) {
-  constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = X3 ? 5 : 10;                         // 32 KB (x3) / 16 KB stages next to the resident A tile
-  constexpr int HK = KB * KBLK;
-  constexpr int NJ = BN / KBLK;                             // 64-item blocks per tile (K blocks of the dH GEMM)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;                                  // [NP][KB][TILE_B]        hout tile (resident)
-  const uint32_t sB = sA + NP * KB * TILE_B;                 // [NS][NP][TILE_B]        Bt / W blocks
-  const uint32_t sBar = sB + NS * NP * TILE_B;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
-                 bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
-                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
-  const int64_t total = ((n_tokens + BM - 1) / BM) * n_vtiles;
-  const Share sh(total, n_vtiles);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
-    ptx::mbar_init(bar_a, 1);
-    ptx::mbar_init(bar_afree, 1);
-    ptx::mbar_init(bar_dfull, N_EPI_WARPS);
-    ptx::mbar_init(bar_dempty, 1);
-    ptx::mbar_init(bar_hfull, 1);
-    ptx::mbar_init(bar_hempty, N_EPI_WARPS);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // TMEM columns: [0,256) logits double buffer | [256,384) dH accumulator | [384,448) dS hi | [448,512) dS lo.
-  // dS never touches shared memory: the epilogue packs it to bf16 pairs and tcgen05.st's it as the A operand of the
-  // second GEMM (128 token lanes x 128 items = 64 packed columns per part), halving that GEMM's shared-memory reads.
-  const uint32_t tmem_dh = tmem_base + 2 * BN;
-  const uint32_t tmem_ds = tmem_base + 2 * BN + 128;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------- TMA producer
-    // stage order must equal the MMA warp's consumption order: Bt(w0), then per item w: Bt(w+1), W(w)
-    if (sh.w0 < sh.w1) {
-      if (lane == 0) { ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmW_hi); }
-      Pipe p;
-      int seg = 0;
-      auto load_s_operands = [&](int64_t w) {
-        if (sh.seg_first(w)) {
-          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
-          const int row0 = sh.outer(w) * BM;
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-            for (int kb = 0; kb < KB; ++kb) {
-              ptx::tma_load_2d(sA + kb * TILE_B, &tmA_hi, bar_a, kb * KBLK, row0);
-              if (X3) ptx::tma_load_2d(sA + (KB + kb) * TILE_B, &tmA_lo, bar_a, kb * KBLK, row0);
-            }
-          }
-          ++seg;
-        }
-        const int v0 = v_begin + sh.inner(w) * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-            const uint32_t dst = sB + p.stage * NP * TILE_B;
-            ptx::tma_load_2d(dst, &tmB_hi, bar_full + 8 * p.stage, kb * KBLK, v0);
-            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmB_lo, bar_full + 8 * p.stage, kb * KBLK, v0);
-          }
-          p.advance(NS);
-        }
-      };
-      auto load_w = [&](int64_t w) {
-        const int v0 = v_begin + sh.inner(w) * BN;
-        for (int j = 0; j < NJ; ++j) {
-          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * HK * 128);
-            const uint32_t dst = sB + p.stage * NP * TILE_B;
-            ptx::tma_load_2d(dst, &tmW_hi, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
-            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmW_lo, bar_full + 8 * p.stage, v0 + j * KBLK, 0);
-          }
-          p.advance(NS);
-        }
-      };
-      load_s_operands(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) load_s_operands(w + 1);
-        load_w(w);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------- MMA issuer
-    if (sh.w0 < sh.w1) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
-      constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(BM, HK);
-      Pipe p;
-      int seg_s = -1, tc_s = 0;      // S stream: segment index, running tile count
-      int seg_d = -1, tc_d = 0;      // dH stream
-      auto issue_s = [&](int64_t w) {
-        if (sh.seg_first(w)) {
-          ++seg_s;
-          ptx::mbar_wait(bar_a, seg_s & 1);
-          ptx::tc_fence_after_sync();
-        }
-        const int buf = tc_s & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s >> 1) & 1) ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_base + buf * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t b = sB + p.stage * NP * TILE_B;
-          mma_kblock<X3>(d, sA + kb * TILE_B, sA + (KB + kb) * TILE_B, b, b + TILE_B, idesc_s, kb == 0);
-          commit_elect(bar_empty + 8 * p.stage);
-          p.advance(NS);
-        }
-        commit_elect(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) commit_elect(bar_afree);   // sA may be reloaded once these MMAs have completed
-        ++tc_s;
-      };
-      issue_s(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) issue_s(w + 1);
-        const bool first = sh.seg_first(w);
-        if (first) {
-          if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
-            ptx::mbar_wait(bar_hempty, seg_d & 1);
-            ptx::tc_fence_after_sync();
-          }
-          ++seg_d;
-        }
-        ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in shared memory
-        ptx::tc_fence_after_sync();
-        for (int j = 0; j < NJ; ++j) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t b = sB + p.stage * NP * TILE_B;
-          const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
-          if (ptx::elect_one()) {
-#pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k) {
-              const uint32_t a_hi = tmem_ds + j * (KBLK / 2) + k * 8, a_lo = a_hi + BN / 2;
-              const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
-              if (X3) {
-                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc_h, acc);
-                ptx::umma_bf16_ts(tmem_dh, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, 1u);
-                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, 1u);
-              } else {
-                ptx::umma_bf16_ts(tmem_dh, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc_h, acc);
-              }
-            }
-          }
-          __syncwarp();
-          commit_elect(bar_empty + 8 * p.stage);
-          p.advance(NS);
-        }
-        commit_elect(bar_dempty);                       // dS buffer may be overwritten
-        if (sh.seg_last(w)) commit_elect(bar_hfull);
-        ++tc_d;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------------------------------- epilogue
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
-    const float inv = inv_nvalid[0];
-    RowTerms rt;
-    int tc = 0, seg = -1;
-    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
-      const int buf = tc & 1;
-      const int64_t n = (int64_t)sh.outer(w) * BM + row;
-      if (sh.seg_first(w)) { ++seg; rt = load_row_terms(n, n_tokens, mrow, srow, coef, tgt, inv); }
-      const int vc0 = v_begin + sh.inner(w) * BN + half * 64;
-      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
-      ptx::tc_fence_after_sync();
-      float z[64];
-      load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-      dlogit_half_tile(z, rt, vc0, v_end);
-      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);    // previous tile's dH MMAs are done with the dS operand
-      ptx::tc_fence_after_sync();
-      {
-        // this thread's 64 dlogits -> 32 packed bf16 pairs (hi) and 32 (lo) at columns [half*32, half*32+32)
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x0 = z[2 * e], x1 = z[2 * e + 1];
-          const __nv_bfloat162 hv = __floats2bfloat162_rn(x0, x1);
-          hi[e] = *reinterpret_cast<const uint32_t*>(&hv);
-          if (X3) lo[e] = pack_bf16x2(x0 - __low2float(hv), x1 - __high2float(hv));
-        }
-        const uint32_t dst = tmem_ds + ((uint32_t)(q * 32) << 16) + half * 32;
-        ptx::tmem_st_32x32(dst, hi);
-        if (X3) ptx::tmem_st_32x32(dst + BN / 2, lo);
-        ptx::tmem_st_wait();
-      }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_dfull);
-      if (sh.seg_last(w)) {
-        // flush the segment's dH accumulator: this warp owns HK/2 columns of its 32 rows
-        ptx::mbar_wait(bar_hfull, seg & 1);
-        ptx::tc_fence_after_sync();
-        const int h0 = half * (HK / 2);
-        const bool row_ok = n < n_tokens;
-        const bool vec_ok = (H & 3) == 0;
-        flush_acc_red(tmem_dh + ((uint32_t)(q * 32) << 16) + h0, HK / 2, dh + n * H + h0, H - h0, row_ok, vec_ok,
-                      hscale ? hscale + n * H + h0 : nullptr);
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_hempty);
-      }
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ================================================================================================================
-// backward, item-stationary: dW_out[:, v] += sum_n hs[n,:] * dlogit[n,v]
-//   outer = item tile (Bt resident per segment), inner = token tile.  Per token tile:  S = A.Bt^T -> epilogue writes
-//   dS row-wise (rows = tokens, like the dH kernel) -> dW (TMEM [128 x 128 items]) += Ht . dS with Ht = hs^T [Hk, Np]
-//   bf16 hi/lo (K-major, box 64 tokens x 128 rows) and dS read back as an MN-major B operand (K = tokens runs down
-//   the rows).  Segment results leave through red.global.add.v4.f32 into the pre-zeroed dW_out.
-template <int KB, bool X3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-ce_tc_backward_dw_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                         const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo,
-                         const int32_t* __restrict__ tgt, const float* __restrict__ mrow,
-                         const float* __restrict__ srow, const float* __restrict__ coef,
-                         const float* __restrict__ inv_nvalid, float* __restrict__ dW, int64_t n_tokens, int H,
-                         int v_begin, int v_end, int ldw) {
-  constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = X3 ? 3 : 6;
-  constexpr int NJ = BM / KBLK;                             // 64-token blocks per tile (K blocks of the dW GEMM)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sBt = base;                                 // [NP][KB][TILE_B]       W_out^T tile (resident)
-  const uint32_t sD = sBt + NP * KB * TILE_B;                // [NP][NJ][TILE_B]       dS tile
-  const uint32_t sB = sD + NP * NJ * TILE_B;                 // [NS][NP][TILE_B]       A / Ht blocks
-  const uint32_t sBar = sB + NS * NP * TILE_B;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 8 * NS, bar_tfull = sBar + 16 * NS,
-                 bar_tempty = bar_tfull + 16, bar_a = bar_tempty + 16, bar_afree = bar_a + 8,
-                 bar_dfull = bar_afree + 8, bar_dempty = bar_dfull + 8, bar_hfull = bar_dempty + 8,
-                 bar_hempty = bar_hfull + 8, tmem_slot = bar_hempty + 8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
-  const int n_ttiles = (int)((n_tokens + BM - 1) / BM);
-  const int64_t total = (int64_t)n_vtiles * n_ttiles;
-  const Share sh(total, n_ttiles);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { ptx::mbar_init(bar_full + 8 * i, 1); ptx::mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_tfull + 8 * i, 1); ptx::mbar_init(bar_tempty + 8 * i, N_EPI_WARPS); }
-    ptx::mbar_init(bar_a, 1);
-    ptx::mbar_init(bar_afree, 1);
-    ptx::mbar_init(bar_dfull, N_EPI_WARPS);
-    ptx::mbar_init(bar_dempty, 1);
-    ptx::mbar_init(bar_hfull, 1);
-    ptx::mbar_init(bar_hempty, N_EPI_WARPS);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tmem_dw = tmem_base + 2 * BN;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------------------------------- TMA producer
-    if (sh.w0 < sh.w1) {
-      if (lane == 0) { ptx::prefetch_tmap(&tmA_hi); ptx::prefetch_tmap(&tmB_hi); ptx::prefetch_tmap(&tmT_hi); }
-      Pipe p;
-      int seg = 0;
-      auto load_s_operands = [&](int64_t w) {
-        if (sh.seg_first(w)) {
-          if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
-          const int v0 = v_begin + sh.outer(w) * BN;
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
-            for (int kb = 0; kb < KB; ++kb) {
-              ptx::tma_load_2d(sBt + kb * TILE_B, &tmB_hi, bar_a, kb * KBLK, v0);
-              if (X3) ptx::tma_load_2d(sBt + (KB + kb) * TILE_B, &tmB_lo, bar_a, kb * KBLK, v0);
-            }
-          }
-          ++seg;
-        }
-        const int r0 = sh.inner(w) * BM;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);
-            const uint32_t dst = sB + p.stage * NP * TILE_B;
-            ptx::tma_load_2d(dst, &tmA_hi, bar_full + 8 * p.stage, kb * KBLK, r0);
-            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmA_lo, bar_full + 8 * p.stage, kb * KBLK, r0);
-          }
-          p.advance(NS);
-        }
-      };
-      auto load_t = [&](int64_t w) {
-        const int r0 = sh.inner(w) * BM;
-        for (int j = 0; j < NJ; ++j) {
-          ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * p.stage, NP * TILE_B);   // box = 128 rows (rows >= Hk are zero)
-            const uint32_t dst = sB + p.stage * NP * TILE_B;
-            ptx::tma_load_2d(dst, &tmT_hi, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
-            if (X3) ptx::tma_load_2d(dst + TILE_B, &tmT_lo, bar_full + 8 * p.stage, r0 + j * KBLK, 0);
-          }
-          p.advance(NS);
-        }
-      };
-      load_s_operands(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) load_s_operands(w + 1);
-        load_t(w);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------- MMA issuer
-    if (sh.w0 < sh.w1) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(BM, BN);
-      // dW GEMM: M = hidden (padded to 128), N = items, K = tokens.  A = Ht block (K-major, from TMA); B = dS exactly
-      // as the epilogue wrote it (rows = tokens = K, 64 items per 128-byte row) read as an MN-major operand.
-      constexpr uint32_t idesc_w = ptx::umma_idesc_bf16_bmn(128, BN);
-      Pipe p;
-      int seg_s = -1, tc_s = 0, seg_d = -1, tc_d = 0;
-      auto issue_s = [&](int64_t w) {
-        if (sh.seg_first(w)) {
-          ++seg_s;
-          ptx::mbar_wait(bar_a, seg_s & 1);
-          ptx::tc_fence_after_sync();
-        }
-        const int buf = tc_s & 1;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s >> 1) & 1) ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_base + buf * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t a = sB + p.stage * NP * TILE_B;
-          mma_kblock<X3>(d, a, a + TILE_B, sBt + kb * TILE_B, sBt + (KB + kb) * TILE_B, idesc_s, kb == 0);
-          commit_elect(bar_empty + 8 * p.stage);
-          p.advance(NS);
-        }
-        commit_elect(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) commit_elect(bar_afree);
-        ++tc_s;
-      };
-      issue_s(sh.w0);
-      for (int64_t w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) issue_s(w + 1);
-        const bool first = sh.seg_first(w);
-        if (first) {
-          if (seg_d >= 0) {
-            ptx::mbar_wait(bar_hempty, seg_d & 1);
-            ptx::tc_fence_after_sync();
-          }
-          ++seg_d;
-        }
-        ptx::mbar_wait(bar_dfull, tc_d & 1);
-        ptx::tc_fence_after_sync();
-        for (int j = 0; j < NJ; ++j) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t a = sB + p.stage * NP * TILE_B;     // Ht block: rows = hidden, K = 64 tokens
-          const uint64_t da_hi = ptx::umma_desc_k_sw128(a), da_lo = ptx::umma_desc_k_sw128(a + TILE_B);
-          // 16 tokens = 16 rows of 128 B (2048 B) further down the dS image per K step; the two 64-item blocks of the
-          // tile are TILE_B apart (LBO)
-          const uint64_t db_hi0 = ptx::umma_desc_mn_sw128(sD + (uint32_t)(j * KBLK) * 128, TILE_B);
-          const uint64_t db_lo0 = ptx::umma_desc_mn_sw128(sD + NJ * TILE_B + (uint32_t)(j * KBLK) * 128, TILE_B);
-          if (ptx::elect_one()) {
-#pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k) {
-              const uint64_t db_hi = db_hi0 + (uint64_t)((k * 16 * 128) >> 4);
-              const uint64_t db_lo = db_lo0 + (uint64_t)((k * 16 * 128) >> 4);
-              const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
-              if (X3) {
-                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_lo, idesc_w, acc);
-                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_lo, k * 16), db_hi, idesc_w, 1u);
-                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, 1u);
-              } else {
-                ptx::umma_bf16(tmem_dw, ptx::umma_desc_advance_k(da_hi, k * 16), db_hi, idesc_w, acc);
-              }
-            }
-          }
-          __syncwarp();
-          commit_elect(bar_empty + 8 * p.stage);
-          p.advance(NS);
-        }
-        commit_elect(bar_dempty);
-        if (sh.seg_last(w)) commit_elect(bar_hfull);
-        ++tc_d;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------------------------------- epilogue
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
-    uint8_t* sD_gen = smem_raw + (sD - ptx::smem_u32(smem_raw));
-    const float inv = inv_nvalid[0];
-    int tc = 0, seg = -1;
-    RowTerms rt_next;
-    if (sh.w0 < sh.w1) rt_next = load_row_terms((int64_t)sh.inner(sh.w0) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
-    for (int64_t w = sh.w0; w < sh.w1; ++w, ++tc) {
-      const int buf = tc & 1;
-      if (sh.seg_first(w)) ++seg;
-      const RowTerms rt = rt_next;
-      if (w + 1 < sh.w1)                            // prefetch the next tile's row terms behind this tile's math
-        rt_next = load_row_terms((int64_t)sh.inner(w + 1) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
-      const int vc0 = v_begin + sh.outer(w) * BN + half * 64;
-      ptx::mbar_wait(bar_tfull + 8 * buf, (tc >> 1) & 1);
-      ptx::tc_fence_after_sync();
-      float z[64];
-      load_half_tile(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * 64, z);
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
-      dlogit_half_tile(z, rt, vc0, v_end);
-      ptx::mbar_wait(bar_dempty, (tc & 1) ^ 1);
-      store_dlogit_row<X3>(sD_gen, z, row, half, NJ * TILE_B);   // rows = tokens; consumed MN-major by the dW GEMM
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_dfull);
-      if (sh.seg_last(w)) {
-        // flush the segment's dW accumulator: rows = hidden unit, this warp's 64 item columns
-        ptx::mbar_wait(bar_hfull, seg & 1);
-        ptx::tc_fence_after_sync();
-        const int h = row;
-        const bool vec_ok = (ldw & 3) == 0 && (v_begin & 3) == 0;
-        flush_acc_red(tmem_dw + ((uint32_t)(q * 32) << 16) + half * 64, 64, dW + (size_t)h * ldw + vc0, v_end - vc0,
-                      h < H, vec_ok, nullptr);
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_hempty);
-      }
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ================================================================================================================
 // backward for wide hidden layers (Hk up to 256), ONE kernel template for both gradients.
 //   P = the stationary side (128 rows per tile), Q = the streamed side (128 rows per tile):
 //     ITEM_ST = false: P = tokens, Q = items   ->  out = dh     [n, h] += sum_v dS[n, v] . W_out[h, v]
@@ -1471,10 +761,9 @@ struct TsCfg {
   // GEMM), so that every barrier has a single waiting warp in lock-step with it; a consumer tracks the parity of ITS
   // barrier per slot in a bit mask.  (With one barrier per slot the two warps alias on the phase parity: the warp that
   // runs ahead takes a completion that belonged to the other warp for its own.)
-  static constexpr bool TW = true;
   static constexpr int NS = (KB <= 2) ? (KB + 2 * NC) : (NS_RAW > 8 ? 8 : NS_RAW);   // Hk <= 128: ring length = period
-  static constexpr int THREADS = TW ? 352 : 320;
-  static constexpr int EPI0 = TW ? 3 : 2;                   // first epilogue warp
+  static constexpr int THREADS = 352;
+  static constexpr int EPI0 = 3;                            // first epilogue warp
   static constexpr int ACC_COLS = NC * 128;
   static constexpr int SBUF = (2 * BN + ACC_COLS + BN <= 512) ? 2 : 1;
   static constexpr uint32_t TERMS_B = 128 * 16;             // per-token terms of one streamed tile (ITEM_ST)
@@ -1583,7 +872,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           for (int c = 0; c < NC; ++c) {
             ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
             if (ptx::elect_one()) {
-              const uint32_t fb = (C::TW ? bar_fullz : bar_full) + 8 * p.stage;
+              const uint32_t fb = bar_fullz + 8 * p.stage;
               ptx::mbar_arrive_expect_tx(fb, NP * TILE_B);   // rows >= Hk arrive as zeros
               const uint32_t dst = sB + p.stage * NP * TILE_B;
               ptx::tma_load_2d(dst, &tmZ_hi, fb, q0 + j * KBLK, c * 128);
@@ -1598,78 +887,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         load_z(w);
       }
     }
-  } else if (warp == 1 && !C::TW) {
-    // ------------------------------------------------------------------------------------------- MMA issuer
-    if (sh.w0 < sh.w1) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
-      Pipe p;
-      int seg_s = -1, tc_s = 0, seg_d = -1, tc_d = 0;
-      auto issue_s = [&](int w) {
-        if (sh.seg_first(w)) {
-          ++seg_s;
-          ptx::mbar_wait(bar_a, seg_s & 1);
-          ptx::tc_fence_after_sync();
-        }
-        const int buf = tc_s % SBUF;
-        ptx::mbar_wait(bar_tempty + 8 * buf, ((tc_s / SBUF) & 1) ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_base + buf * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t b = sB + p.stage * NP * TILE_B;
-          mma_kblock<X3>(d, sX + kb * TILE_B, sX + (KB + kb) * TILE_B, b, b + TILE_B, idesc, kb == 0);
-          commit_elect(bar_empty + 8 * p.stage);
-          p.advance(NS);
-        }
-        commit_elect(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) commit_elect(bar_afree);
-        ++tc_s;
-      };
-      issue_s(sh.w0);
-      for (int w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) issue_s(w + 1);
-        const bool first = sh.seg_first(w);
-        if (first) {
-          if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
-            ptx::mbar_wait(bar_hempty, seg_d & 1);
-            ptx::tc_fence_after_sync();
-          }
-          ++seg_d;
-        }
-        ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in tensor memory
-        ptx::tc_fence_after_sync();
-        for (int j = 0; j < NJ; ++j)
-          for (int c = 0; c < NC; ++c) {
-            ptx::mbar_wait(bar_full + 8 * p.stage, p.phase);
-            ptx::tc_fence_after_sync();
-            const uint32_t b = sB + p.stage * NP * TILE_B;
-            const uint64_t db_hi = ptx::umma_desc_k_sw128(b), db_lo = ptx::umma_desc_k_sw128(b + TILE_B);
-            const uint32_t d = tmem_acc + c * 128;
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k) {
-                const uint32_t a_hi = tmem_ds + j * (KBLK / 2) + k * 8, a_lo = a_hi + BN / 2;
-                const uint32_t acc = (first && j == 0 && k == 0) ? 0u : 1u;
-                if (X3) {
-                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_lo, k * 16), idesc, acc);
-                  ptx::umma_bf16_ts(d, a_lo, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
-                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, 1u);
-                } else {
-                  ptx::umma_bf16_ts(d, a_hi, ptx::umma_desc_advance_k(db_hi, k * 16), idesc, acc);
-                }
-              }
-            }
-            __syncwarp();
-            commit_elect(bar_empty + 8 * p.stage);
-            p.advance(NS);
-          }
-        commit_elect(bar_dempty);                           // the dS columns may be overwritten
-        if (sh.seg_last(w)) commit_elect(bar_hfull);
-        ++tc_d;
-      }
-    }
-  } else if (warp == 1 && C::TW) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------- MMA issuer, logits
     // ring positions: S(0) | S(1) G(0) | S(2) G(1) | ... | S(n-1) G(n-2) | G(n-1)   (KB stages per S, NZ per G)
     if (sh.w0 < sh.w1) {
@@ -1703,7 +921,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           for (int i = 0; i < NZ; ++i) p.advance(NS);
       }
     }
-  } else if (warp == 2 && C::TW) {
+  } else if (warp == 2) {
     // ------------------------------------------------------------------------------------------- MMA issuer, gradient
     if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
@@ -1761,7 +979,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     const int half = (warp - C::EPI0) >> 2;
     const int row = q * 32 + lane;
     const int e = threadIdx.x - 32 * C::EPI0;                // 0..255 among the epilogue threads
-    const float inv = inv_nvalid[0];
+    const float inv = inv_nvalid ? inv_nvalid[0] : 1.0f;    // NULL: un-normalised gradients (the optimiser divides)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float4* sT_gen = reinterpret_cast<float4*>(smem_raw + (sT - ptx::smem_u32(smem_raw)));
     RowTerms rt;                                             // !ITEM_ST: this thread's token row; ITEM_ST: prefetch
@@ -1967,23 +1185,6 @@ int launch_ts(int KB, bool x3, bool item_st, int grid, const CUtensorMap& x_hi, 
 }
 
 template <int KB, bool X3, bool BIAS>
-int launch_fwd_atm(const uint16_t* A_hi, const uint16_t* A_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                   const float* b_out, float* ws_m, float* ws_s, int64_t n_tokens, int v_begin, int v_end,
-                   cudaStream_t st) {
-  constexpr int NP = X3 ? 2 : 1;
-  constexpr int NS = X3 ? 6 : 12;
-  const size_t smem = 1024 + (size_t)NS * NP * TILE_B + 256;
-  auto k = ce_tc_forward_atm_kernel<KB, NS, X3, BIAS>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return -(int)e;
-  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
-  k<<<persistent_grid(total), TC_THREADS, smem, st>>>(A_hi, A_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin,
-                                                      v_end, forward_slots(n_tokens, v_begin, v_end));
-  SEQREC_CHECK_LAUNCH();
-  return 0;
-}
-
-template <int KB, bool X3, bool BIAS>
 int launch_topk(const uint16_t* A_hi, const uint16_t* A_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                 const float* b_out, float* cand_v, int32_t* cand_i, int64_t n_rows, int V, int k, cudaStream_t st) {
   constexpr int NP = X3 ? 2 : 1;
@@ -2032,7 +1233,21 @@ extern "C" int seqrec_topk_tc(const uint16_t* A_hi, const uint16_t* A_lo, const 
 #undef TK2
 #undef TK
   if (rc) return rc;
-  topk_merge_kernel<<<ceil_div(n_rows * 32, 256), 256, 0, st>>>(ws_v, ws_i, n_lists, m, s, topk_ids, topk_p, n_rows, k);
+  topk_merge_kernel<<<ceil_div(n_rows * 32, 256), 256, 0, st>>>(ws_v, ws_i, n_lists, n_rows * k, m, s, topk_ids, topk_p,
+                                                                n_rows, k);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// merge of n_lists candidate lists per row (vocabulary-parallel ranking: one list of k (probability, item id) pairs per
+// item shard): value descending, lower item id first on ties -- the same selection the single-GPU ranking ends with
+extern "C" int seqrec_topk_merge(const float* cand_v, const int32_t* cand_i, int n_lists, int64_t list_stride,
+                                 int32_t* topk_ids, float* topk_p, int64_t n_rows, int k, void* stream) {
+  SEQREC_ARG(cand_v && cand_i && topk_ids && n_rows > 0 && k >= 1 && n_lists >= 1, 1);
+  SEQREC_ARG(n_lists * k <= 384 && list_stride >= n_rows * k, 2);
+  topk_merge_kernel<<<ceil_div(n_rows * 32, 256), 256, 0, as_stream(stream)>>>(cand_v, cand_i, n_lists, list_stride,
+                                                                               nullptr, nullptr, topk_ids, topk_p,
+                                                                               n_rows, k);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -2045,12 +1260,6 @@ extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const
                                                                                   n_tokens, H, ldw);
   SEQREC_CHECK_LAUNCH();
   return 0;
-}
-
-/* diagnostics only (not in the public header): device buffer of 64 x 8 clock64() stamps written by CTA 0 */
-extern "C" int seqrec_ce_tc_debug_buffer(long long* dev_buf) {
-  cudaError_t e = cudaMemcpyToSymbol(g_ce_dbg, &dev_buf, sizeof(dev_buf));
-  return e == cudaSuccess ? 0 : -(int)e;
 }
 
 extern "C" int seqrec_ce_tc_partials(int64_t n_tokens, int v_begin, int v_end) {
@@ -2071,27 +1280,6 @@ extern "C" int seqrec_ce_tc_forward(const uint16_t* A_hi, const uint16_t* A_lo, 
   if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
   cudaStream_t st = as_stream(stream);
-  // SEQREC_CE_FWD_ATM=1 selects the variant that keeps the token tile in tensor memory (TS-mode MMA).  Measured equal
-  // to the SS-mode kernel on B200 (cfg2 0.118 ms, cfg3 5.7 ms either way: the forward is bound by its exp2 epilogue,
-  // not by shared-memory bandwidth), so the SS kernel stays the default.
-  static const bool atm = [] { const char* e = getenv("SEQREC_CE_FWD_ATM"); return e && e[0] == '1'; }();
-  if (atm) {
-#define ATM2(KB, X3V, BV) \
-  return launch_fwd_atm<KB, X3V, BV>(A_hi, x3 ? A_lo : A_hi, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, st)
-#define ATM(KB)                                                                      \
-  {                                                                                  \
-    if (x3) { if (b_out) ATM2(KB, true, true); else ATM2(KB, true, false); }         \
-    else    { if (b_out) ATM2(KB, false, true); else ATM2(KB, false, false); }       \
-  }
-    switch (Hk / KBLK) {
-      case 1: ATM(1)
-      case 2: ATM(2)
-      case 3: ATM(3)
-      default: ATM(4)
-    }
-#undef ATM2
-#undef ATM
-  }
 #define FWD2(KB, NS, X3V, BV) \
   return launch_fwd<KB, NS, X3V, BV>(a_hi, a_lo, b_hi, b_lo, b_out, ws_m, ws_s, n_tokens, v_begin, v_end, st)
 #define FWD(KB, NS)                                                                      \
@@ -2126,75 +1314,26 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
   if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
   if ((rc = make_tmap(&b_hi, Bt_hi, V, Hk, Hk, BN))) return rc;
   if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
-  const int NP = x3 ? 2 : 1;
   const int KB = Hk / KBLK;
-  // The unified kernel with dS in tensor memory serves every width (for Hk <= 128 with two MMA-issuing warps: cfg2
-  // logits backward 0.292 -> 0.272 ms).  SEQREC_CE_BWD_TS=0 routes Hk <= 128 to the two older kernels below (dH with dS
-  // in TMEM, dW with dS in shared memory), so the implementations can be compared on the same problem.
-  static const bool legacy = [] { const char* e = getenv("SEQREC_CE_BWD_TS"); return e && e[0] == '0'; }();
-  if (KB > 2 || !legacy || b_out) {                        // (the legacy kernels have no output-bias path)
-    const int64_t total_ts = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
-    const int grid_ts = persistent_grid(total_ts);
-    if (dh) {
-      if (!accumulate_dh) {
-        cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)n_tokens * H, st);
-        if (e != cudaSuccess) return -(int)e;
-      }
-      if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
-      if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
-      if ((rc = launch_ts(KB, x3 != 0, false, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
-                          hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, st)))
-        return rc;
-    }
-    if (dW_out) {
-      if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
-      if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
-      if ((rc = launch_ts(KB, x3 != 0, true, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
-                          nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)))
-        return rc;
-    }
-    return 0;
-  }
-  const size_t smem = 1024 + (size_t)NP * KB * TILE_B + (size_t)NP * 2 * TILE_B + (size_t)(x3 ? 3 : 6) * NP * TILE_B + 256;
-  const size_t smem_dh = 1024 + (size_t)NP * KB * TILE_B + (size_t)(x3 ? 5 : 10) * NP * TILE_B + 256;
-  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
-  const int grid = persistent_grid(total);
+  const int64_t total_ts = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+  const int grid_ts = persistent_grid(total_ts);
   if (dh) {
-    // every segment red-adds its partial dH, so the destination starts from zero unless the caller accumulates
     if (!accumulate_dh) {
       cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)n_tokens * H, st);
       if (e != cudaSuccess) return -(int)e;
     }
-    if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, Hk))) return rc;
-    if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, Hk))) return rc;
-#define DH(KBV, X3V)                                                                                          \
-  {                                                                                                           \
-    auto k = ce_tc_backward_dh_kernel<KBV, X3V>;                                                              \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dh);       \
-    if (e != cudaSuccess) return -(int)e;                                                                     \
-    k<<<grid, TC_THREADS, smem_dh, st>>>(a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid, hscale, \
-                                      dh, n_tokens, H, v_begin, v_end);                                       \
-  }
-    if (KB == 1) { if (x3) DH(1, true) else DH(1, false) }
-    else         { if (x3) DH(2, true) else DH(2, false) }
-#undef DH
-    SEQREC_CHECK_LAUNCH();
+    if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
+    if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
+    if ((rc = launch_ts(KB, x3 != 0, false, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
+                        hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, st)))
+      return rc;
   }
   if (dW_out) {
     if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
-#define DW(KBV, X3V)                                                                                          \
-  {                                                                                                           \
-    auto k = ce_tc_backward_dw_kernel<KBV, X3V>;                                                              \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    if (e != cudaSuccess) return -(int)e;                                                                     \
-    k<<<grid, TC_THREADS, smem, st>>>(a_hi, a_lo, b_hi, b_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,        \
-                                      dW_out, n_tokens, H, v_begin, v_end, ldw);                              \
-  }
-    if (KB == 1) { if (x3) DW(1, true) else DW(1, false) }
-    else         { if (x3) DW(2, true) else DW(2, false) }
-#undef DW
-    SEQREC_CHECK_LAUNCH();
+    if ((rc = launch_ts(KB, x3 != 0, true, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
+                        nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)))
+      return rc;
   }
   return 0;
 }

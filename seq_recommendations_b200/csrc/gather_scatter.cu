@@ -9,7 +9,8 @@
 // (B,T) -> (T,B) ids/targets/mask; pad = negative id.  Also counts valid tokens.
 __global__ void format_batch_kernel(const int32_t* __restrict__ ids_bt, const int32_t* __restrict__ tgt_bt,
                                     int32_t* __restrict__ ids_tb, int32_t* __restrict__ tgt_tb,
-                                    uint8_t* __restrict__ mask_tb, int32_t* __restrict__ n_valid, int B, int T) {
+                                    uint8_t* __restrict__ mask_tb, int32_t* __restrict__ n_valid, int B, int T,
+                                    int n_in, int n_items, int32_t* __restrict__ err) {
   __shared__ int32_t tile_i[32][33];
   __shared__ int32_t tile_t[32][33];
   const int b0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -30,7 +31,12 @@ __global__ void format_batch_kernel(const int32_t* __restrict__ ids_bt, const in
     if (t < T && b < B) {
       int32_t vi = tile_i[threadIdx.x][r];
       int32_t vt = tile_t[threadIdx.x][r];
+      // range check (the reference raises IndexError in np_utils.to_categorical for such an id): an id >= n_in or a
+      // target >= n_items never reaches a kernel that would index a table with it -- the token becomes a pad and the
+      // error flag is raised (bit 0: input id, bit 1: target), which the host turns into an exception
+      if (vi >= n_in) { vi = -1; if (err) atomicOr(err, 1); }
       bool ok = vi >= 0;
+      if (ok && tgt_tb && (vt >= n_items || vt < 0)) { ok = false; vi = -1; if (err) atomicOr(err, 2); }
       ids_tb[(int64_t)t * B + b] = vi;
       if (tgt_tb) tgt_tb[(int64_t)t * B + b] = ok ? vt : -1;
       mask_tb[(int64_t)t * B + b] = ok ? 1 : 0;
@@ -42,10 +48,12 @@ __global__ void format_batch_kernel(const int32_t* __restrict__ ids_bt, const in
 }
 
 extern "C" int seqrec_format_batch(const int32_t* ids_bt, const int32_t* tgt_bt, int32_t* ids_tb, int32_t* tgt_tb,
-                                   uint8_t* mask_tb, int32_t* n_valid, int B, int T, void* stream) {
-  SEQREC_ARG(B > 0 && T > 0, 1);
+                                   uint8_t* mask_tb, int32_t* n_valid, int B, int T, int n_in, int n_items,
+                                   int32_t* err, void* stream) {
+  SEQREC_ARG(B > 0 && T > 0 && n_in > 0 && n_items > 0, 1);
   dim3 grid(ceil_div(T, 32), ceil_div(B, 32)), block(32, 8);
-  format_batch_kernel<<<grid, block, 0, as_stream(stream)>>>(ids_bt, tgt_bt, ids_tb, tgt_tb, mask_tb, n_valid, B, T);
+  format_batch_kernel<<<grid, block, 0, as_stream(stream)>>>(ids_bt, tgt_bt, ids_tb, tgt_tb, mask_tb, n_valid, B, T,
+                                                             n_in, n_items, err);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }

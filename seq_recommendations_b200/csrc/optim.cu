@@ -61,16 +61,20 @@ sumsq_rows_kernel(const float* __restrict__ g, const int32_t* __restrict__ rows,
   }
 }
 
-__device__ __forceinline__ float clip_scale(const double* sumsq, float clipnorm) {
-  if (!(clipnorm > 0.f) || sumsq == nullptr) return 1.0f;
-  const float norm = (float)sqrt(sumsq[0]);
-  return (norm >= clipnorm) ? clipnorm / norm : 1.0f;  // Keras clip_norm: K.switch(n >= c, g*c/n, g)
+// factor applied to the stored gradient: 1/gdenom (the backward pass leaves gradients UN-normalised -- sums over tokens;
+// gdenom[0] = the global number of unmasked steps the Keras objective divides by) times the clip factor of the
+// normalised gradient.  sumsq[0] = sum of squares of the stored (un-normalised) gradient.
+__device__ __forceinline__ float clip_scale(const double* sumsq, float clipnorm, const float* gdenom) {
+  const float inv = gdenom ? 1.0f / gdenom[0] : 1.0f;
+  if (!(clipnorm > 0.f) || sumsq == nullptr) return inv;
+  const float norm = (float)sqrt(sumsq[0]) * inv;
+  return (norm >= clipnorm) ? inv * (clipnorm / norm) : inv;  // Keras clip_norm: K.switch(n >= c, g*c/n, g)
 }
 
 __global__ void __launch_bounds__(256)
 adagrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ a, int64_t n, float lr,
-               float eps, float clipnorm, const double* __restrict__ sumsq) {
-  const float sc = clip_scale(sumsq, clipnorm);
+               float eps, float clipnorm, const double* __restrict__ sumsq, const float* __restrict__ gdenom) {
+  const float sc = clip_scale(sumsq, clipnorm, gdenom);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(a)) & 15) == 0;
@@ -101,8 +105,8 @@ __global__ void __launch_bounds__(256)
 adagrad_rows_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ a,
                     const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows,
                     int32_t* __restrict__ touched, int GH, float lr, float eps, float clipnorm,
-                    const double* __restrict__ sumsq) {
-  const float sc = clip_scale(sumsq, clipnorm);
+                    const double* __restrict__ sumsq, const float* __restrict__ gdenom) {
+  const float sc = clip_scale(sumsq, clipnorm, gdenom);
   const int lane = threadIdx.x & 31;
   const int nr = n_rows[0];
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nr; w += (gridDim.x * blockDim.x) >> 5) {
@@ -159,19 +163,19 @@ extern "C" int seqrec_sumsq_rows(const float* g, const int32_t* rows, const int3
 }
 
 extern "C" int seqrec_adagrad(float* p, const float* g, float* a, int64_t n, float lr, float eps, float clipnorm,
-                              const double* sumsq, void* stream) {
+                              const double* sumsq, const float* gdenom, void* stream) {
   SEQREC_ARG(n > 0, 1);
-  adagrad_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(p, g, a, n, lr, eps, clipnorm, sumsq);
+  adagrad_kernel<<<grid_for(n, 256 * 4), 256, 0, as_stream(stream)>>>(p, g, a, n, lr, eps, clipnorm, sumsq, gdenom);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int seqrec_adagrad_rows(float* p, float* g, float* a, const int32_t* rows, const int32_t* n_rows,
                                    int32_t* touched, int GH, int max_rows, float lr, float eps, float clipnorm,
-                                   const double* sumsq, void* stream) {
+                                   const double* sumsq, const float* gdenom, void* stream) {
   SEQREC_ARG(GH > 0 && max_rows > 0, 1);
   adagrad_rows_kernel<<<grid_for(max_rows, 8), 256, 0, as_stream(stream)>>>(p, g, a, rows, n_rows, touched, GH, lr,
-                                                                            eps, clipnorm, sumsq);
+                                                                            eps, clipnorm, sumsq, gdenom);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }

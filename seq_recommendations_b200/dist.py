@@ -56,6 +56,21 @@ class Comm:
             return
         dist.reduce_scatter_tensor(out, inp.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
 
+    def all_to_all_rows(self, inp):
+        """inp (world*n, ...): block j goes to rank j; returns (world*n, ...) whose block i came from rank i."""
+        if not self.enabled:
+            return inp
+        out = torch.empty_like(inp)
+        dist.all_to_all_single(out, inp.contiguous(), group=self.group)
+        return out
+
+    def broadcast(self, t, src=0):
+        """In-place broadcast of rank `src`'s tensor (replicas must start from identical weights)."""
+        if self.enabled:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, src) if self.group is not None else src,
+                           group=self.group)
+        return t
+
     def barrier(self):
         if self.enabled:
             dist.barrier(group=self.group)

@@ -10,8 +10,10 @@ libseqrec_b200.so.  There is no CPU path: constructing a HotPath without CUDA or
 
 HBM layout (all fp32 unless noted; token n = t*B + b, time-major):
   weights   W_in (F,G*H) | flat[U (H,G*H) | b (G*H) | W_out (H,V) | b_out (V)]         Keras layouts, row-major
-  grads     dW_in (F,G*H) zero-invariant + touched flags + row list | flat like the weights, with the per-step
-            scalars (n_valid, touched-row count, squared gradient norm) in its tail: one fill clears both
+  grads     ONE allocation: dW_in (F,G*H) zero-invariant | step floats [n_valid, loss_sum, ...] | flat like the weights |
+            per-step integer scalars (n_valid, touched-row count, squared gradient norm).  One fill clears everything
+            behind dW_in at the start of a step; one all-reduce covers [dW_in |] step floats | dU | db.  Gradients are
+            stored UN-normalised (sums over tokens); the optimiser kernels divide by the global n_valid
   accum     Adagrad accumulators, same shapes
   per batch ids/tgt int32 [T][B], mask u8 [T][B], xg [T][B][G*H] (xp -> gates -> dxp in place),
             hout [T][B][H], cst [T][B][H], dh [T][B][H], per-token stats m,s,zy,ce,py,coef [N], ws [splits][N]
@@ -128,7 +130,8 @@ class HotPath:
             self.v_lo = self.comm.rank * self.V
         self.dropout_in = 0.0
         self.dropout_out = 0.0
-        self.seed = int(seed)
+        # identical seeds on every rank would draw identical dropout masks for different shards: fold the rank in
+        self.seed = int(seed) * max(1, self.comm.world) + self.comm.rank
         # dropout stream position, on the device ([0] next offset, [1] kernel-internal ticket): a captured step draws
         # fresh factors at every replay
         self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)
@@ -143,12 +146,21 @@ class HotPath:
             o += _align(s)
         self._seg = list(zip(offs, sizes))
         self.flat_p = torch.zeros(o, dtype=f32, device=dev)
-        # gradients and the per-step scalars share one allocation, so a training step clears both with ONE fill:
-        # scal[0] unmasked tokens (int32), [1] touched-row count (int32), [2:4] squared gradient norm (float64)
-        self._grads_and_scal = torch.zeros(o + 4, dtype=f32, device=dev)   # o is a multiple of 64 floats
-        self.flat_g = self._grads_and_scal[:o]
-        self.scal = self._grads_and_scal[o:o + 4].view(torch.int32)
+        # ONE gradient allocation: dW_in (zero-invariant: only touched rows are ever non-zero, the row-sparse Adagrad
+        # re-zeroes them) | 64 step floats | flat dense gradients | 4 words of integer step scalars.  A training step
+        # clears everything behind dW_in with ONE fill when the batch is staged; a data-parallel step reduces
+        # [dW_in (dense exchange only) | step floats | dU | db] in ONE all-reduce.
+        #   stepf[0] unmasked tokens (float), [1] loss sum, [2] squared norm of the vocabulary-sharded gradients
+        #   scal[0] unmasked tokens (int32), [1] touched-row count (int32), [2:4] squared gradient norm (float64)
+        self._fgh = _align(self.F * self.GH)
+        self._gbuf = torch.zeros(self._fgh + 64 + o + 4, dtype=f32, device=dev)
+        self.dW_in = self._gbuf[:self.F * self.GH].view(self.F, self.GH)
+        self.stepf = self._gbuf[self._fgh:self._fgh + 64]
+        self._grads_and_scal = self._gbuf[self._fgh:]
+        self.flat_g = self._gbuf[self._fgh + 64:self._fgh + 64 + o]
+        self.scal = self._gbuf[self._fgh + 64 + o:].view(torch.int32)
         self.flat_a = torch.zeros(o, dtype=f32, device=dev)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # id range violations seen by format_batch
 
         def views(flat):
             U = flat[offs[0]:offs[0] + sizes[0]].view(self.H, self.GH)
@@ -159,8 +171,8 @@ class HotPath:
 
         self.U, self.b, self.W_out, self.b_out = views(self.flat_p)
         self.dU, self.db, self.dW_out, self.db_out = views(self.flat_g)
+        self.aU, self.ab, self.aW_out, self.ab_out = views(self.flat_a)      # Adagrad accumulators
         self.W_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
-        self.dW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
         self.aW_in = torch.zeros((self.F, self.GH), dtype=f32, device=dev)
         self.Ut = torch.empty((self.GH, self.H), dtype=f32, device=dev)
         self._needs_ut = _lib.load().seqrec_rnn_needs_ut(CELL[cell], self.H) != 0
@@ -182,7 +194,8 @@ class HotPath:
         self.rows = torch.empty(self.F, dtype=torch.int32, device=dev)
         self.n_rows = self.scal[1:2]
         self.sumsq = self.scal[2:4].view(torch.float64)
-        self.inv_nvalid = torch.ones(1, dtype=f32, device=dev)
+        self.n_valid_f = self.stepf[0:1]
+        self.step_loss_sum = self.stepf[1:2]
         self.trainable = {"W_in": True, "U": True, "b": True, "W_out": True, "b_out": True}
         self.opt = None
         self.prof = None  # list of (phase name, cuda event) marks when bench.py profiles a step
@@ -301,19 +314,58 @@ class HotPath:
             out.append(w.detach().cpu().numpy().copy())
         return out
 
-    def set_weights(self, weights):
+    def set_weights(self, weights, sync=True):
+        """weights: full-catalog arrays in `get_weights()` order (a vocabulary-parallel model keeps its column shard).
+        sync: in a multi-process run every rank takes RANK 0's arrays (one broadcast per weight), so replicas can never
+        start from different weights -- e.g. when each process drew its own random initialisation."""
         ws = self.weight_list()
         if len(weights) != len(ws):
             raise ValueError("expected %d weight arrays, got %d" % (len(ws), len(weights)))
-        if self.vocab_parallel:
-            weights = list(weights)
-            for i in range(3, len(weights)):
-                weights[i] = np.asarray(weights[i])[..., self.v_lo:self.v_lo + self.V]
-        for dst, src in zip(ws, weights):
+        for i, (dst, src) in enumerate(zip(ws, weights)):
             src = np.asarray(src, dtype=np.float32)
-            if tuple(src.shape) != tuple(dst.shape):
-                raise ValueError("weight shape %s does not match %s" % (src.shape, tuple(dst.shape)))
-            dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+            full_shape = tuple(dst.shape)
+            if self.vocab_parallel and i >= 3:
+                full_shape = full_shape[:-1] + (self.V_total,)
+            if tuple(src.shape) != full_shape:
+                raise ValueError("weight shape %s does not match %s" % (src.shape, full_shape))
+            if sync and self.comm.enabled:
+                t = torch.from_numpy(np.ascontiguousarray(src)).to(self.device)
+                self.comm.broadcast(t, 0)
+                if self.vocab_parallel and i >= 3:
+                    t = t[..., self.v_lo:self.v_lo + self.V]
+                dst.copy_(t)
+            else:
+                if self.vocab_parallel and i >= 3:
+                    src = src[..., self.v_lo:self.v_lo + self.V]
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+        self._w_version += 1
+
+    def get_accumulator(self, name):
+        """Adagrad accumulator of one weight (state checkpoints)."""
+        return self.get_weight(name, prefix="a")
+
+    def set_accumulator(self, name, value):
+        self.set_weight(name, value, prefix="a")
+
+    def get_weight(self, name, prefix=""):
+        """One weight by name ('W_in', 'U', 'b', 'W_out', 'b_out') as a full-width float32 numpy array."""
+        t = getattr(self, prefix + name)
+        if self.vocab_parallel and name in ("W_out", "b_out"):
+            full = self.comm.all_gather_cat(t.detach().t().contiguous() if t.dim() == 2 else t.detach())
+            t = full.t() if t.dim() == 2 else full
+        return t.detach().cpu().numpy().copy()
+
+    def set_weight(self, name, value, sync=True, prefix=""):
+        t = getattr(self, prefix + name)
+        v = np.asarray(value, dtype=np.float32)
+        sharded = self.vocab_parallel and name in ("W_out", "b_out")
+        full_shape = tuple(t.shape[:-1]) + (self.V_total,) if sharded else tuple(t.shape)
+        if tuple(v.shape) != full_shape:
+            raise ValueError("weight %s: shape %s does not match %s" % (name, v.shape, full_shape))
+        d = torch.from_numpy(np.ascontiguousarray(v)).to(self.device)
+        if sync:
+            self.comm.broadcast(d, 0)
+        t.copy_(d[..., self.v_lo:self.v_lo + self.V] if sharded else d)
         self._w_version += 1
 
     def reset_optimizer_state(self):
@@ -335,23 +387,45 @@ class HotPath:
         (self._grads_and_scal if grads else self.scal).zero_()
 
     def _format(self, w, have_t=True, grads=False):
-        """(B,T) device ids/targets -> time-major ids/targets/mask + valid-token count (the in-graph part of ingest)."""
+        """(B,T) device ids/targets -> time-major ids/targets/mask + valid-token count (the in-graph part of ingest).
+        Ids >= F / targets >= V become pads and raise the device error flag (see check_errors)."""
         self._zero_step_scalars(grads)
+        n_in = self.F if w.x_dense is None else 1 << 30
         call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
-             ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, self.stream)
+             ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, n_in, self.V_total,
+             ptr(self.err_flag), self.stream)
+
+    def check_errors(self):
+        """Raise if a staged batch held an item id outside the input table or a target outside the catalog (the
+        reference raises IndexError in np_utils.to_categorical, preprocessor.py:75-78).  Host arrays are checked when
+        they are staged; device-resident batches are checked by the formatter kernel, which masks the offending token
+        and raises a flag -- read here (one 4-byte D2H; called by the model surface once per epoch / call)."""
+        bits = int(self.err_flag.item())
+        if bits:
+            self.err_flag.zero_()
+            what = [n for b, n in ((1, "input item id >= %d" % self.F), (2, "target id outside [0, %d)" % self.V_total))
+                    if bits & b]
+            raise ValueError("batch holds an out-of-range id: " + " and ".join(what))
+
+    def _check_host_ids(self, ids, tgt):
+        if ids is not None and not isinstance(ids, torch.Tensor):
+            a = np.asarray(ids)
+            if a.size and int(a.max()) >= self.F:
+                raise ValueError("input item id %d is outside the input table (%d rows)" % (int(a.max()), self.F))
+        if tgt is not None and not isinstance(tgt, torch.Tensor):
+            a = np.asarray(tgt)
+            if a.size and int(a.max()) >= self.V_total:
+                raise ValueError("target id %d is outside the catalog (%d items)" % (int(a.max()), self.V_total))
 
     def _stage(self, w, ids, tgt, x_dense=None, format_now=True, grads=False):
         """Host (numpy / pinned torch) or device batch -> time-major device buffers.  ids (B,T) int32, pad < 0."""
-        st = self.stream
+        self._check_host_ids(ids if x_dense is None else None, tgt)
 
         def to_dev(dst, pin, src):
             if src is None:
                 return None
             if isinstance(src, torch.Tensor):
-                if src.device.type == "cuda":
-                    dst.copy_(src, non_blocking=True)
-                else:
-                    dst.copy_(src, non_blocking=True)  # pinned source: async H2D
+                dst.copy_(src, non_blocking=True)      # device source, or pinned host source: asynchronous either way
             else:
                 # the pinned staging buffer is reused every call: wait until the previous asynchronous copy out of it
                 # has really run (with CUDA-graph replay the host can be a whole step ahead of the device)
@@ -363,33 +437,24 @@ class HotPath:
             return dst
 
         w.x_dense = None
+        have_t = tgt is not None
         if x_dense is None:
             to_dev(w.ids_bt, w.pin_ids, ids)
-            have_t = tgt is not None
-            if have_t:
-                to_dev(w.tgt_bt, w.pin_tgt, tgt)
-            if w.pin_dirty:
-                w.pin_event = torch.cuda.Event()
-                w.pin_event.record(torch.cuda.current_stream(self.device))
-                w.pin_dirty = False
-            if not format_now:
-                return
-            self._format(w, have_t, grads)
         else:
-            self._zero_step_scalars(grads)
             # dense-feature input (RNNBaseline): x_dense (B,T,F) float; mask = any(x != 0) (model.py:246)
             xd = x_dense if isinstance(x_dense, torch.Tensor) else torch.from_numpy(
                 np.ascontiguousarray(x_dense, dtype=np.float32))
             xd = xd.to(self.device, dtype=torch.float32, non_blocking=True)
             w.x_dense = xd.permute(1, 0, 2).contiguous()
-            valid_bt = (xd != 0).any(dim=-1)
-            marker = torch.where(valid_bt, 0, -1).to(torch.int32)
-            w.ids_bt.copy_(marker)
-            have_t = tgt is not None
-            if have_t:
-                to_dev(w.tgt_bt, w.pin_tgt, tgt)
-            call("seqrec_format_batch", ptr(w.ids_bt), ptr(w.tgt_bt) if have_t else None, ptr(w.ids),
-                 ptr(w.tgt) if have_t else None, ptr(w.mask), ptr(w.n_valid_i), w.B, w.T, st)
+            w.ids_bt.copy_(torch.where((xd != 0).any(dim=-1), 0, -1).to(torch.int32))
+        if have_t:
+            to_dev(w.tgt_bt, w.pin_tgt, tgt)
+        if w.pin_dirty:
+            w.pin_event = torch.cuda.Event()
+            w.pin_event.record(torch.cuda.current_stream(self.device))
+            w.pin_dirty = False
+        if format_now:
+            self._format(w, have_t, grads)
 
     def _dropout(self, shape, rate):
         t = torch.empty(shape, dtype=torch.float32, device=self.device)
@@ -471,9 +536,9 @@ class HotPath:
         call("seqrec_rnn_weight_grad", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(self.dU), ptr(self.db),
              w.T, w.B, self.H, st)
 
-    def _forward_ce(self, w, with_targets=True, training=False, mean=False):
+    def _forward_ce(self, w, with_targets=True, training=False, train=False):
         n_splits = self._ce_partials(w, with_targets, training)
-        self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets, mean)
+        self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets, train)
 
     def _ce_partials(self, w, with_targets=True, training=False):
         """Logits kernels only: per-token partial (max, sum-exp) rows in w.ws_m / w.ws_s and the target logit in w.zy.
@@ -504,32 +569,36 @@ class HotPath:
             n_splits = self._ce_splits(w.N)
             call("seqrec_ce_forward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
                  ptr(w.tgt) if with_targets else None, ptr(w.ws_m), ptr(w.ws_s), ptr(w.zy), w.N, self.H, self.V, 0,
-                 self.V, self.V, n_splits, 0, st)
+                 self.V, self.V, n_splits, st)
         return n_splits
 
-    def _finalize_ce(self, w, ws_m, ws_s, n_splits, with_targets=True, mean=False):
-        """mean: this rank's tokens are the whole batch -- the kernel also writes 1/n_valid (self.inv_nvalid) and the
-        masked-mean loss (w.loss_mean), which saves three one-element launches between the logits passes."""
-        if mean:
+    def _finalize_ce(self, w, ws_m, ws_s, n_splits, with_targets=True, train=False):
+        """train: a training step -- the loss sum and the unmasked-token count go (as floats) into the step-float block
+        at the head of the gradient buffer (reduced over ranks together with dU / db), and the local masked-mean loss
+        into w.loss_mean."""
+        if train:
             call("seqrec_ce_finalize_mean", ptr(ws_m), ptr(ws_s), ptr(w.zy), ptr(w.mask), ptr(w.m), ptr(w.s), ptr(w.ce),
-                 ptr(w.py), ptr(w.coef), ptr(w.loss_sum), ptr(w.n_valid_i), ptr(self.inv_nvalid), ptr(w.loss_mean),
-                 w.N, n_splits, self.stream)
+                 ptr(w.py), ptr(w.coef), ptr(self.step_loss_sum), ptr(w.n_valid_i), ptr(self.n_valid_f),
+                 ptr(w.loss_mean), w.N, n_splits, self.stream)
         else:
             call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
                  ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
         self._mark("misc")
 
     def _backward_ce(self, w):
+        """K6.  Gradients leave UN-normalised (dlogit = (p - onehot) * coef, no 1/n_valid): everything downstream is
+        linear in that factor, so the optimiser kernels apply 1/n_valid_global once -- which is what lets a
+        data-parallel step run its backward pass before the token counts of the other ranks are known."""
         st = self.stream
         if w.tc["bwd"]:
             call("seqrec_ce_tc_backward", ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), ptr(self.Bt_hi),
                  ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(w.tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
-                 ptr(self.inv_nvalid), ptr(w.hscale), ptr(w.dh), ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
+                 None, ptr(w.hscale), ptr(w.dh), ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
                  self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, ptr(self.b_out), ptr(self.db_out), st)
         else:
             call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
-                 ptr(w.m), ptr(w.s), ptr(w.coef), ptr(self.inv_nvalid), ptr(w.dh), ptr(self.dW_out), ptr(self.db_out),
-                 w.N, self.H, self.V, 0, self.V, self.V, 0, 0, st)
+                 ptr(w.m), ptr(w.s), ptr(w.coef), None, ptr(w.dh), ptr(self.dW_out), ptr(self.db_out),
+                 w.N, self.H, self.V, 0, self.V, self.V, 0, st)
 
     # ------------------------------------------------------------------------------------------------ public steps
     def loss_batch(self, ids, tgt, x_dense=None):
@@ -551,19 +620,18 @@ class HotPath:
         one-element device tensor (no host sync)."""
         if self.opt is None:
             raise _lib.SeqrecError("compile_model / set_optimizer must be called before training")
-        if self.vocab_parallel:
-            return self._train_batch_vp(ids, tgt, x_dense)
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
+        core = self._train_core_vp if self.vocab_parallel else self._train_core
         self._mark("ingest")
         graphable = (self.use_graphs and x_dense is None and self.prof is None and
                      (not self.comm.enabled or self.graph_collectives))
         if not graphable:
             self._stage(w, ids, tgt, x_dense, grads=True)
-            return self._train_core(w)
-        # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~22 launches of a step are
-        # submitted as one graph, which removes the launch gaps between them.  The first step of a (B,T) shape runs
-        # eagerly, the second one captures.
+            return core(w)
+        # CUDA-graph replay of the whole step (fixed shapes and buffers): the ~22 launches of a step -- and the NCCL
+        # calls of a multi-GPU step -- are submitted as one graph, which removes the launch gaps between them.  The
+        # first step of a (B,T) shape runs eagerly, the second one captures.
         self._stage(w, ids, tgt, None, format_now=False)
         key = self._graph_key()
         if w.graph is not None and w.graph_key != key:
@@ -572,12 +640,12 @@ class HotPath:
             w.graph_calls += 1
             if w.graph_calls < 2:
                 self._format(w, grads=True)
-                return self._train_core(w)
+                return core(w)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._format(w, grads=True)
-                w.graph_loss = self._train_core(w)
+                w.graph_loss = core(w)
             w.graph, w.graph_key = g, key
         w.graph.replay()
         self._w_version += 1
@@ -590,74 +658,59 @@ class HotPath:
                 self.dropout_out, self.overlap, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
 
     def _train_core(self, w):
-        """forward + backward + exchange + update on the staged batch (everything after the host->device copy)."""
+        """forward + backward + exchange + update on the staged batch (everything after the host->device copy).
+
+        Data parallel: no collective sits between the forward and the backward pass.  The backward runs
+        un-normalised; [n_valid, loss_sum] ride in the step-float block in front of dU | db and are summed over the
+        ranks by the SAME all-reduce (plus the dense dW_in when the catalog is small enough for the dense exchange:
+        the three live in one allocation).  dW_out / db_out are reduced behind the recurrent backward pass.  The
+        optimiser kernels then divide by the global n_valid."""
         st = self.stream
         comm = self.comm
         self._split_version = -1                  # a training step always follows a weight update: re-stage W_out
-        # data parallel: the ids of all ranks (union of touched rows for the dense dW_in exchange) travel behind the
-        # forward pass; n_valid and loss_sum are reduced together in ONE two-float all-reduce after it (the forward
-        # needs neither: 1/n_valid first enters in the logits backward)
         dense_rows = (comm.enabled and w.x_dense is None and
                       embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense")
+        # union of touched rows for the dense dW_in exchange: the ids of all ranks travel behind the forward pass
         all_ids, ids_handle = comm.all_gather_cat_async(w.ids.view(-1)) if dense_rows else (None, None)
         if w.tc["fwd"]:
             self._mark("stage_operands")
             with self._branch():                  # bf16 operands of the updated W_out, behind gather + scan
                 self._stage_weight_operands()
         self._forward_hidden(w, training=True)
-        self._forward_ce(w, training=True, mean=not comm.enabled)
-        if comm.enabled:
-            pair = torch.cat([w.n_valid_i.to(torch.float32), w.loss_sum])
-            comm.all_reduce_sum(pair)
-            torch.reciprocal(pair[0:1], out=self.inv_nvalid)
-            loss = pair[1:2] * self.inv_nvalid
-        else:
-            # written with inv_nvalid by the finalize kernel; a graph replay hands out the static buffer (as it always
-            # did), an eager step a private copy
-            loss = w.loss_mean if torch.cuda.is_current_stream_capturing() else w.loss_mean.clone()
+        self._forward_ce(w, training=True, train=True)
 
-        # ---- backward (flat_g was cleared with the step scalars when the batch was staged)
+        # ---- backward (the gradient buffer was cleared with the step scalars when the batch was staged)
         self._mark("ce_bwd")
         self._backward_ce(w)
-        # data parallel: dW_out / db_out are final here -- their all-reduce runs on NCCL's stream behind the recurrent
-        # backward pass; the (small) dU / db reduction follows the weight-gradient GEMM
+        # dW_out / db_out are final here: their all-reduce runs on NCCL's stream behind the recurrent backward pass
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
         pending = [comm.all_reduce_sum(self.flat_g[head:], async_op=True)] if comm.enabled else []
         self._mark("rnn_bwd")
         self._rnn_backward(w)
-        # ---- input-kernel gradient first: its exchange then overlaps the recurrent weight-gradient GEMMs, which run
-        #      as a parallel branch (both only read dxp)
+        # ---- input-kernel gradient and recurrent weight-gradient GEMMs as parallel branches (both only read dxp)
         branch_wgrad = self.overlap and self.prof is None
         if branch_wgrad:
             with self._branch():
                 self._rnn_weight_grad(w)
         self._mark("scatter")
+        dense_in = False
         if w.x_dense is None:                     # (n_rows and sumsq were cleared when the batch was staged)
-            if not comm.enabled:
+            if not comm.enabled or dense_rows:
                 call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                      ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
-            elif dense_rows:
-                call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
-                     ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
-                pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
-                if ids_handle is not None:
-                    ids_handle.wait()
-                call("seqrec_mark_rows", ptr(all_ids), None, ptr(self.touched), ptr(self.rows), ptr(self.n_rows),
-                     all_ids.numel(), self.F, st)
+                if dense_rows:
+                    dense_in = True
+                    if ids_handle is not None:
+                        ids_handle.wait()
+                    call("seqrec_mark_rows", ptr(all_ids), None, ptr(self.touched), ptr(self.rows), ptr(self.n_rows),
+                         all_ids.numel(), self.F, st)
             else:
-                all_ids = comm.all_gather_cat(w.ids.view(-1))
-                all_mask = comm.all_gather_cat(w.mask.view(-1))
-                all_dxp = comm.all_gather_cat(w.xg.view(w.N, self.GH))
-                all_scale = comm.all_gather_cat(w.in_scale) if w.in_scale is not None else None
-                call("seqrec_scatter_add_rows", ptr(all_dxp), ptr(all_ids), ptr(all_mask), ptr(all_scale),
-                     ptr(self.dW_in), ptr(self.touched), ptr(self.rows), ptr(self.n_rows), all_ids.numel(), self.F,
-                     self.GH, st)
+                self._scatter_gathered_rows(w)
         else:
             self.dW_in.zero_()
             call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
-            if comm.enabled:
-                pending.append(comm.all_reduce_sum(self.dW_in, async_op=True))
+            dense_in = comm.enabled
         self._mark("rnn_wgrad")
         if branch_wgrad:
             self._join()
@@ -665,7 +718,8 @@ class HotPath:
             self._rnn_weight_grad(w)
         self._mark("allreduce")
         if comm.enabled:
-            pending.append(comm.all_reduce_sum(self.flat_g[:head], async_op=True))
+            lo = 0 if dense_in else self._fgh
+            pending.append(comm.all_reduce_sum(self._gbuf[lo:self._fgh + 64 + head], async_op=True))
 
         # ---- global-norm clip + Adagrad (needs every reduced gradient: clipnorm is global)
         for h in pending:
@@ -674,14 +728,31 @@ class HotPath:
         self._mark("optim")
         self._apply_update(w, scalars_clean=True)
         self._w_version += 1
+        if comm.enabled:
+            loss = self.step_loss_sum / self.n_valid_f
+        else:
+            # written by the finalize kernel; a graph replay hands out the static buffer, an eager step a private copy
+            loss = w.loss_mean if torch.cuda.is_current_stream_capturing() else w.loss_mean.clone()
         self._mark("end")
         return loss
 
+    def _scatter_gathered_rows(self, w):
+        """Row exchange of dW_in (large catalogs): all-gather (ids, dxp rows [, y->z dropout factors]) and scatter-add
+        them locally, so every replica applies the identical row-sparse update.  Pads carry id -1 (formatter)."""
+        comm = self.comm
+        all_ids = comm.all_gather_cat(w.ids.view(-1))
+        all_dxp = comm.all_gather_cat(w.xg.view(w.N, self.GH))
+        all_scale = comm.all_gather_cat(w.in_scale) if w.in_scale is not None else None
+        all_mask = (all_ids >= 0).to(torch.uint8)
+        call("seqrec_scatter_add_rows", ptr(all_dxp), ptr(all_ids), ptr(all_mask), ptr(all_scale), ptr(self.dW_in),
+             ptr(self.touched), ptr(self.rows), ptr(self.n_rows), all_ids.numel(), self.F, self.GH, self.stream)
+
     # ------------------------------------------------------------------------------------------------ vocabulary parallel
-    def _vp_forward(self, w, training):
+    def _vp_forward(self, w, training, train=False):
         """Shared by training and evaluation: every rank scores ALL ranks' tokens against its item shard, then the
         per-token (max, sum-exp) partials and the target logit are merged across ranks.  Returns the work object that
-        holds the global-token buffers (token order: rank-major blocks of each rank's time-major tokens)."""
+        holds the global-token buffers (token order: rank-major blocks of each rank's time-major tokens).
+        Three collectives: hidden rows, targets (pads are -1, so the mask travels with them), packed (m, s, zy)."""
         comm = self.comm
         wg = self.work(w.B * comm.world, w.T)
         hs = w.hout.view(w.N, self.H)
@@ -690,72 +761,74 @@ class HotPath:
         wg.hout.view(wg.N, self.H).copy_(comm.all_gather_cat(hs))
         wg.hscale = None
         tgt_all = comm.all_gather_cat(w.tgt.view(-1))
-        wg.mask.view(-1).copy_(comm.all_gather_cat(w.mask.view(-1)))
+        valid = tgt_all >= 0
+        wg.mask.view(-1).copy_(valid)
         local = (tgt_all >= self.v_lo) & (tgt_all < self.v_lo + self.V)
         wg.tgt.view(-1).copy_(torch.where(local, tgt_all - self.v_lo, torch.full_like(tgt_all, -1)))
         wg.zy.zero_()
         n_splits = self._ce_partials(wg, True, training)
-        # local merge -> (m_r, s_r) per token, exchange, global merge with the owner's target logit
+        # local merge -> (m_r, s_r) per token; ONE exchange of the packed (m, s, zy); global merge (only the owner of a
+        # target contributes a non-zero zy)
         call("seqrec_ce_finalize", ptr(wg.ws_m), ptr(wg.ws_s), None, None, ptr(wg.m), ptr(wg.s), None, None, None, None,
              wg.N, n_splits, self.stream)
-        m_all = comm.all_gather_cat(wg.m)
-        s_all = comm.all_gather_cat(wg.s)
-        comm.all_reduce_sum(wg.zy)
-        self._finalize_ce(wg, m_all, s_all, comm.world, True)
+        packed = comm.all_gather_cat(torch.stack([wg.m, wg.s, wg.zy]).unsqueeze(0))      # (P, 3, N)
+        packed = packed.permute(1, 0, 2).contiguous()                                    # (3, P, N)
+        torch.sum(packed[2], dim=0, out=wg.zy)
+        if train:
+            # n_valid and the loss sum of ALL tokens are known locally (identical on every rank): they go into the step
+            # floats directly and stay outside the reduced range
+            self.scal[0:1].copy_(valid.sum().to(torch.int32))
+        self._finalize_ce(wg, packed[0], packed[1], comm.world, True, train=train)
         return wg
 
-    def _train_batch_vp(self, ids, tgt, x_dense=None):
-        B, T = (ids.shape if ids is not None else x_dense.shape[:2])
-        w = self.work(int(B), int(T))
+    def _train_core_vp(self, w):
+        """Vocabulary-parallel step: data-parallel scan, logits against the local V/P items for the
+        tokens of ALL ranks.  Seven collectives per step, all inside the captured graph: all-gather hidden rows / targets
+        / packed softmax partials, reduce-scatter dh, ONE all-reduce of [sharded squared norm | dU | db], all-gather ids
+        and dxp rows for the row-sparse dW_in."""
         st = self.stream
         comm = self.comm
-        self._mark("ingest")
-        self._stage(w, ids, tgt, x_dense)
-        n_valid = w.n_valid_i.to(torch.float32)
-        comm.all_reduce_sum(n_valid)
-        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        self._split_version = -1
         self._forward_hidden(w, training=True)
-        wg = self._vp_forward(w, training=True)
-        loss = wg.loss_sum * self.inv_nvalid      # identical on every rank: the sum runs over all ranks' tokens
+        wg = self._vp_forward(w, training=True, train=True)
         # ---- backward: dW_out / db_out of the shard are complete locally; dh is summed over the item shards
-        self.flat_g.zero_()
         self._mark("ce_bwd")
         self._backward_ce(wg)
         self._mark("allreduce")
         comm.reduce_scatter_sum(w.dh.view(w.N, self.H), wg.dh.view(wg.N, self.H))
         if w.hscale is not None:
             w.dh.view(w.N, self.H).mul_(w.hscale)
+        (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
+        head = o_b + s_b
+        o = self.opt
+        if o["clipnorm"] > 0:
+            # squared norm of the SHARDED gradients (summed over ranks below, in the slot right in front of dU);
+            # replicated gradients count once
+            call("seqrec_sumsq", ptr(self.flat_g[head:]), self.flat_g.numel() - head, ptr(self.sumsq), st)
+            self.stepf[63:64].copy_(self.sumsq)
+            self.sumsq.zero_()
         self._mark("rnn_bwd")
         self._rnn_backward(w)
         self._mark("rnn_wgrad")
         self._rnn_weight_grad(w)
         self._mark("scatter")
-        (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
-        head = o_b + s_b
-        comm.all_reduce_sum(self.flat_g[:head])   # replicated recurrent parameters
-        self.n_rows.zero_()
-        all_ids = comm.all_gather_cat(w.ids.view(-1))
-        all_mask = comm.all_gather_cat(w.mask.view(-1))
-        all_dxp = comm.all_gather_cat(w.xg.view(w.N, self.GH))
-        all_scale = comm.all_gather_cat(w.in_scale) if w.in_scale is not None else None
-        call("seqrec_scatter_add_rows", ptr(all_dxp), ptr(all_ids), ptr(all_mask), ptr(all_scale), ptr(self.dW_in),
-             ptr(self.touched), ptr(self.rows), ptr(self.n_rows), all_ids.numel(), self.F, self.GH, st)
-        # ---- global norm: replicated gradients count once, the sharded ones are summed over ranks
-        o = self.opt
+        comm.all_reduce_sum(self._gbuf[self._fgh + 63:self._fgh + 64 + head])
+        self._scatter_gathered_rows(w)
+        # ---- global norm + update
         max_rows = min(self.F, w.N * comm.world)
         self._mark("optim")
-        self.sumsq.zero_()
         if o["clipnorm"] > 0:
-            call("seqrec_sumsq", ptr(self.flat_g[head:]), self.flat_g.numel() - head, ptr(self.sumsq), st)
-            comm.all_reduce_sum(self.sumsq)
+            self.sumsq.copy_(self.stepf[63:64])
             call("seqrec_sumsq", ptr(self.flat_g[:head]), head, ptr(self.sumsq), st)
             call("seqrec_sumsq_rows", ptr(self.dW_in), ptr(self.rows), ptr(self.n_rows), self.GH, max_rows,
                  ptr(self.sumsq), st)
         call("seqrec_adagrad", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_a), self.flat_p.numel(), o["lr"],
-             o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+             o["eps"], o["clipnorm"], ptr(self.sumsq), ptr(self.n_valid_f), st)
         call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows), ptr(self.n_rows),
-             ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+             ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq),
+             ptr(self.n_valid_f), st)
         self._w_version += 1
+        loss = wg.loss_mean if torch.cuda.is_current_stream_capturing() else wg.loss_mean.clone()
         self._mark("end")
         return loss
 
@@ -766,6 +839,7 @@ class HotPath:
     def _apply_update(self, w, scalars_clean=False):
         st = self.stream
         o = self.opt
+        den = ptr(self.n_valid_f)                 # gradients are stored un-normalised: the kernels divide
         if not scalars_clean:
             self.sumsq.zero_()
         segs = self._segments()
@@ -793,23 +867,23 @@ class HotPath:
                     # also re-zeroes the touched rows of dW_in and their flags (zero invariant of the dense buffer)
                     call("seqrec_adagrad_rows", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), ptr(self.rows),
                          ptr(self.n_rows), ptr(self.touched), self.GH, max_rows, o["lr"], o["eps"], o["clipnorm"],
-                         ptr(self.sumsq), self.stream)
+                         ptr(self.sumsq), den, self.stream)
                 else:
                     self.dW_in.zero_()
                     self.touched.zero_()
             else:
                 if self.trainable["W_in"]:
                     call("seqrec_adagrad", ptr(self.W_in), ptr(self.dW_in), ptr(self.aW_in), self.W_in.numel(), o["lr"],
-                         o["eps"], o["clipnorm"], ptr(self.sumsq), self.stream)
+                         o["eps"], o["clipnorm"], ptr(self.sumsq), den, self.stream)
                 self.dW_in.zero_()
         if all_dense:
             call("seqrec_adagrad", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_a), self.flat_p.numel(), o["lr"],
-                 o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+                 o["eps"], o["clipnorm"], ptr(self.sumsq), den, st)
         else:
             for n, off, sz in segs:
                 if self.trainable[n]:
                     call("seqrec_adagrad", ptr(self.flat_p[off:off + sz]), ptr(self.flat_g[off:off + sz]),
-                         ptr(self.flat_a[off:off + sz]), sz, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), st)
+                         ptr(self.flat_a[off:off + sz]), sz, o["lr"], o["eps"], o["clipnorm"], ptr(self.sumsq), den, st)
         self._join()
 
     def _rank_rows(self, wt, hrows, m, s, n, k):
@@ -848,21 +922,20 @@ class HotPath:
         n_splits = self._ce_partials(wg, False, False)
         call("seqrec_ce_finalize", ptr(wg.ws_m), ptr(wg.ws_s), None, None, ptr(wg.m), ptr(wg.s), None, None, None, None,
              wg.N, n_splits, self.stream)
-        m_all = comm.all_gather_cat(wg.m)
-        s_all = comm.all_gather_cat(wg.s)
-        self._finalize_ce(wg, m_all, s_all, comm.world, False)          # catalog-wide (m, s) of every gathered row
+        packed = comm.all_gather_cat(torch.stack([wg.m, wg.s]).unsqueeze(0)).permute(1, 0, 2).contiguous()
+        self._finalize_ce(wg, packed[0], packed[1], comm.world, False)  # catalog-wide (m, s) of every gathered row
         loc_i, loc_p = self._rank_rows(wg, wg.hout.view(wg.N, self.H), wg.m, wg.s, wg.N, k)
         loc_i = loc_i + self.v_lo                                        # global item ids
-        all_i = comm.all_gather_cat(loc_i.view(1, wg.N, k))              # (P shards, P*n_loc rows, k)
-        all_p = comm.all_gather_cat(loc_p.view(1, wg.N, k))
-        lo = comm.rank * n_loc
-        ci = all_i[:, lo:lo + n_loc].permute(1, 0, 2).reshape(n_loc, comm.world * k)
-        cp = all_p[:, lo:lo + n_loc].permute(1, 0, 2).reshape(n_loc, comm.world * k)
-        order = torch.argsort(ci, dim=1, stable=True)                    # ids ascending ...
-        ci, cp = torch.gather(ci, 1, order), torch.gather(cp, 1, order)
-        order = torch.argsort(cp, dim=1, descending=True, stable=True)   # ... then probability descending, stable
-        top_i = torch.gather(ci, 1, order)[:, :k].contiguous()
-        top_p = torch.gather(cp, 1, order)[:, :k].contiguous()
+        # every rank needs the P candidate lists of ITS rows only: one all-to-all (block j of the local result holds
+        # rank j's rows), then the same (probability descending, lower id first) merge kernel the 1-GPU ranking ends with
+        cand_i = comm.all_to_all_rows(loc_i)                             # (P lists, n_loc rows, k)
+        cand_p = comm.all_to_all_rows(loc_p)
+        if comm.world * k > 384:
+            raise ValueError("vocabulary-parallel ranking needs world * k <= 384")
+        top_i = torch.empty((n_loc, k), dtype=torch.int32, device=self.device)
+        top_p = torch.empty((n_loc, k), dtype=torch.float32, device=self.device)
+        call("seqrec_topk_merge", ptr(cand_p), ptr(cand_i), comm.world, n_loc * k, ptr(top_i), ptr(top_p), n_loc, k,
+             self.stream)
         if last_step_only:
             return top_i, top_p
         return (top_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),
@@ -876,33 +949,31 @@ class HotPath:
         w = self.work(int(B), int(T))
         st = self.stream
         saved_opt = self.opt
-        self._stage(w, ids, tgt, x_dense)
-        n_valid = w.n_valid_i.to(torch.float32)
-        self.comm.all_reduce_sum(n_valid)
-        torch.reciprocal(n_valid, out=self.inv_nvalid)
+        self._stage(w, ids, tgt, x_dense, grads=True)
         self._forward_hidden(w, training=True)
-        self._forward_ce(w, training=True)
-        loss = (w.loss_sum * self.inv_nvalid).clone()
-        self.flat_g.zero_()
+        self._forward_ce(w, training=True, train=True)
         self._backward_ce(w)
         dh = w.dh.clone()
         self._rnn_backward(w)
         self._rnn_weight_grad(w)
-        self.n_rows.zero_()
         if w.x_dense is None:
             call("seqrec_scatter_add_rows", ptr(w.xg), ptr(w.ids), ptr(w.mask), ptr(w.in_scale), ptr(self.dW_in),
                  ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
         else:
             self.dW_in.zero_()
             call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
+        self.check_errors()
+        # the kernels leave un-normalised gradients (the optimiser divides by n_valid): normalise here for the caller
+        n_valid = float(self.n_valid_f.item())
+        loss = float(self.step_loss_sum.item()) / n_valid
         grads = [self.dW_in, self.dU, self.db, self.dW_out] + ([self.db_out] if self.out_bias else [])
-        out = [g.detach().cpu().numpy().copy() for g in grads]
+        out = [(g.detach().double() / n_valid).float().cpu().numpy() for g in grads]
         rows = self.rows[: int(self.n_rows.item())].cpu().numpy().copy() if w.x_dense is None else None
         self.dW_in.zero_()
         self.touched.zero_()
         self.opt = saved_opt
-        return float(loss.item()), out, dict(dh=dh.cpu().numpy(), rows=rows,
-                                             dxp=w.xg.detach().cpu().numpy().copy())
+        return loss, out, dict(dh=(dh / n_valid).cpu().numpy(), rows=rows,
+                               dxp=(w.xg.detach() / n_valid).cpu().numpy())
 
     # ------------------------------------------------------------------------------------------------ scoring
     def hidden_batch(self, ids, x_dense=None):

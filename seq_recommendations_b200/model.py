@@ -143,19 +143,12 @@ class _Net(object):
         names = ["W_in", "U"] + (["b"] if self.rnn_bias else []) + ["W_out"] + (["b_out"] if self.hot.out_bias else [])
         return names
 
-    def _tensor(self, name):
-        return getattr(self.hot, name)
-
     def _get(self, name):
-        return self._tensor(name).detach().cpu().numpy().copy()
+        """Full-width array (the column shards of a vocabulary-parallel model are gathered by HotPath)."""
+        return self.hot.get_weight(name)
 
     def _set(self, name, value):
-        t = self._tensor(name)
-        v = np.asarray(value, dtype=np.float32)
-        if tuple(v.shape) != tuple(t.shape):
-            raise ValueError("weight %s: shape %s does not match %s" % (name, v.shape, tuple(t.shape)))
-        t.copy_(torch.from_numpy(np.ascontiguousarray(v)))
-        self.hot._w_version += 1
+        self.hot.set_weight(name, value)
 
     def get_weights(self):
         return [self._get(n) for n in self._names()]
@@ -183,19 +176,67 @@ class _Net(object):
                 return l
         raise ValueError("No such layer: " + str(name))
 
+    @staticmethod
+    def _npz_path(filepath):
+        """Checkpoints are .npz archives (h5py is absent from this image): a path that claims to be HDF5 gets '.npz'
+        appended, so no file ever carries zip bytes under an .h5 / .hdf5 name."""
+        return filepath + ".npz" if filepath.lower().endswith((".h5", ".hdf5")) else filepath
+
+    def _write_npz(self, filepath, arrays):
+        """Rank 0 writes (temp file + rename: a reader never sees a torn archive), everybody waits."""
+        comm = self.hot.comm
+        if comm.rank == 0:
+            d = os.path.dirname(filepath)
+            if d and not os.path.exists(d):
+                os.makedirs(d)
+            tmp = "%s.tmp.%d" % (filepath, os.getpid())
+            with open(tmp, "wb") as f:
+                np.savez(f, **arrays)
+            os.replace(tmp, filepath)
+        comm.barrier()
+
     def save_weights(self, filepath, overwrite=True):
-        """Weights-only checkpoint in `get_weights()` order.  h5 needs h5py (absent in this image) -- the flat
-        `weight{i}` layout of model.py:201-208 is written as .npz instead."""
+        """Weights-only checkpoint in `get_weights()` order, the flat `weight{i}` layout of model.py:201-208 as an .npz
+        archive (collective in a multi-process run: shards are gathered, rank 0 writes)."""
         ws = self.get_weights()
-        d = os.path.dirname(filepath)
-        if d and not os.path.exists(d):
-            os.makedirs(d)
-        with open(filepath, "wb") as f:
-            np.savez(f, **{"weight%d" % i: w for i, w in enumerate(ws)})
+        self._write_npz(self._npz_path(filepath), {"weight%d" % i: w for i, w in enumerate(ws)})
+
+    @staticmethod
+    def _open_npz(filepath):
+        if not os.path.exists(filepath) and os.path.exists(_Net._npz_path(filepath)):
+            filepath = _Net._npz_path(filepath)
+        with open(filepath, "rb") as f:
+            magic = f.read(8)
+        if magic.startswith(b"\x89HDF"):
+            raise IOError("%s is an HDF5 file (a Keras / reference checkpoint).  h5py is not available in this image; "
+                          "convert it with `h5py` to an .npz archive holding weight0..weightN in get_weights() order "
+                          "(model.py:201-208) and load that." % filepath)
+        return np.load(filepath)
 
     def load_weights(self, filepath, by_name=False):
-        with np.load(filepath) as z:
-            self.set_weights([z["weight%d" % i] for i in range(len(z.files))])
+        with self._open_npz(filepath) as z:
+            n = len([k for k in z.files if k.startswith("weight")])
+            self.set_weights([z["weight%d" % i] for i in range(n)])
+
+    def save_state(self, filepath, epoch=0):
+        """Resumable checkpoint (not in the reference, whose checkpoints restart Adagrad): weights, the Adagrad
+        accumulators of every weight, the optimizer hyper-parameters and the epoch counter."""
+        arrays = {"weight%d" % i: w for i, w in enumerate(self.get_weights())}
+        for i, n in enumerate(self._names()):
+            arrays["accum%d" % i] = self.hot.get_accumulator(n)
+        o = self.hot.opt or {}
+        arrays["epoch"] = np.asarray(int(epoch))
+        arrays["opt"] = np.asarray([o.get("lr", 0.0), o.get("eps", 0.0), o.get("clipnorm", 0.0)], dtype=np.float64)
+        self._write_npz(self._npz_path(filepath), arrays)
+
+    def load_state(self, filepath):
+        """Inverse of save_state; returns the stored epoch.  compile() first (it resets the accumulators)."""
+        with self._open_npz(filepath) as z:
+            names = self._names()
+            self.set_weights([z["weight%d" % i] for i in range(len(names))])
+            for i, n in enumerate(names):
+                self.hot.set_accumulator(n, z["accum%d" % i])
+            return int(z["epoch"])
 
     # ---- compile -------------------------------------------------------------------------------------------------
     def compile(self, loss="categorical_crossentropy", optimizer="adam", metrics=None):
@@ -227,9 +268,10 @@ class _Net(object):
         return (ids[idx] if ids is not None else None), (xd[idx] if xd is not None else None)
 
     def _epoch_eval(self, ids, xd, tgt, batch_size):
-        """Keras test_loop: batch-size-weighted mean of per-batch masked-mean losses."""
+        """Keras test_loop: batch-size-weighted mean of per-batch masked-mean losses.  The per-batch
+        means stay on the device; one read-back per call."""
         n = len(tgt)
-        total = torch.zeros(1, dtype=torch.float64, device=self.hot.device)
+        per_batch, sizes = [], []
         for lo in range(0, n, batch_size):
             hi = min(n, lo + batch_size)
             i, d = self._slice(ids, xd, slice(lo, hi))
@@ -237,8 +279,18 @@ class _Net(object):
             if self.hot.comm.enabled:
                 self.hot.comm.all_reduce_sum(ls)
                 self.hot.comm.all_reduce_sum(nv)
-            total += (ls / nv).double() * (hi - lo)
+            per_batch.append(ls / nv)
+            sizes.append(hi - lo)
+        w = torch.tensor(sizes, dtype=torch.float64, device=self.hot.device)
+        total = (torch.cat(per_batch).double() * w).sum()
+        self.hot.check_errors()
         return float(total.item()) / n
+
+    def _resident(self, a):
+        """A whole id array in HBM (int32), when it is small enough to keep there for the epochs of a fit call."""
+        if a is None or a.nbytes > (2 << 30):
+            return None
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.hot.device)
 
     # ---- Keras Model methods ------------------------------------------------------------------------------------
     def fit(self, x, y, validation_data=None, epochs=10, batch_size=100, verbose=1, callbacks=None, shuffle=True):
@@ -247,13 +299,16 @@ class _Net(object):
                                       % (self.optimizer,))
         ids, xd = self._inputs(x)
         tgt = to_id_batch(y)
+        self.hot._check_host_ids(ids, tgt)
         n = len(tgt)
         val = None
         if validation_data is not None:
             vi, vd = self._inputs(validation_data[0])
             val = (vi, vd, to_id_batch(validation_data[1]))
+        # Keras 2.0.x order: user callbacks first, History last -- History records what the callbacks put into `logs`
+        # (ValLossHistoryCut's `my_loss`, model.py:114)
         history = cb.History()
-        cbs = [history] + list(callbacks or [])
+        cbs = list(callbacks or []) + [history]
         for c in cbs:
             c.set_model(self)
             c.set_params({"epochs": epochs, "batch_size": batch_size, "samples": n, "verbose": verbose})
@@ -261,19 +316,35 @@ class _Net(object):
         logs0 = {}
         for c in cbs:
             c.on_train_begin(logs0)
+        # id batches: the training set goes to HBM once; an epoch then costs one H2D copy of the shuffled index and
+        # two on-device row gathers per batch (no per-batch numpy fancy indexing, no pinned staging copy)
+        dev_ids = dev_tgt = None
+        if xd is None:
+            dev_ids, dev_tgt = self._resident(ids), self._resident(tgt)
+            if dev_ids is None or dev_tgt is None:
+                dev_ids = dev_tgt = None
+        n_batches = (n + batch_size - 1) // batch_size
+        sizes = torch.tensor([min(batch_size, n - b * batch_size) for b in range(n_batches)], dtype=torch.float64,
+                             device=self.hot.device)
+        losses = torch.zeros(n_batches, dtype=torch.float32, device=self.hot.device)
         index = np.arange(n)
         for epoch in range(epochs):
             for c in cbs:
                 c.on_epoch_begin(epoch)
             if shuffle:
                 np.random.shuffle(index)
-            acc = torch.zeros(1, dtype=torch.float64, device=self.hot.device)
-            for lo in range(0, n, batch_size):
-                sel = index[lo:lo + batch_size]
-                i, d = self._slice(ids, xd, sel)
-                loss = self.hot.train_batch(i, tgt[sel], d)
-                acc += loss.double() * len(sel)
-            logs = {"loss": float(acc.item()) / n}
+            dev_index = torch.from_numpy(index).to(self.hot.device) if dev_ids is not None else None
+            for b, lo in enumerate(range(0, n, batch_size)):
+                if dev_ids is not None:
+                    sel = dev_index[lo:lo + batch_size]
+                    loss = self.hot.train_batch(dev_ids.index_select(0, sel), dev_tgt.index_select(0, sel))
+                else:
+                    sel = index[lo:lo + batch_size]
+                    i, d = self._slice(ids, xd, sel)
+                    loss = self.hot.train_batch(i, tgt[sel], d)
+                losses[b:b + 1].copy_(loss)
+            logs = {"loss": float((losses.double() * sizes).sum().item()) / n}
+            self.hot.check_errors()
             for m in self.metrics_names[1:]:
                 logs[m] = logs["loss"]
             if val is not None:
@@ -293,13 +364,16 @@ class _Net(object):
     def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None, validation_data=None,
                       validation_steps=None):
         history = cb.History()
-        cbs = [history] + list(callbacks or [])
+        cbs = list(callbacks or []) + [history]
         for c in cbs:
             c.set_model(self)
+            c.set_params({"epochs": epochs, "steps": steps_per_epoch, "verbose": verbose})
         self.stop_training = False
         for c in cbs:
             c.on_train_begin({})
         for epoch in range(epochs):
+            for c in cbs:
+                c.on_epoch_begin(epoch)
             acc, cnt = 0.0, 0
             for _ in range(steps_per_epoch):
                 x, y = next(generator)

@@ -18,6 +18,45 @@ def rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30))
 
 
+def model_surface_checks(comm, dev):
+    """The reference-facing surface under torchrun: (1) every process draws its OWN random initial weights (seed=None,
+    the default) -- the replicas must still start, and stay, identical (rank 0's weights are broadcast); (2) a
+    vocabulary-parallel model saves and loads FULL-width weights (shards gathered, rank 0 writes, temp file + rename)."""
+    import tempfile
+    from seq_recommendations_b200.model import RNNFullModel
+    from seq_recommendations_b200.optimizers import Adagrad
+    ok = True
+    V, H, T, B = 512, 32, 6, 16 * comm.world
+    ids, tgt = synthetic.make_batch(V, T, B, seed=9, min_len=1)
+    lo, hi = dist.shard_rows(B, comm.rank, comm.world)
+    for vp in (False, True):
+        mdl = RNNFullModel(T, V, V, z_dim=H, rnn_type="GRU", z_to_z_activation="tanh", y_to_y=False, x_to_y=False,
+                           seed=None, comm=comm, vocab_parallel=vp)
+        mdl.compile_model(optimizer=Adagrad(lr=0.05, epsilon=1e-8, clipnorm=1.0))
+        mdl.model.train_on_batch(ids[lo:hi], tgt[lo:hi])
+        ws = mdl.model.get_weights()
+        assert ws[3].shape == (H, V), ws[3].shape                 # full catalog width, also when sharded
+        flat = torch.cat([torch.from_numpy(w).reshape(-1) for w in ws]).to(dev)
+        mx, mn = flat.clone(), flat.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(mn, op=torch.distributed.ReduceOp.MIN)
+        spread = float(((mx - mn).abs().max() / flat.abs().max()).item())
+        same = spread <= 2e-5
+        # checkpoint round trip (collective): path agreed through rank 0
+        box = [tempfile.mkdtemp() if comm.rank == 0 else None]
+        torch.distributed.broadcast_object_list(box, src=0)
+        path = os.path.join(box[0], "ckpt.%d.hdf5" % int(vp))
+        mdl.model.save_weights(path)
+        mdl.model.set_weights([np.zeros_like(w) for w in ws])
+        mdl.model.load_weights(path)
+        back = mdl.model.get_weights()
+        rt = all(np.array_equal(a, b) for a, b in zip(ws, back))
+        print("rank %d: model surface vocab_parallel=%s: replica spread %.1e, checkpoint round trip %s -> %s" % (
+            comm.rank, vp, spread, rt, "OK" if same and rt else "MISMATCH"), flush=True)
+        ok = ok and same and rt
+    return ok
+
+
 def main():
     comm = dist.init_from_env("nccl")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -86,6 +125,7 @@ def main():
         if (dense and spread != 0.0) or spread > 2e-5:
             print("rank %d: replicas diverged (dense=%s, spread %.2e)" % (comm.rank, dense, spread), flush=True)
             ok = False
+    ok = model_surface_checks(comm, dev) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
     comm.barrier()

@@ -102,3 +102,88 @@ def test_cfg5_scoring_topk_and_target_prob_reduced_batch():
         hit = np.nonzero(top_i[b] == last_t[b])[0]
         if len(hit):
             assert abs(py[b, -1] - top_p[b, hit[0]]) <= 1e-4 * top_p[b, hit[0]] + 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The named BASELINE shapes against the float64 ORACLE (not against the CUDA path itself): loss and all four gradients,
+# norm-wise (1e-4, north_star) AND element-wise (|a - b| <= 1e-4 * max|b|: a localised error cannot hide in a norm).
+# cfg2 runs at its full size; cfg3 / cfg4 / cfg5 keep their catalog width, hidden size and sequence length and reduce
+# only the batch (factor stated per test) so that the CPU oracle finishes in seconds.
+def _elementwise_ok(a, b, tol=1e-4):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max()) <= tol * float(np.abs(b).max()) + 1e-12
+
+
+def _oracle_grads_compact(cell, act, ws, ids, tgt):
+    """float64 oracle loss / gradients with the INPUT table restricted to the rows the batch touches (the dense
+    (V, G*H) float64 gradient of a 1M-row table would be 6 GB of zeros); returns the used row ids with it."""
+    used = np.unique(ids[ids >= 0])
+    remap = np.full(int(ids.max()) + 2, -1, dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    cid = np.where(ids >= 0, remap[np.maximum(ids, 0)], -1)
+    ora = ks.Model(cell, act, [ws[0][used]] + list(ws[1:]), dtype=torch.float64)
+    loss, gs = ora.grads(as_t(cid), as_t(tgt), as_t(ids) >= 0)
+    return float(loss), [g.numpy() for g in gs], used
+
+
+def _check_grads_vs_oracle(cfg, B, T=None, seed=3):
+    V, H = cfg["V"], cfg["H"]
+    T = T or cfg["T"]
+    ws = synthetic.make_weights(cfg["cell"], V, H, seed=seed)
+    ids, tgt = synthetic.make_batch(V, T, B, seed=seed + 1)
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws, tc="x3")
+    w = hot.work(B, T)
+    assert w.tc["fwd"] and w.tc["bwd"], "the named shapes must run on the tensor-core logits kernels"
+    loss, grads, extra = hot.grad_batch(ids, tgt)
+    rl, rg, used = _oracle_grads_compact(cfg["cell"], cfg["act"], ws, ids, tgt)
+    assert abs(loss - rl) <= 1e-4 * abs(rl), (loss, rl)
+    assert np.array_equal(np.sort(extra["rows"]), used)              # exactly the touched rows carry a gradient
+    names = ["dW_in", "dU", "db", "dW_out"]
+    mine = [grads[0][used]] + grads[1:]
+    for n, g, r in zip(names, mine, rg):
+        assert rel_err(g, r) <= 1e-4, (n, rel_err(g, r))
+        assert _elementwise_ok(g, r), (n, float(np.abs(g - r).max()), float(np.abs(r).max()))
+    untouched = np.setdiff1d(np.arange(min(V, 20000)), used)[:500]
+    assert not grads[0][untouched].any()
+
+
+def test_cfg2_full_size_gradients_match_float64_oracle():
+    """configs[1] at FULL size: V=10k, GRU-128, T=50, B=256 (12 800 tokens x 10 000 items)."""
+    _check_grads_vs_oracle(synthetic.CONFIGS["cfg2_reddit_gru128"], B=256)
+
+
+def test_cfg3_shape_gradients_match_float64_oracle():
+    """configs[2]: V=50k, LSTM-256, T=100; batch reduced 1024 -> 8 (factor 128)."""
+    _check_grads_vs_oracle(synthetic.CONFIGS["cfg3_lstm256_50k"], B=8)
+
+
+def test_cfg4_shape_gradients_match_float64_oracle():
+    """configs[3]: V=1M, GRU-256, T=50; batch reduced 1024 -> 4 (factor 256)."""
+    _check_grads_vs_oracle(synthetic.CONFIGS["cfg4_gru256_1m"], B=4)
+
+
+def test_cfg5_shape_scoring_matches_float64_oracle():
+    """configs[4]: V=100k, GRU-256, T=200; batch reduced 4096 -> 4 (factor 1024): p(true item) at every step within
+    1e-4 relative, top-20 of the last step bit-exact wherever the oracle's ranking is decided by more than fp32 noise."""
+    cfg = synthetic.CONFIGS["cfg5_score_gru256_100k"]
+    V, H, T, B, k = cfg["V"], cfg["H"], cfg["T"], 4, 20
+    ws = synthetic.make_weights(cfg["cell"], V, H, seed=0)
+    ws[3] = ws[3] * 20.0                                          # a ranking that is not flat
+    ids, tgt = synthetic.make_batch(V, T, B, seed=1)
+    hot = HotPath(cfg["cell"], cfg["act"], V, H, V, weights=ws)
+    ora = ks.Model(cfg["cell"], cfg["act"], ws, dtype=torch.float64)
+    ref = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)
+    py = hot.target_prob_batch(ids, tgt).cpu().numpy()
+    rpy = ks.target_prob(ref, as_t(tgt), as_t(ids) >= 0).numpy()
+    assert np.abs(py / rpy - 1).max() <= 1e-4
+    ti, tp = hot.topk_batch(ids, k, last_step_only=True)
+    want = ks.topk_items(ref[:, -1], k)
+    refp = np.take_along_axis(ref[:, -1].numpy(), want.astype(np.int64), axis=1)
+    got = ti.cpu().numpy()
+    for b in range(B):
+        gaps = np.abs(np.diff(refp[b])) / refp[b, :-1]
+        if gaps.min() > 1e-5:
+            assert np.array_equal(got[b], want[b])
+        else:
+            assert np.array_equal(np.sort(got[b]), np.sort(want[b]))
+    assert np.abs(tp.cpu().numpy() / np.take_along_axis(ref[:, -1].numpy(), got.astype(np.int64), axis=1) - 1).max() <= 1e-4

@@ -42,9 +42,42 @@ def test_format_batch_transposes_and_counts():
     d = lambda *s, dt=torch.int32: torch.empty(s, dtype=dt, device="cuda")
     ids_tb, tgt_tb, mask_tb, nv = d(37, 45), d(37, 45), d(37, 45, dt=torch.uint8), torch.zeros(1, dtype=torch.int32, device="cuda")
     dids, dtgt = torch.tensor(ids).cuda(), torch.tensor(tgt).cuda()
-    call("seqrec_format_batch", ptr(dids), ptr(dtgt), ptr(ids_tb), ptr(tgt_tb), ptr(mask_tb), ptr(nv), 45, 37, stream())
+    call("seqrec_format_batch", ptr(dids), ptr(dtgt), ptr(ids_tb), ptr(tgt_tb), ptr(mask_tb), ptr(nv), 45, 37, 500, 500,
+         None, stream())
     assert np.array_equal(ids_tb.cpu().numpy(), ids.T) and np.array_equal(tgt_tb.cpu().numpy(), tgt.T)
     assert np.array_equal(mask_tb.cpu().numpy().astype(bool), (ids >= 0).T) and int(nv.item()) == int((ids >= 0).sum())
+
+
+def test_format_batch_masks_out_of_range_ids_and_raises_the_flag():
+    """An id >= the table height (or a target outside the catalog) must never reach a kernel that indexes with it: the
+    formatter turns the token into a pad and raises the device flag; HotPath turns the flag into a ValueError (the
+    reference raises IndexError in np_utils.to_categorical, preprocessor.py:75-78)."""
+    ids, tgt = synthetic.make_batch(500, 12, 9, seed=6, all_valid=True)
+    bad_i, bad_t = ids.copy(), tgt.copy()
+    bad_i[2, 3] = 500
+    bad_t[4, 5] = 777
+    d = lambda *s, dt=torch.int32: torch.empty(s, dtype=dt, device="cuda")
+    ids_tb, tgt_tb, mask_tb = d(12, 9), d(12, 9), d(12, 9, dt=torch.uint8)
+    nv, err = torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+    call("seqrec_format_batch", ptr(torch.tensor(bad_i).cuda()), ptr(torch.tensor(bad_t).cuda()), ptr(ids_tb), ptr(tgt_tb),
+         ptr(mask_tb), ptr(nv), 9, 12, 500, 500, ptr(err), stream())
+    assert int(err.item()) == 3 and int(nv.item()) == 12 * 9 - 2
+    m = mask_tb.cpu().numpy().T
+    assert m[2, 3] == 0 and m[4, 5] == 0 and m.sum() == 12 * 9 - 2
+    assert ids_tb.cpu().numpy().T[2, 3] == -1 and tgt_tb.cpu().numpy().T[4, 5] == -1
+    # through the engine: host arrays are rejected when staged, device batches when the flag is read
+    hot, _, _ = make_pair("GRU", "tanh", 500, 16, seed=1)
+    hot.set_optimizer("adagrad", lr=0.01, epsilon=1e-8, clipnorm=1.0)
+    with pytest.raises(ValueError):
+        hot.train_batch(bad_i, tgt)
+    with pytest.raises(ValueError):
+        hot.train_batch(ids, bad_t)
+    hot.train_batch(torch.tensor(bad_i).cuda(), torch.tensor(tgt).cuda())
+    with pytest.raises(ValueError):
+        hot.check_errors()
+    hot.train_batch(torch.tensor(ids).cuda(), torch.tensor(tgt).cuda())
+    hot.check_errors()                                            # the flag was cleared by the raise
+    assert np.all(np.isfinite(hot.get_weights()[0]))
 
 
 @pytest.mark.parametrize("V,GH,N", [(40, 384, 4000), (7, 13, 999), (100000, 64, 2048)])
@@ -256,7 +289,7 @@ def test_dense_feature_inputs_match_oracle():
 
 @pytest.mark.parametrize("N,splits", [(1, 1), (777, 3), (12800, 5)])
 def test_finalize_mean_matches_finalize_and_numpy(N, splits):
-    """seqrec_ce_finalize_mean = seqrec_ce_finalize + (1/n_valid, masked mean): same per-token outputs bit for bit, and
+    """seqrec_ce_finalize_mean = seqrec_ce_finalize + (n_valid as float, masked mean): same per-token outputs bit for bit, and
     the two scalars against a float64 numpy restatement (Keras masked mean: sum of masked losses / unmasked steps)."""
     rng = np.random.default_rng(N)
     ws_m = torch.tensor(rng.standard_normal((splits, N)).astype(np.float32)).cuda()
@@ -282,7 +315,7 @@ def test_finalize_mean_matches_finalize_and_numpy(N, splits):
     for a, b in zip(outs[0][:6], outs[1][:6]):
         assert torch.equal(a, b)
     nv = float(mask_h.sum())
-    assert outs[1][6].item() == np.float32(1.0) / np.float32(nv)
+    assert outs[1][6].item() == np.float32(nv)
     ref_mean = outs[1][2].double().numpy().sum() / nv
     assert abs(outs[1][7].item() - ref_mean) <= 1e-6 * abs(ref_mean)
     # and the per-token losses against numpy: merged (m, s) -> -log(clip(exp(zy - m) / s))
