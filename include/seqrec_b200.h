@@ -171,6 +171,23 @@ int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint
                           const float* inv_nvalid, const float* hscale, float* dh, float* dW_out, int64_t n_tokens,
                           int H, int Hk, int V, int Vp, int64_t Np, int v_begin, int v_end, int ldw,
                           int accumulate_dh, int x3, const float* b_out, float* db_out, void* stream);
+/* ---- K5 + K6 (dH half) from ONE logits pass (csrc/ce_tc.cu, TS_FUSED) -----------------------------------------
+ * The softmax is evaluated against a per-token REFERENCE logit ref[n] (the exact fp32 target logit from
+ * seqrec_target_logit) instead of the running row maximum -- exp(z - ref) needs no rescaling (ref is one of the row's
+ * logits; fp32 carries e^88 without loss of relative precision), so every CTA that shares a token tile accumulates
+ *     acc[n,:] += sum_v exp(z[n,v] - ref[n]) . W_out[:,v]          s[n] += sum_v exp(z[n,v] - ref[n])
+ * against the same reference and both leave through reductions: acc (N,H) and s (N) must be ZERO on entry.
+ * Then seqrec_ce_finalize(ws_m = ref, ws_s = s, splits = 1) gives loss / clip coefficient, and seqrec_ce_dh_finish
+ *     dh[n,:] = coef[n] . (acc[n,:] / s[n] - W_out[:, tgt[n]]) (. hscale[n,:])          in place over acc
+ * (tgt[n] < 0: no one-hot term -- the target belongs to another item shard; coef[n] == 0: zeros).  With the
+ * item-stationary dW kernel (seqrec_ce_tc_backward with dh = NULL, m = ref) a training step issues 4 logits-sized GEMMs
+ * for 3 algorithmic ones instead of 5.  Operands as for seqrec_ce_tc_backward. */
+int seqrec_ce_tc_fused(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                       const uint16_t* W_hi, const uint16_t* W_lo, const float* ref, const uint8_t* mask,
+                       const float* b_out, float* acc, float* s, int64_t n_tokens, int H, int Hk, int V, int Vp,
+                       int v_begin, int v_end, int x3, void* stream);
+int seqrec_ce_dh_finish(float* dh, const float* s, const float* coef, const int32_t* tgt, const uint16_t* Bt_hi,
+                        const uint16_t* Bt_lo, const float* hscale, int64_t n_tokens, int H, int Hk, void* stream);
 int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
                         const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream);
 

@@ -772,7 +772,20 @@ struct TsCfg {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int KB, bool X3, bool ITEM_ST>
+// MODE selects the variant: TS_DH / TS_DW as described above, and
+//   TS_FUSED (token-stationary): forward statistics AND dH from ONE logits pass.  The softmax is evaluated against a
+//   per-row REFERENCE logit instead of the row maximum: ref[n] = the target logit zy[n] (exact fp32, computed before this
+//   kernel).  exp(z - ref) needs no running maximum (ref is one of the row's logits, so max - ref >= 0 and the sum is
+//   >= ~1; fp32 -- and the bf16 hi/lo operand -- carry 8 exponent bits, so values up to e^88 lose no relative
+//   precision), hence no accumulator rescale and no per-CTA partial states: every CTA that shares a token tile
+//   accumulates  acc[n,:] += sum_v exp(z[n,v] - ref[n]) . W_out[:,v]  and  s[n] += sum_v exp(z[n,v] - ref[n])  against
+//   the SAME reference, and both leave through reductions.  seqrec_ce_finalize (splits = 1, m = ref) and
+//   seqrec_ce_dh_finish then give the loss, the clip coefficient and  dh = coef . (acc / s - W_out[:, target]).
+//   Rows whose target sits more than ~88 nats below the maximum overflow to s = inf: p(target) = 0 is then clipped,
+//   the clip passes no gradient (coef = 0) and the finish kernel writes zeros -- the reference's result.
+enum { TS_DH = 0, TS_DW = 1, TS_FUSED = 2 };
+
+template <int KB, bool X3, int MODE>
 __global__ void __launch_bounds__(352, 1)
 ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                          const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
@@ -781,7 +794,10 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
                          const float* __restrict__ srow, const float* __restrict__ coef,
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
                          float* __restrict__ out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
-                         uint32_t smem_bytes, const float* __restrict__ b_out, float* __restrict__ db_out) {
+                         uint32_t smem_bytes, const float* __restrict__ b_out, float* __restrict__ db_out,
+                         const uint8_t* __restrict__ tok_mask, float* __restrict__ s_out) {
+  constexpr bool ITEM_ST = MODE == TS_DW;
+  constexpr bool FUSED = MODE == TS_FUSED;
   using C = TsCfg<KB, X3>;
   constexpr int NP = C::NP, NS = C::NS, NC = C::NC, SBUF = C::SBUF;
   constexpr int NJ = BN / KBLK;                             // 64-wide K blocks of the second GEMM per tile
@@ -984,6 +1000,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     float4* sT_gen = reinterpret_cast<float4*>(smem_raw + (sT - ptx::smem_u32(smem_raw)));
     RowTerms rt;                                             // !ITEM_ST: this thread's token row; ITEM_ST: prefetch
     float bias_v = 0.f, db_acc = 0.f;                        // ITEM_ST: b_out of this thread's item, its dL/db partial
+    float s_acc = 0.f;                                       // FUSED: this thread's share of sum_v exp(z - ref)
     int tc = 0, seg = -1;
     if (ITEM_ST && sh.w0 < sh.w1) {
       if (e < 128) {
@@ -996,7 +1013,13 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       const int buf = tc % SBUF;
       if (sh.seg_first(w)) {
         ++seg;
-        if (!ITEM_ST) rt = load_row_terms((int64_t)sh.outer(w) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+        if (MODE == TS_DH) rt = load_row_terms((int64_t)sh.outer(w) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+        if (FUSED) {                                         // exp(z - ref) un-normalised, no one-hot term
+          const int64_t n = (int64_t)sh.outer(w) * BM + row;
+          rt.nb = -INFINITY; rt.scale = 0.f; rt.cf = 0.f; rt.tg = -1;
+          if (n < n_tokens && tok_mask[n]) { rt.nb = -mrow[n] * LOG2E; rt.scale = 1.f; }
+          s_acc = 0.f;
+        }
         if (ITEM_ST) {
           const int v = v_begin + sh.outer(w) * BN + row;
           bias_v = (b_out && v < v_end) ? b_out[v] : 0.f;
@@ -1020,6 +1043,12 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             if (vc0 + j < v_end) z[j] += __ldg(b_out + vc0 + j);
         }
         dlogit_half_tile(z, rt, vc0, v_end);
+        if (FUSED) {
+          float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) { a4[0] += z[j]; a4[1] += z[j + 1]; a4[2] += z[j + 2]; a4[3] += z[j + 3]; }
+          s_acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
+        }
       } else {
         const int v = v_begin + sh.outer(w) * BN + row;      // this thread's item
         const bool row_ok = v < v_end;
@@ -1063,7 +1092,8 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         if (!ITEM_ST) {
           const int64_t n = (int64_t)sh.outer(w) * BM + row;
           flush_acc_red(tmem_acc + lane_off + h0, C::ACC_COLS / 2, out + n * H + h0, H - h0, n < n_tokens,
-                        (H & 3) == 0, hscale ? hscale + n * H + h0 : nullptr);
+                        (H & 3) == 0, (hscale && !FUSED) ? hscale + n * H + h0 : nullptr);
+          if (FUSED && n < n_tokens && s_acc != 0.f) atomicAdd(s_out + n, s_acc);
         } else {
           const int v = v_begin + sh.outer(w) * BN + row;
           const bool row_ok = v < v_end;
@@ -1143,36 +1173,43 @@ int launch_fwd(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorM
   return 0;
 }
 
-template <int KB, bool X3, bool ITEM_ST>
+template <int KB, bool X3, int MODE>
 int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& y_hi,
                   const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo, const int32_t* tgt,
                   const float* m, const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
                   float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw, const float* b_out,
-                  float* db_out, cudaStream_t st) {
+                  float* db_out, const uint8_t* tok_mask, float* s_out, cudaStream_t st) {
   using C = TsCfg<KB, X3>;
   size_t smem = (size_t)C::SMEM_NEED + 1024;                 // slack for the 1024-byte alignment of the tiles
   if (smem > 227 * 1024) smem = 227 * 1024;                  // (the kernel traps if the aligned layout does not fit)
-  auto k = ce_tc_backward_ts_kernel<KB, X3, ITEM_ST>;
+  auto k = ce_tc_backward_ts_kernel<KB, X3, MODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
-                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out);
+                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out, tok_mask, s_out);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_ts(int KB, bool x3, bool item_st, int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo,
+int launch_ts(int KB, bool x3, int mode, int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo,
               const CUtensorMap& y_hi, const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo,
               const int32_t* tgt, const float* m, const float* s, const float* coef, const float* inv_nvalid,
               const float* hscale, float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
-              const float* b_out, float* db_out, cudaStream_t st) {
-#define TS3(KBV, X3V, ISV)                                                                                         \
-  return launch_ts_one<KBV, X3V, ISV>(grid, x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, \
-                                      out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)
-#define TS2(KBV)                                                         \
-  {                                                                      \
-    if (x3) { if (item_st) TS3(KBV, true, true); else TS3(KBV, true, false); }     \
-    else    { if (item_st) TS3(KBV, false, true); else TS3(KBV, false, false); }   \
+              const float* b_out, float* db_out, const uint8_t* tok_mask, float* s_out, cudaStream_t st) {
+#define TS3(KBV, X3V, MV)                                                                                          \
+  return launch_ts_one<KBV, X3V, MV>(grid, x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, \
+                                     out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, tok_mask, s_out, st)
+#define TS2(KBV)                                                                           \
+  {                                                                                        \
+    if (x3) {                                                                              \
+      if (mode == TS_DW) TS3(KBV, true, TS_DW);                                            \
+      else if (mode == TS_FUSED) TS3(KBV, true, TS_FUSED);                                 \
+      else TS3(KBV, true, TS_DH);                                                          \
+    } else {                                                                               \
+      if (mode == TS_DW) TS3(KBV, false, TS_DW);                                           \
+      else if (mode == TS_FUSED) TS3(KBV, false, TS_FUSED);                                \
+      else TS3(KBV, false, TS_DH);                                                         \
+    }                                                                                      \
   }
   switch (KB) {
     case 1: TS2(1)
@@ -1324,16 +1361,89 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
     }
     if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
     if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
-    if ((rc = launch_ts(KB, x3 != 0, false, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
-                        hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, st)))
+    if ((rc = launch_ts(KB, x3 != 0, TS_DH, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
+                        hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, nullptr, nullptr, st)))
       return rc;
   }
   if (dW_out) {
     if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
-    if ((rc = launch_ts(KB, x3 != 0, true, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
-                        nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, st)))
+    if ((rc = launch_ts(KB, x3 != 0, TS_DW, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
+                        nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, nullptr, nullptr, st)))
       return rc;
   }
+  return 0;
+}
+
+
+// ================================================================================================================
+// Fused forward + dH (TS_FUSED above) and its finish pass.
+//   seqrec_ce_tc_fused:   acc (N,H) += sum_v exp(z - ref) . W_out[:,v]   and   s (N) += sum_v exp(z - ref),
+//                         ref = zy (target logit); acc and s must be zero on entry (both leave through reductions).
+//   seqrec_ce_dh_finish:  dh[n,:] = coef[n] . (acc[n,:] / s[n] - W_out[:, tgt[n]]) (. hscale), in place over acc.
+//                         coef comes from seqrec_ce_finalize (splits = 1, ws_m = ref, ws_s = s); rows with coef = 0 (pads,
+//                         clip-saturated, overflowed s) are written as zeros.  The target column of W_out is read from the
+//                         bf16 hi/lo image of W_out^T (hi + lo: 16 mantissa bits, the precision class of the x3 products).
+extern "C" int seqrec_ce_tc_fused(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                                  const uint16_t* W_hi, const uint16_t* W_lo, const float* ref, const uint8_t* mask,
+                                  const float* b_out, float* acc, float* s, int64_t n_tokens, int H, int Hk, int V,
+                                  int Vp, int v_begin, int v_end, int x3, void* stream) {
+  SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
+  SEQREC_ARG((Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256) && H <= Hk, 2);
+  SEQREC_ARG(Vp >= V && Vp % 8 == 0 && ref && mask && acc && s, 3);
+  SEQREC_ARG(A_hi && Bt_hi && W_hi && (!x3 || (A_lo && Bt_lo && W_lo)), 4);
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, w_hi, w_lo;
+  int rc;
+  if ((rc = make_tmap(&a_hi, A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&a_lo, x3 ? A_lo : A_hi, n_tokens, Hk, Hk, BM))) return rc;
+  if ((rc = make_tmap(&b_hi, Bt_hi, V, Hk, Hk, BN))) return rc;
+  if ((rc = make_tmap(&b_lo, x3 ? Bt_lo : Bt_hi, V, Hk, Hk, BN))) return rc;
+  if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
+  if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
+  const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
+  return launch_ts(Hk / KBLK, x3 != 0, TS_FUSED, persistent_grid(total), a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, nullptr, ref,
+                   nullptr, nullptr, nullptr, nullptr, acc, n_tokens, H, v_begin, v_end, V, b_out, nullptr, mask, s, st);
+}
+
+namespace {
+// one warp per token row
+__global__ void __launch_bounds__(256)
+ce_dh_finish_kernel(float* __restrict__ dh, const float* __restrict__ srow, const float* __restrict__ coef,
+                    const int32_t* __restrict__ tgt, const __nv_bfloat16* __restrict__ Bt_hi,
+                    const __nv_bfloat16* __restrict__ Bt_lo, const float* __restrict__ hscale, int64_t n_tokens, int H,
+                    int Hk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_tokens) return;
+  const float cf = coef[n];
+  float* row = dh + n * H;
+  if (cf == 0.f) {
+    for (int h = lane; h < H; h += 32) row[h] = 0.f;
+    return;
+  }
+  const float inv_s = 1.0f / srow[n];
+  const int32_t y = tgt[n];                                  // -1: the target lives on another item shard
+  for (int h = lane; h < H; h += 32) {
+    float wy = 0.f;
+    if (y >= 0) {
+      wy = __bfloat162float(Bt_hi[(size_t)y * Hk + h]);
+      if (Bt_lo) wy += __bfloat162float(Bt_lo[(size_t)y * Hk + h]);
+    }
+    float v = cf * (row[h] * inv_s - wy);
+    if (hscale) v *= hscale[n * H + h];
+    row[h] = v;
+  }
+}
+}  // namespace
+
+extern "C" int seqrec_ce_dh_finish(float* dh, const float* s, const float* coef, const int32_t* tgt,
+                                   const uint16_t* Bt_hi, const uint16_t* Bt_lo, const float* hscale, int64_t n_tokens,
+                                   int H, int Hk, void* stream) {
+  SEQREC_ARG(dh && s && coef && tgt && Bt_hi && n_tokens > 0 && H > 0 && Hk >= H, 1);
+  ce_dh_finish_kernel<<<ceil_div(n_tokens * 32, 256), 256, 0, as_stream(stream)>>>(
+      dh, s, coef, tgt, reinterpret_cast<const __nv_bfloat16*>(Bt_hi), reinterpret_cast<const __nv_bfloat16*>(Bt_lo),
+      hscale, n_tokens, H, Hk);
+  SEQREC_CHECK_LAUNCH();
   return 0;
 }

@@ -212,6 +212,9 @@ class HotPath:
         if self.tc_mode not in ("x3", "bf16", "off"):
             raise ValueError("tc must be 'x3', 'bf16' or 'off'")
         self.tc_x3 = self.tc_mode == "x3"
+        # training: forward statistics and dH from ONE logits pass (seqrec_ce_tc_fused); SEQREC_CE_FUSED=0 falls back to
+        # the separate forward + token-stationary backward kernels
+        self.ce_fused = os.environ.get("SEQREC_CE_FUSED", "1") != "0"
         self.Hk = (self.H + 63) // 64 * 64
         self.Vp = (self.V + 7) // 8 * 8
         self._w_version = 0
@@ -585,7 +588,35 @@ class HotPath:
                  ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
         self._mark("misc")
 
-    def _backward_ce(self, w):
+    def _ce_train_fused(self, w, zy_reduce=None, s_reduce=None):
+        """Training-step logits pass on the tensor cores, fused: statistics + dh from ONE logits computation
+        (seqrec_ce_tc_fused), finalize, dh finish.  Leaves w.m (= the per-token reference logit), w.s, w.coef ready for
+        the item-stationary dW kernel.  zy_reduce / s_reduce: vocabulary-parallel hooks that sum the target logit and
+        the partial sum-exp over the item shards."""
+        st = self.stream
+        self._mark("stage_operands")
+        self._stage_weight_operands()
+        call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
+             ptr(w.Ht_lo), w.N, self.H, self.Hk, w.Np, st)
+        w.tc_operands_fresh = True
+        self._join()                              # W_out operands staged on the branch by the caller
+        self._mark("ce_fwd")
+        call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
+             ptr(w.zy), w.N, self.H, self.V, st)
+        if zy_reduce is not None:
+            zy_reduce(w.zy)
+        w.dh.zero_()
+        w.s.zero_()
+        call("seqrec_ce_tc_fused", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.Wb_hi),
+             ptr(self.Wb_lo), ptr(w.zy), ptr(w.mask), ptr(self.b_out), ptr(w.dh), ptr(w.s), w.N, self.H, self.Hk,
+             self.V, self.Vp, 0, self.V, 1 if self.tc_x3 else 0, st)
+        if s_reduce is not None:
+            s_reduce(w.s)
+        self._finalize_ce(w, w.zy, w.s, 1, True, train=True)
+        call("seqrec_ce_dh_finish", ptr(w.dh), ptr(w.s), ptr(w.coef), ptr(w.tgt), ptr(self.Bt_hi), ptr(self.Bt_lo),
+             ptr(w.hscale), w.N, self.H, self.Hk, st)
+
+    def _backward_ce(self, w, dh=True):
         """K6.  Gradients leave UN-normalised (dlogit = (p - onehot) * coef, no 1/n_valid): everything downstream is
         linear in that factor, so the optimiser kernels apply 1/n_valid_global once -- which is what lets a
         data-parallel step run its backward pass before the token counts of the other ranks are known."""
@@ -593,7 +624,7 @@ class HotPath:
         if w.tc["bwd"]:
             call("seqrec_ce_tc_backward", ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), ptr(self.Bt_hi),
                  ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(w.tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
-                 None, ptr(w.hscale), ptr(w.dh), ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
+                 None, ptr(w.hscale), ptr(w.dh) if dh else None, ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
                  self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, ptr(self.b_out), ptr(self.db_out), st)
         else:
             call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
@@ -677,11 +708,15 @@ class HotPath:
             with self._branch():                  # bf16 operands of the updated W_out, behind gather + scan
                 self._stage_weight_operands()
         self._forward_hidden(w, training=True)
-        self._forward_ce(w, training=True, train=True)
+        fused = self.ce_fused and w.tc["bwd"]
+        if fused:
+            self._ce_train_fused(w)
+        else:
+            self._forward_ce(w, training=True, train=True)
 
         # ---- backward (the gradient buffer was cleared with the step scalars when the batch was staged)
         self._mark("ce_bwd")
-        self._backward_ce(w)
+        self._backward_ce(w, dh=not fused)
         # dW_out / db_out are final here: their all-reduce runs on NCCL's stream behind the recurrent backward pass
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
@@ -766,6 +801,17 @@ class HotPath:
         local = (tgt_all >= self.v_lo) & (tgt_all < self.v_lo + self.V)
         wg.tgt.view(-1).copy_(torch.where(local, tgt_all - self.v_lo, torch.full_like(tgt_all, -1)))
         wg.zy.zero_()
+        if train:
+            # n_valid and the loss sum of ALL tokens are known locally (identical on every rank): they go into the step
+            # floats directly and stay outside the reduced range
+            self.scal[0:1].copy_(valid.sum().to(torch.int32))
+        if train and self.ce_fused and wg.tc["bwd"]:
+            # fused statistics + dh pass: the target logit (owner's shard) is summed over the shards FIRST and is every
+            # rank's reference; the partial sum-exps then add up across shards (same reference) -- two N-float all-reduces
+            self._ce_train_fused(wg, zy_reduce=comm.all_reduce_sum, s_reduce=comm.all_reduce_sum)
+            wg.fused = True
+            return wg
+        wg.fused = False
         n_splits = self._ce_partials(wg, True, training)
         # local merge -> (m_r, s_r) per token; ONE exchange of the packed (m, s, zy); global merge (only the owner of a
         # target contributes a non-zero zy)
@@ -774,10 +820,6 @@ class HotPath:
         packed = comm.all_gather_cat(torch.stack([wg.m, wg.s, wg.zy]).unsqueeze(0))      # (P, 3, N)
         packed = packed.permute(1, 0, 2).contiguous()                                    # (3, P, N)
         torch.sum(packed[2], dim=0, out=wg.zy)
-        if train:
-            # n_valid and the loss sum of ALL tokens are known locally (identical on every rank): they go into the step
-            # floats directly and stay outside the reduced range
-            self.scal[0:1].copy_(valid.sum().to(torch.int32))
         self._finalize_ce(wg, packed[0], packed[1], comm.world, True, train=train)
         return wg
 
@@ -793,7 +835,7 @@ class HotPath:
         wg = self._vp_forward(w, training=True, train=True)
         # ---- backward: dW_out / db_out of the shard are complete locally; dh is summed over the item shards
         self._mark("ce_bwd")
-        self._backward_ce(wg)
+        self._backward_ce(wg, dh=not wg.fused)
         self._mark("allreduce")
         comm.reduce_scatter_sum(w.dh.view(w.N, self.H), wg.dh.view(wg.N, self.H))
         if w.hscale is not None:
@@ -942,17 +984,21 @@ class HotPath:
                 top_p.view(w.T, w.B, k).permute(1, 0, 2).contiguous())
 
     # ------------------------------------------------------------------------------------------------ gradients only
-    def grad_batch(self, ids, tgt, x_dense=None):
+    def grad_batch(self, ids, tgt, x_dense=None, fused=None):
         """fwd + bwd WITHOUT the update (parity tests): returns loss and the raw (unclipped) gradients as numpy arrays
-        in weight-list order.  Leaves the dW_in zero-invariant intact."""
+        in weight-list order.  Leaves the dW_in zero-invariant intact.  fused: None = what a training step runs."""
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
         w = self.work(int(B), int(T))
         st = self.stream
         saved_opt = self.opt
         self._stage(w, ids, tgt, x_dense, grads=True)
         self._forward_hidden(w, training=True)
-        self._forward_ce(w, training=True, train=True)
-        self._backward_ce(w)
+        use_fused = (self.ce_fused if fused is None else bool(fused)) and w.tc["bwd"]
+        if use_fused:
+            self._ce_train_fused(w)
+        else:
+            self._forward_ce(w, training=True, train=True)
+        self._backward_ce(w, dh=not use_fused)
         dh = w.dh.clone()
         self._rnn_backward(w)
         self._rnn_weight_grad(w)

@@ -59,8 +59,9 @@ def test_format_batch_masks_out_of_range_ids_and_raises_the_flag():
     d = lambda *s, dt=torch.int32: torch.empty(s, dtype=dt, device="cuda")
     ids_tb, tgt_tb, mask_tb = d(12, 9), d(12, 9), d(12, 9, dt=torch.uint8)
     nv, err = torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
-    call("seqrec_format_batch", ptr(torch.tensor(bad_i).cuda()), ptr(torch.tensor(bad_t).cuda()), ptr(ids_tb), ptr(tgt_tb),
-         ptr(mask_tb), ptr(nv), 9, 12, 500, 500, ptr(err), stream())
+    d_bad_i, d_bad_t = torch.tensor(bad_i).cuda(), torch.tensor(bad_t).cuda()      # keep the device copies alive
+    call("seqrec_format_batch", ptr(d_bad_i), ptr(d_bad_t), ptr(ids_tb), ptr(tgt_tb), ptr(mask_tb), ptr(nv), 9, 12, 500,
+         500, ptr(err), stream())
     assert int(err.item()) == 3 and int(nv.item()) == 12 * 9 - 2
     m = mask_tb.cpu().numpy().T
     assert m[2, 3] == 0 and m[4, 5] == 0 and m.sum() == 12 * 9 - 2
