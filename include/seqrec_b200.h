@@ -84,6 +84,17 @@ int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8
  * U (H, G*H) and Ut = U^T (G*H, H).  For GRU, cst receives r*h_{t-1} (operand of dU's candidate block). */
 int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const float* Ut, const uint8_t* mask,
                         const float* hout, float* cst, const float* dhout, int T, int B, int H, void* stream);
+/* ---- K3 / K4 with Keras `recurrent_dropout` (model.py:346, :351; tune_params.py:83, tune_params_msnbc.py:54,77) ----
+ * rec_mask (G, B, H): one inverted-dropout mask per gate block, constant over time; gate block g multiplies h_{t-1}
+ * by rec_mask[g] before its recurrent product (GRU candidate: r * h_{t-1} * rec_mask[2]).  Same buffers and contracts
+ * as seqrec_rnn_forward / seqrec_rnn_backward / seqrec_rnn_weight_grad; always the generic fp32 scan.  scratch: T*B*H
+ * floats. */
+int seqrec_rnn_forward_rd(int cell, int act, float* xg, const float* U, const float* rec_mask, const uint8_t* mask,
+                          float* hout, float* cst, int T, int B, int H, void* stream);
+int seqrec_rnn_backward_rd(int cell, int act, float* xg, const float* Ut, const float* rec_mask, const uint8_t* mask,
+                           const float* hout, float* cst, const float* dhout, int T, int B, int H, void* stream);
+int seqrec_rnn_weight_grad_rd(int cell, const float* dxp, const float* hout, const float* cst, const float* rec_mask,
+                              float* scratch, float* dU, float* db, int T, int B, int H, void* stream);
 /* 1 when seqrec_rnn_backward reads Ut for this (cell, H); 0 when the register-resident scan (GRU / SimpleRNN with
  * H <= 128, U held in registers for all T steps) serves it from U and Ut may be NULL */
 int seqrec_rnn_needs_ut(int cell, int H);

@@ -31,6 +31,9 @@ SIGNATURES = {
     "seqrec_gemm_tn_atomic": [_p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_forward": [_i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_forward_rd": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_backward_rd": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_rnn_weight_grad_rd": [_i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_needs_ut": [_i, _i],
     "seqrec_rnn_tc_applicable": [_i, _i],
     "seqrec_rnn_tc_forward": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],

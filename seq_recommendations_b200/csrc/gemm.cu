@@ -199,3 +199,50 @@ extern "C" int seqrec_rnn_weight_grad(int cell, const float* dxp, const float* h
   }
   return 0;
 }
+
+
+// out[t,b,:] = in[t,b,:] * m[b,:]   (h_{t-1} * rm[g]: operand of gate block g's dU under recurrent dropout)
+__global__ void __launch_bounds__(256)
+mul_rows_bcast_kernel(const float* __restrict__ in, const float* __restrict__ m, float* __restrict__ out, int64_t total,
+                      int64_t BH) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) out[i] = in[i] * m[i % BH];
+}
+
+// seqrec_rnn_weight_grad under recurrent dropout: gate block g sees h_{t-1} * rec_mask[g], so dU is G separate products
+// (GRU candidate block: cst = r * h_{t-1} * rec_mask[2], written by seqrec_rnn_backward_rd).  scratch: T*B*H floats.
+extern "C" int seqrec_rnn_weight_grad_rd(int cell, const float* dxp, const float* hout, const float* cst,
+                                         const float* rec_mask, float* scratch, float* dU, float* db, int T, int B,
+                                         int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && H > 0 && rec_mask && scratch, 1);
+  cudaStream_t st = as_stream(stream);
+  const int G = (cell == SEQREC_CELL_LSTM) ? 4 : (cell == SEQREC_CELL_GRU ? 3 : 1);
+  const int GH = G * H;
+  const int64_t N = (int64_t)T * B;
+  int rc = 0;
+  const int direct = (cell == SEQREC_CELL_GRU) ? 2 : G;      // gate blocks whose operand is h_{t-1} * rm[g]
+  if (T > 1) {
+    const int64_t total = (N - B) * H;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > SEQREC_NUM_SMS * 16) blocks = SEQREC_NUM_SMS * 16;
+    for (int g = 0; g < direct; ++g) {
+      mul_rows_bcast_kernel<<<(int)blocks, 256, 0, st>>>(hout, rec_mask + (size_t)g * B * H, scratch, total,
+                                                         (int64_t)B * H);
+      SEQREC_CHECK_LAUNCH();
+      rc = launch_gemm_tn(scratch, H, dxp + (size_t)B * GH + g * H, GH, dU + g * H, GH, H, H, (int)(N - B), st);
+      if (rc) return rc;
+    }
+  }
+  if (cell == SEQREC_CELL_GRU) {
+    rc = launch_gemm_tn(cst, H, dxp + 2 * H, GH, dU + 2 * H, GH, H, H, (int)N, st);
+    if (rc) return rc;
+  }
+  if (db) {
+    int64_t rpb = (N + 63) / 64;
+    if (rpb < 64) rpb = 64;
+    dim3 grid(ceil_div(GH, 256), ceil_div(N, rpb));
+    colsum_atomic_kernel<<<grid, 256, 0, st>>>(dxp, GH, db, N, GH, rpb);
+    SEQREC_CHECK_LAUNCH();
+  }
+  return 0;
+}

@@ -46,10 +46,14 @@ __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward
-template <int CELL, int ACT, int RB, bool USMEM>
+// RD = recurrent dropout (Keras `recurrent_dropout`, model.py:346,351): G inverted-dropout masks rm[g] (B,H), constant
+// over time, multiply h_{t-1} before the recurrent product of gate block g (GRU candidate: r * h_{t-1} * rm[2]).  The
+// masked copies hm[g] = h * rm[g] are kept in shared memory next to h.
+template <int CELL, int ACT, int RB, bool USMEM, bool RD>
 __global__ void __launch_bounds__(RNN_THREADS, 1)
 rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const uint8_t* __restrict__ mask,
-                   float* __restrict__ hout, float* __restrict__ cst, int T, int B, int H) {
+                   float* __restrict__ hout, float* __restrict__ cst, int T, int B, int H,
+                   const float* __restrict__ rm) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H;
   const int Hp = round_up4(H);
@@ -58,11 +62,15 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
   float* h_s = smem;                 // [RB][Hp]   current hidden state
   float* c_s = h_s + RB * Hp;        // [RB][Hp]   LSTM cell state / GRU r*h
   float* a_s = c_s + RB * Hp;        // [RB][GHp]  pre-activations (GRU: z,r post-activation after phase 1b)
-  float* U_s = a_s + RB * GHp;       // [H][GH]    (USMEM only)
+  float* hm_s = a_s + RB * GHp;      // [G][RB][Hp] h * rm[g] (RD only)
+  float* U_s = hm_s + (RD ? G * RB * Hp : 0);   // [H][GH]    (USMEM only)
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * RB;
 
   for (int i = tid; i < RB * Hp; i += RNN_THREADS) { h_s[i] = 0.f; c_s[i] = 0.f; }
+  if (RD) {
+    for (int i = tid; i < G * RB * Hp; i += RNN_THREADS) hm_s[i] = 0.f;
+  }
   if (USMEM) {
     for (int i = tid; i < H * GH; i += RNN_THREADS) U_s[i] = U[i];
   }
@@ -76,8 +84,9 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
       float acc[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = (b0 + r < B) ? xg[(tok0 + r) * GH + j] : 0.f;
-      if (USMEM) mv_accum<RB>(acc, h_s, Hp, U_s, GH, j, 0, H);
-      else       mv_accum<RB>(acc, h_s, Hp, U, GH, j, 0, H);
+      const float* hv_s = RD ? hm_s + (j / H) * RB * Hp : h_s;   // gate block of column j
+      if (USMEM) mv_accum<RB>(acc, hv_s, Hp, U_s, GH, j, 0, H);
+      else       mv_accum<RB>(acc, hv_s, Hp, U, GH, j, 0, H);
 #pragma unroll
       for (int r = 0; r < RB; ++r) a_s[r * GHp + j] = acc[r];
     }
@@ -90,7 +99,7 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
         const float rr = hard_sigmoid_f(a_s[r * GHp + H + u]);
         a_s[r * GHp + u] = z;
         a_s[r * GHp + H + u] = rr;
-        c_s[r * Hp + u] = rr * h_s[r * Hp + u];
+        c_s[r * Hp + u] = rr * (RD ? hm_s[(2 * RB + r) * Hp + u] : h_s[r * Hp + u]);
       }
       __syncthreads();
       // ---- phase 2: candidate pre-activation
@@ -140,6 +149,10 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
       const float hv = m ? hn : hp;
       h_s[r * Hp + u] = hv;
       hout[tok * H + u] = hv;
+      if (RD) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) hm_s[(g * RB + r) * Hp + u] = hv * rm[((size_t)g * B + b0 + r) * H + u];
+      }
     }
     __syncthreads();
   }
@@ -148,11 +161,11 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
 // ---------------------------------------------------------------------------------------------------------------
 // backward.  Walks t = T-1 .. 0 carrying dh (and dc).  xg holds the saved post-activation gates on entry and the
 // pre-activation gradients dxp on exit.  Ut = U^T (G*H, H).
-template <int CELL, int ACT, int RB, bool USMEM>
+template <int CELL, int ACT, int RB, bool USMEM, bool RD>
 __global__ void __launch_bounds__(RNN_THREADS, 1)
 rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const uint8_t* __restrict__ mask,
                     const float* __restrict__ hout, float* __restrict__ cst, const float* __restrict__ dhout,
-                    int T, int B, int H) {
+                    int T, int B, int H, const float* __restrict__ rm) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H;
   const int Hp = round_up4(H);
@@ -216,7 +229,8 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
         dd_s[r * Hp + u] = dh * z;
         dc_s[r * Hp + u] = rr;
         hp_s[r * Hp + u] = hp;
-        cst[tok * H + u] = rr * hp;  // operand of dU's candidate block
+        // operand of dU's candidate block (with recurrent dropout: r * h_{t-1} * rm[2])
+        cst[tok * H + u] = rr * hp * (RD ? rm[((size_t)2 * B + b0 + r) * H + u] : 1.0f);
       } else {
         const float y = hout[tok * H + u];
         da[u] = dh * act_grad_from_y<ACT>(y);
@@ -236,6 +250,7 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
         for (int r = 0; r < RB; ++r) {
           const float rr = dc_s[r * Hp + k];
           const float hp = hp_s[r * Hp + k];
+          if (RD) acc[r] *= (b0 + r < B) ? rm[((size_t)2 * B + b0 + r) * H + k] : 0.f;   // d(r*h) from d(r*h*rm)
           da_s[r * GHp + H + k] = acc[r] * hp * hard_sigmoid_grad_from_y(rr);
           dd_s[r * Hp + k] += acc[r] * rr;
         }
@@ -248,8 +263,22 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
       float acc[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = dd_s[r * Hp + k];
-      if (USMEM) mv_accum<RB>(acc, da_s, GHp, Ut_s, H, k, 0, J);
-      else       mv_accum<RB>(acc, da_s, GHp, Ut, H, k, 0, J);
+      if (!RD) {
+        if (USMEM) mv_accum<RB>(acc, da_s, GHp, Ut_s, H, k, 0, J);
+        else       mv_accum<RB>(acc, da_s, GHp, Ut, H, k, 0, J);
+      } else {
+        // dL/dh_{t-1} += rm[g] * (da_g . U_g^T), one gate block at a time
+        for (int g = 0; g < J / H; ++g) {
+          float part[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) part[r] = 0.f;
+          if (USMEM) mv_accum<RB>(part, da_s, GHp, Ut_s, H, k, g * H, (g + 1) * H);
+          else       mv_accum<RB>(part, da_s, GHp, Ut, H, k, g * H, (g + 1) * H);
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            if (b0 + r < B) acc[r] = fmaf(part[r], rm[((size_t)g * B + b0 + r) * H + k], acc[r]);
+        }
+      }
 #pragma unroll
       for (int r = 0; r < RB; ++r) dh_s[r * Hp + k] = acc[r];
     }
@@ -273,50 +302,62 @@ static int pick_rb(int B) {
 
 static const size_t kMaxDynSmem = 227 * 1024;
 
-template <int CELL, int ACT, int RB>
-static int launch_fwd(float* xg, const float* U, const uint8_t* mask, float* hout, float* cst, int T, int B, int H,
-                      cudaStream_t st) {
+template <int CELL, int ACT, int RB, bool RD>
+static int launch_fwd_rd(float* xg, const float* U, const uint8_t* mask, float* hout, float* cst, int T, int B, int H,
+                         const float* rm, cudaStream_t st) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H, Hp = round_up4(H), GHp = round_up4(GH);
-  const size_t base = sizeof(float) * (size_t)(2 * RB * Hp + RB * GHp);
+  const size_t base = sizeof(float) * (size_t)(2 * RB * Hp + RB * GHp + (RD ? G * RB * Hp : 0));
   const size_t with_u = base + sizeof(float) * (size_t)H * GH;
   const int grid = ceil_div(B, RB);
   if (with_u <= kMaxDynSmem) {
-    auto k = rnn_forward_kernel<CELL, ACT, RB, true>;
+    auto k = rnn_forward_kernel<CELL, ACT, RB, true, RD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_u);
     if (e != cudaSuccess) return -(int)e;
-    k<<<grid, RNN_THREADS, with_u, st>>>(xg, U, mask, hout, cst, T, B, H);
+    k<<<grid, RNN_THREADS, with_u, st>>>(xg, U, mask, hout, cst, T, B, H, rm);
   } else {
-    auto k = rnn_forward_kernel<CELL, ACT, RB, false>;
+    auto k = rnn_forward_kernel<CELL, ACT, RB, false, RD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
     if (e != cudaSuccess) return -(int)e;
-    k<<<grid, RNN_THREADS, base, st>>>(xg, U, mask, hout, cst, T, B, H);
+    k<<<grid, RNN_THREADS, base, st>>>(xg, U, mask, hout, cst, T, B, H, rm);
   }
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
-
 template <int CELL, int ACT, int RB>
-static int launch_bwd(float* xg, const float* Ut, const uint8_t* mask, const float* hout, float* cst,
-                      const float* dhout, int T, int B, int H, cudaStream_t st) {
+static int launch_fwd(float* xg, const float* U, const uint8_t* mask, float* hout, float* cst, int T, int B, int H,
+                      const float* rm, cudaStream_t st) {
+  return rm ? launch_fwd_rd<CELL, ACT, RB, true>(xg, U, mask, hout, cst, T, B, H, rm, st)
+            : launch_fwd_rd<CELL, ACT, RB, false>(xg, U, mask, hout, cst, T, B, H, nullptr, st);
+}
+
+template <int CELL, int ACT, int RB, bool RD>
+static int launch_bwd_rd(float* xg, const float* Ut, const uint8_t* mask, const float* hout, float* cst,
+                         const float* dhout, int T, int B, int H, const float* rm, cudaStream_t st) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H, Hp = round_up4(H), GHp = round_up4(GH);
   const size_t base = sizeof(float) * (size_t)(4 * RB * Hp + RB * GHp);
   const size_t with_u = base + sizeof(float) * (size_t)H * GH;
   const int grid = ceil_div(B, RB);
   if (with_u <= kMaxDynSmem) {
-    auto k = rnn_backward_kernel<CELL, ACT, RB, true>;
+    auto k = rnn_backward_kernel<CELL, ACT, RB, true, RD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_u);
     if (e != cudaSuccess) return -(int)e;
-    k<<<grid, RNN_THREADS, with_u, st>>>(xg, Ut, mask, hout, cst, dhout, T, B, H);
+    k<<<grid, RNN_THREADS, with_u, st>>>(xg, Ut, mask, hout, cst, dhout, T, B, H, rm);
   } else {
-    auto k = rnn_backward_kernel<CELL, ACT, RB, false>;
+    auto k = rnn_backward_kernel<CELL, ACT, RB, false, RD>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
     if (e != cudaSuccess) return -(int)e;
-    k<<<grid, RNN_THREADS, base, st>>>(xg, Ut, mask, hout, cst, dhout, T, B, H);
+    k<<<grid, RNN_THREADS, base, st>>>(xg, Ut, mask, hout, cst, dhout, T, B, H, rm);
   }
   SEQREC_CHECK_LAUNCH();
   return 0;
+}
+template <int CELL, int ACT, int RB>
+static int launch_bwd(float* xg, const float* Ut, const uint8_t* mask, const float* hout, float* cst,
+                      const float* dhout, int T, int B, int H, const float* rm, cudaStream_t st) {
+  return rm ? launch_bwd_rd<CELL, ACT, RB, true>(xg, Ut, mask, hout, cst, dhout, T, B, H, rm, st)
+            : launch_bwd_rd<CELL, ACT, RB, false>(xg, Ut, mask, hout, cst, dhout, T, B, H, nullptr, st);
 }
 
 #define DISPATCH_RB(FN, CELL, ACT, ...)                                   \
@@ -345,28 +386,24 @@ static int reg_rb(int rb, int H) { return H > 96 ? (rb > 2 ? 2 : rb) : (rb > 4 ?
 
 extern "C" int seqrec_rnn_needs_ut(int cell, int H) { return rnn_reg_applicable(cell, H) ? 0 : 1; }
 
-extern "C" int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8_t* mask, float* hout,
-                                  float* cst, int T, int B, int H, void* stream) {
-  SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
-  cudaStream_t st = as_stream(stream);
+static int rnn_forward_any(int cell, int act, float* xg, const float* U, const uint8_t* mask, float* hout, float* cst,
+                           int T, int B, int H, const float* rm, cudaStream_t st) {
   const int rb = pick_rb(B);
-  if (rnn_reg_applicable(cell, H))
+  if (!rm && rnn_reg_applicable(cell, H))
     return rnn_reg_launch(cell, act, reg_rb(rb, H), true, xg, U, mask, hout, cst, nullptr, T, B, H, st);
   switch (cell) {
-    case SEQREC_CELL_SIMPLE: DISPATCH_ACT(launch_fwd, SEQREC_CELL_SIMPLE, xg, U, mask, hout, cst, T, B, H, st)
-    case SEQREC_CELL_LSTM: DISPATCH_ACT(launch_fwd, SEQREC_CELL_LSTM, xg, U, mask, hout, cst, T, B, H, st)
-    case SEQREC_CELL_GRU: DISPATCH_ACT(launch_fwd, SEQREC_CELL_GRU, xg, U, mask, hout, cst, T, B, H, st)
+    case SEQREC_CELL_SIMPLE: DISPATCH_ACT(launch_fwd, SEQREC_CELL_SIMPLE, xg, U, mask, hout, cst, T, B, H, rm, st)
+    case SEQREC_CELL_LSTM: DISPATCH_ACT(launch_fwd, SEQREC_CELL_LSTM, xg, U, mask, hout, cst, T, B, H, rm, st)
+    case SEQREC_CELL_GRU: DISPATCH_ACT(launch_fwd, SEQREC_CELL_GRU, xg, U, mask, hout, cst, T, B, H, rm, st)
     default: return -1003;
   }
 }
 
-extern "C" int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const float* Ut,
-                                   const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T,
-                                   int B, int H, void* stream) {
-  SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
-  cudaStream_t st = as_stream(stream);
+static int rnn_backward_any(int cell, int act, float* xg, const float* U, const float* Ut, const uint8_t* mask,
+                            const float* hout, float* cst, const float* dhout, int T, int B, int H, const float* rm,
+                            cudaStream_t st) {
   const int rb = pick_rb(B);
-  if (rnn_reg_applicable(cell, H)) {
+  if (!rm && rnn_reg_applicable(cell, H)) {
     SEQREC_ARG(U != nullptr, 2);
     return rnn_reg_launch(cell, act, reg_rb(rb, H), false, xg, U, mask, const_cast<float*>(hout), cst, dhout, T, B,
                           H, st);
@@ -374,9 +411,39 @@ extern "C" int seqrec_rnn_backward(int cell, int act, float* xg, const float* U,
   SEQREC_ARG(Ut != nullptr, 3);
   switch (cell) {
     case SEQREC_CELL_SIMPLE:
-      DISPATCH_ACT(launch_bwd, SEQREC_CELL_SIMPLE, xg, Ut, mask, hout, cst, dhout, T, B, H, st)
-    case SEQREC_CELL_LSTM: DISPATCH_ACT(launch_bwd, SEQREC_CELL_LSTM, xg, Ut, mask, hout, cst, dhout, T, B, H, st)
-    case SEQREC_CELL_GRU: DISPATCH_ACT(launch_bwd, SEQREC_CELL_GRU, xg, Ut, mask, hout, cst, dhout, T, B, H, st)
+      DISPATCH_ACT(launch_bwd, SEQREC_CELL_SIMPLE, xg, Ut, mask, hout, cst, dhout, T, B, H, rm, st)
+    case SEQREC_CELL_LSTM:
+      DISPATCH_ACT(launch_bwd, SEQREC_CELL_LSTM, xg, Ut, mask, hout, cst, dhout, T, B, H, rm, st)
+    case SEQREC_CELL_GRU: DISPATCH_ACT(launch_bwd, SEQREC_CELL_GRU, xg, Ut, mask, hout, cst, dhout, T, B, H, rm, st)
     default: return -1003;
   }
+}
+
+extern "C" int seqrec_rnn_forward(int cell, int act, float* xg, const float* U, const uint8_t* mask, float* hout,
+                                  float* cst, int T, int B, int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
+  return rnn_forward_any(cell, act, xg, U, mask, hout, cst, T, B, H, nullptr, as_stream(stream));
+}
+
+extern "C" int seqrec_rnn_backward(int cell, int act, float* xg, const float* U, const float* Ut,
+                                   const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T,
+                                   int B, int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && H > 0, 1);
+  return rnn_backward_any(cell, act, xg, U, Ut, mask, hout, cst, dhout, T, B, H, nullptr, as_stream(stream));
+}
+
+// Keras `recurrent_dropout` (model.py:346, :351; swept by tune_params.py:83, tune_params_msnbc.py:54,77): rec_mask
+// (G, B, H) holds one inverted-dropout mask per gate block, constant over time.  Always the generic fp32 scan: the
+// tensor-core and register-resident scans share ONE h operand between the gate blocks.
+extern "C" int seqrec_rnn_forward_rd(int cell, int act, float* xg, const float* U, const float* rec_mask,
+                                     const uint8_t* mask, float* hout, float* cst, int T, int B, int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && H > 0 && rec_mask != nullptr, 1);
+  return rnn_forward_any(cell, act, xg, U, mask, hout, cst, T, B, H, rec_mask, as_stream(stream));
+}
+
+extern "C" int seqrec_rnn_backward_rd(int cell, int act, float* xg, const float* Ut, const float* rec_mask,
+                                      const uint8_t* mask, const float* hout, float* cst, const float* dhout, int T,
+                                      int B, int H, void* stream) {
+  SEQREC_ARG(T > 0 && B > 0 && H > 0 && rec_mask != nullptr, 1);
+  return rnn_backward_any(cell, act, xg, nullptr, Ut, mask, hout, cst, dhout, T, B, H, rec_mask, as_stream(stream));
 }

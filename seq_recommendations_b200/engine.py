@@ -69,6 +69,8 @@ class _Work:
         self.loss_sum = torch.zeros(1, dtype=f32, device=dev)
         self.hscale = None
         self.in_scale = None
+        self.rec_mask = None
+        self.rd_scratch = None
         self.x_dense = None
         self.pin_event = None
         self.pin_dirty = False
@@ -130,6 +132,7 @@ class HotPath:
             self.v_lo = self.comm.rank * self.V
         self.dropout_in = 0.0
         self.dropout_out = 0.0
+        self.dropout_rec = 0.0                     # Keras recurrent_dropout (z -> z), model.py:346,351
         # identical seeds on every rank would draw identical dropout masks for different shards: fold the rank in
         self.seed = int(seed) * max(1, self.comm.world) + self.comm.rank
         # dropout stream position, on the device ([0] next offset, [1] kernel-internal ticket): a captured step draws
@@ -480,7 +483,14 @@ class HotPath:
         else:
             call("seqrec_gemm_nn", ptr(w.x_dense), ptr(self.W_in), ptr(self.b), ptr(w.xg), w.N, self.GH, self.F, 0, st)
         self._mark("rnn_fwd")
-        if self.rnn_tc:
+        w.rec_mask = None
+        if training and self.dropout_rec > 0:
+            # one inverted-dropout mask per gate block, (G, B, H), constant over the T steps of this batch; such a step
+            # runs on the generic fp32 scan (the tensor-core / register scans share one h operand between the gates)
+            w.rec_mask = self._dropout((self.G, w.B, self.H), self.dropout_rec)
+            call("seqrec_rnn_forward_rd", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.U), ptr(w.rec_mask),
+                 ptr(w.mask), ptr(w.hout), ptr(w.cst), w.T, w.B, self.H, st)
+        elif self.rnn_tc:
             call("seqrec_split_bf16", ptr(self.U), None, ptr(self.Ut_hi), ptr(self.Ut_lo), self.H, self.GH, self.H, 1,
                  st)
             call("seqrec_rnn_tc_forward", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut_hi), ptr(self.Ut_lo),
@@ -495,6 +505,11 @@ class HotPath:
     def _rnn_backward(self, w):
         """K4: dL/dhout (w.dh) -> dxp in place of the saved gates (w.xg)."""
         st = self.stream
+        if w.rec_mask is not None:
+            call("seqrec_transpose", ptr(self.U), ptr(self.Ut), self.H, self.GH, st)
+            call("seqrec_rnn_backward_rd", CELL[self.cell], ACT[self.act], ptr(w.xg), ptr(self.Ut), ptr(w.rec_mask),
+                 ptr(w.mask), ptr(w.hout), ptr(w.cst), ptr(w.dh), w.T, w.B, self.H, st)
+            return
         if self.rnn_tc:
             call("seqrec_split_bf16", ptr(self.U), None, ptr(self.U_hi), ptr(self.U_lo), self.H, self.GH, self.GH, 0,
                  st)
@@ -509,6 +524,12 @@ class HotPath:
     def _rnn_weight_grad(self, w):
         """dU, db from dxp (w.xg), hout and (GRU) r*h_{t-1} (w.cst)."""
         st = self.stream
+        if w.rec_mask is not None:
+            if w.rd_scratch is None:
+                w.rd_scratch = torch.empty((w.T, w.B, self.H), dtype=torch.float32, device=self.device)
+            call("seqrec_rnn_weight_grad_rd", CELL[self.cell], ptr(w.xg), ptr(w.hout), ptr(w.cst), ptr(w.rec_mask),
+                 ptr(w.rd_scratch), ptr(self.dU), ptr(self.db), w.T, w.B, self.H, st)
+            return
         if self.wgrad_tc:
             if w.D_hi is None:
                 bf = torch.bfloat16
@@ -686,7 +707,7 @@ class HotPath:
         """Everything a captured step bakes in BY VALUE (kernel arguments and which kernels are launched at all)."""
         o = self.opt
         return (o["lr"], o["eps"], o["clipnorm"], tuple(sorted(self.trainable.items())), self.dropout_in,
-                self.dropout_out, self.overlap, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
+                self.dropout_out, self.dropout_rec, self.overlap, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
 
     def _train_core(self, w):
         """forward + backward + exchange + update on the staged batch (everything after the host->device copy).

@@ -607,8 +607,6 @@ class RNNFullModel(BaseRNNModel):
             raise NotImplementedError("only linear -> softmax outputs (the reference's experiments) are built")
         if toy_regularizer is not None:
             raise NotImplementedError("kernel regularisers are only used by non-hot-path branches")
-        if z_to_z_dropout:
-            raise NotImplementedError("recurrent_dropout is 0 in every reference experiment (experiments_server.py)")
         self.timesteps = timesteps
         kinit = y_to_z_initializer if rnn_type == "LSTM" else "glorot_uniform"
         ws = _init_weights(rnn_type, y_dim, z_dim, y_dim, bool(toy_bias), kernel_init=kinit, seed=seed)
@@ -616,6 +614,7 @@ class RNNFullModel(BaseRNNModel):
                       seed=0 if seed is None else seed, vocab_parallel=vocab_parallel)
         hot.dropout_in = float(y_to_z_dropout)
         hot.dropout_out = float(z_to_y_dropout)
+        hot.dropout_rec = float(z_to_z_dropout)    # recurrent_dropout (model.py:346,351; tune_params.py:83)
         rnn_w = ["W_in", "U"] + (["b"] if z_bias else [])
         out_w = ["W_out"] + (["b_out"] if toy_bias else [])
         layers = [_Layer(None, "y_input", []), _Layer(None, "mask1", []), _Layer(None, "dropout_1", []),

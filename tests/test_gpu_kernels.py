@@ -267,6 +267,41 @@ def test_dropout_factors_distribution_and_training_effect():
         assert rel_err(g, r.numpy()) <= TOL
 
 
+@pytest.mark.parametrize("cell,act,V,H,T,B", [("LSTM", "relu", 60, 24, 7, 9), ("GRU", "tanh", 300, 128, 6, 20),
+                                              ("simpleRNN", "relu", 40, 33, 5, 11), ("LSTM", "tanh", 500, 256, 5, 70)])
+def test_recurrent_dropout_matches_oracle_with_the_same_masks(cell, act, V, H, T, B):
+    """Keras `recurrent_dropout` (model.py:346,351; swept by tune_params.py:83, tune_params_msnbc.py:54,77): one
+    inverted-dropout mask per gate block, constant over time, on h_{t-1} before the recurrent product.  The oracle is
+    given the factors the device drew (its RNG stream cannot be Theano's); loss and every gradient must agree -- also
+    for the shapes the tensor-core / register-resident scans would otherwise take (they share one h operand between
+    the gates, so such a step runs on the generic scan)."""
+    hot, ora, _ = make_pair(cell, act, V, H, seed=31, bias_scale=0.1)
+    hot.dropout_rec = 0.3
+    ids, tgt = synthetic.make_batch(V, T, B, seed=32, min_len=1)
+    loss, grads, _ = hot.grad_batch(ids, tgt)
+    w = hot.work(B, T)
+    G = {"simpleRNN": 1, "LSTM": 4, "GRU": 3}[cell]
+    assert tuple(w.rec_mask.shape) == (G, B, H)
+    vals = np.unique(w.rec_mask.cpu().numpy())
+    assert np.allclose(vals, [0.0, 1.0 / 0.7]) and 0.15 < float((w.rec_mask == 0).float().mean().item()) < 0.45
+    rec = [w.rec_mask[g].cpu().double() for g in range(G)]
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0, rec_masks=rec)
+    assert abs(loss - float(rl)) <= TOL * abs(float(rl))
+    for name, g, r in zip(["W_in", "U", "b", "W_out"], grads, rg):
+        assert rel_err(g, r.numpy()) <= TOL, (name, rel_err(g, r.numpy()))
+    # inference phase: no masks (K.in_train_phase), the usual scan
+    a = hot.hidden_batch(ids).cpu().numpy()
+    ref = ora.hidden_states(ids=as_t(ids), mask=as_t(ids) >= 0).numpy()
+    assert rel_err(a, ref) <= TOL
+    # and a captured training step draws NEW masks at every replay
+    hot.set_optimizer("adagrad", lr=0.01, epsilon=1e-8, clipnorm=1.0)
+    seen = []
+    for _ in range(4):
+        hot.train_batch(torch.tensor(ids).cuda(), torch.tensor(tgt).cuda())
+        seen.append(hot.work(B, T).rec_mask.clone())
+    assert not torch.equal(seen[-1], seen[-2])
+
+
 def test_dense_feature_inputs_match_oracle():
     """RNNBaseline with [onehot || xs] features: K2 GEMM input projection instead of the gather."""
     from seq_recommendations_b200.engine import HotPath
