@@ -70,6 +70,14 @@ int seqrec_mark_rows(const int32_t* ids, const uint8_t* mask, int32_t* touched, 
  * C[M,N] (+)= A[M,K] . Bm[K,N] (+ bias[N]); plain fp32 SIMT GEMM for the small feature widths of that model. */
 int seqrec_gemm_nn(const float* A, const float* Bm, const float* bias, float* C, int M, int N, int K,
                    int accumulate, void* stream);
+/* K2 on the tcgen05 tensor cores (csrc/gemm_tc.cu): C[M,N] (+)= A[M,K] . Bt[N,K]^T (+ bias[N]), fp32 C (leading dimension
+ * ldc).  A (M, K; ld lda) and Bt (N, K; ld ldb) are K-major bf16 hi/lo pairs staged by seqrec_split_bf16 (lda, ldb
+ * multiples of 8; lo may be NULL when x3 == 0).  x3 != 0: 3-pass split product, ~2^-16 relative (fp32-grade).  Serves
+ * the dense half of the input projection (x_to_z: model.py:354-358; RNNBaseline with [onehot || xs]: model.py:245-255)
+ * and, with the operands staged transposed, the products of the x_to_y / y_to_y branches and their gradients. */
+int seqrec_gemm_tc(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
+                   const float* bias, float* C, int64_t M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc,
+                   int accumulate, int x3, void* stream);
 /* C[M,N] += A[K,M]^T . Bm[K,N]  (weight gradients: dW = X^T . dY), atomics over K-splits; C must be pre-zeroed */
 int seqrec_gemm_tn_atomic(const float* A, const float* Bm, float* C, int M, int N, int K, void* stream);
 
@@ -223,6 +231,30 @@ int seqrec_topk_tc(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B
  * the oracle).  Ends the vocabulary-parallel ranking (one list per item shard).  n_lists * k <= 384. */
 int seqrec_topk_merge(const float* cand_v, const int32_t* cand_i, int n_lists, int64_t list_stride,
                       int32_t* topk_ids, float* topk_p, int64_t n_rows, int k, void* stream);
+
+/* ---- history-feature / skip branches (csrc/dense_ops.cu): RNNFullModel's x_to_z / x_to_y / y_to_y (model.py:354-358,
+ * :376-392) and NoRecurrenceModel (model.py:264-319).  logits z = hs.W + x.B + A[y_{t-1}] (+ biases) carry per-(token,
+ * item) terms; the reference runs these models on small catalogs ((V,V) transition kernel A), so Z (N,V) is materialised.
+ * Z[n,:] += (ids[n] >= 0 ? table[ids[n],:] : 0) + bias      (one-hot . A == row lookup; table or bias may be NULL) */
+int seqrec_add_rows(float* Z, const float* table, const float* bias, const int32_t* ids, int64_t n_tokens, int V,
+                    void* stream);
+/* per-row max m, sum-exp s and target logit zy (may be NULL) of materialised logits; feed seqrec_ce_finalize, splits 1 */
+int seqrec_softmax_rows_stats(const float* Z, const int32_t* tgt, float* m, float* s, float* zy, int64_t n_tokens,
+                              int V, void* stream);
+/* Z <- (exp(Z - m)/s - onehot(tgt)) * coef, in place (un-normalised, like K6; rows with coef == 0 become zeros) */
+int seqrec_softmax_rows_dlogit(float* Z, const int32_t* tgt, const float* m, const float* s, const float* coef,
+                               int64_t n_tokens, int V, void* stream);
+/* model.predict from materialised time-major logits (T,B,V): batch-major probabilities (B,T,V) */
+int seqrec_softmax_rows_probs(const float* Z, const float* m, const float* s, float* probs_btv, int T, int B, int V,
+                              void* stream);
+/* C[M,N] (=|+=) A[M,K] . Bm[N,K]^T   (fp32 SIMT; dH = dZ . W^T) */
+int seqrec_gemm_nt(const float* A, const float* Bm, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                   int accumulate, void* stream);
+/* out[c] += sum_r in[r,c]   (bias gradients; out pre-zeroed) */
+int seqrec_colsum(const float* in, float* out, int64_t rows, int cols, int ld, void* stream);
+/* OnlyNonZeroDiagonal(dim, skip_rows) (model.py:48-66): zero the off-diagonal entries of the (dim, dim) block below the
+ * first skip_rows rows of the (skip_rows + dim, dim) kernel W; Keras applies it to the updated weights */
+int seqrec_diag_constraint(float* W, int skip_rows, int dim, void* stream);
 
 /* ---- K8: global-norm clip + Adagrad (experiments_methods.py:41) -------------------------------------------------
  * sumsq[0] (double, pre-zeroed) += sum g^2 */

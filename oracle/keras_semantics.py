@@ -283,3 +283,112 @@ def init_weights(rng, cell, F, H, V, out_bias=False):
     if out_bias:
         ws.append(np.zeros(V, dtype=np.float32))
     return ws
+
+
+# ---- history-feature / skip branches ----------------------------------------------------------------------------------
+class SkipModel:
+    """RNNFullModel with ANY branch combination (model.py:322-403) and NoRecurrenceModel (model.py:264-319).
+
+    weights: dict with the arrays the chosen branches own --
+      W_in (F_in, G*H), U (H, G*H), b (G*H)        recurrent layer `z_to_z_output`; F_in = [V if y_to_z] + [Fx if x_to_z],
+                                                   the y rows first (model.py:354 concatenate([masked_y, masked_x]))
+      W_toy ((H if cell) + (Fx if x_to_y), V), b_out (V)   `to_y_output` / `x_to_y_output`; rows [z ; x] (model.py:377)
+      A (V, V), a_bias (V)                         `y_to_y_output` / `y_output`
+    Keras semantics restated: Masking per input; `concatenate` and `add` AND the masks of their masked
+    inputs (the y_to_y Dense of RNNFullModel reads the RAW y_input, model.py:389, and carries no mask); Dropout factors
+    are passed in; OnlyNonZeroDiagonal (model.py:48-66) multiplies the UPDATED kernel by [ones(skip, dim); eye(dim)].
+    cell=None is NoRecurrenceModel: softmax(x.B + A[y_{t-1}])."""
+
+    NAMES = ["W_in", "U", "b", "W_toy", "b_out", "A", "a_bias"]
+
+    def __init__(self, cell, act_name, weights, y_to_z=True, x_to_z=False, x_to_y=False, y_to_y=False, diag_b=True,
+                 dtype=torch.float64):
+        self.cell, self.act, self.dtype = cell, act_name, dtype
+        self.y_to_z, self.x_to_z, self.x_to_y, self.y_to_y, self.diag_b = y_to_z, x_to_z, x_to_y, y_to_y, diag_b
+        self.p = {k: torch.tensor(np.asarray(v), dtype=dtype) for k, v in weights.items() if v is not None}
+        self.accum = None
+
+    def forward(self, p, ids, x, in_drop=None, out_scale=None, rec_masks=None):
+        """Returns logits (B,T,V) and the loss mask (B,T).  ids (B,T) int64 (pad < 0) or None; x (B,T,Fx) or None."""
+        V = (p["A"].shape[0] if "A" in p else p["W_toy"].shape[1])
+        m_y = m_x = Y = None
+        if ids is not None:
+            m_y = ids >= 0
+            Y = torch.nn.functional.one_hot(ids.clamp(min=0), V).to(self.dtype) * m_y.unsqueeze(-1).to(self.dtype)
+        if x is not None:
+            m_x = (x != 0).any(dim=-1)
+            x = x * m_x.unsqueeze(-1).to(self.dtype)
+        z = 0.0
+        masks = []
+        if self.cell is not None:
+            parts, zm = [], []
+            if self.y_to_z:
+                parts.append(Y); zm.append(m_y)
+            if self.x_to_z:
+                parts.append(x); zm.append(m_x)
+            z_in = torch.cat(parts, dim=-1)
+            m_z = zm[0] if len(zm) == 1 else (zm[0] & zm[1])
+            if in_drop is not None:
+                z_in = z_in * in_drop
+            xp = z_in @ p["W_in"]
+            if "b" in p:
+                xp = xp + p["b"]
+            Hout = rnn_forward(xp, p["U"], m_z, self.cell, self.act, rec_masks=rec_masks)
+            if out_scale is not None:
+                Hout = Hout * out_scale
+            toy_in = torch.cat([Hout, x], dim=-1) if self.x_to_y else Hout
+            masks.append(m_z)
+            if self.x_to_y:
+                masks.append(m_x)
+            z = toy_in @ p["W_toy"]
+            if "b_out" in p:
+                z = z + p["b_out"]
+            if self.y_to_y:
+                z = z + Y @ p["A"] + (p["a_bias"] if "a_bias" in p else 0.0)      # raw y_input: no mask of its own
+        else:
+            if self.y_to_y:
+                z = z + Y @ p["A"] + (p["a_bias"] if "a_bias" in p else 0.0)
+                masks.append(m_y)
+            if self.x_to_y:
+                z = z + x @ p["W_toy"] + (p["b_out"] if "b_out" in p else 0.0)
+                masks.append(m_x)
+        m_o = masks[0]
+        for m in masks[1:]:
+            m_o = m_o & m
+        return z, m_o
+
+    def loss(self, ids, x, targets, p=None, **kw):
+        z, m_o = self.forward(self.p if p is None else p, ids, x, **kw)
+        return masked_loss(z, targets, m_o)
+
+    def predict_proba(self, ids, x):
+        with torch.no_grad():
+            z, _ = self.forward(self.p, ids, x)
+            return softmax_probs(z)
+
+    def grads(self, ids, x, targets, **kw):
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in self.p.items()}
+        loss, _, _ = self.loss(ids, x, targets, p=p, **kw)
+        names = [n for n in self.NAMES if n in p]
+        gs = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+        return loss.detach(), {n: (g if g is not None else torch.zeros_like(p[n])) for n, g in zip(names, gs)}
+
+    def constrain(self):
+        """OnlyNonZeroDiagonal on the x rows of `to_y_output` / `x_to_y_output` (model.py:300-301, :379)."""
+        if self.x_to_y and self.diag_b:
+            W = self.p["W_toy"]
+            dim = W.shape[1]
+            skip = W.shape[0] - dim
+            mask = torch.cat([torch.ones(skip, dim, dtype=self.dtype), torch.eye(dim, dtype=self.dtype)], dim=0)
+            self.p["W_toy"] = W * mask
+
+    def train_step(self, ids, x, targets, lr=0.01, epsilon=1e-8, clipnorm=1.0, frozen=(), **kw):
+        loss, g = self.grads(ids, x, targets, **kw)
+        names = [n for n in self.NAMES if n in self.p and n not in frozen]
+        gs, norm = clip_by_global_norm([g[n] for n in names], clipnorm)
+        if self.accum is None:
+            self.accum = {n: torch.zeros_like(v) for n, v in self.p.items()}
+        for n, gc in zip(names, gs):
+            self.p[n], self.accum[n] = adagrad_update(self.p[n], gc, self.accum[n], lr, epsilon)
+        self.constrain()
+        return loss, norm

@@ -28,6 +28,7 @@ SIGNATURES = {
     "seqrec_scatter_add_rows": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_mark_rows": [_p, _p, _p, _p, _p, _l, _i, _p],
     "seqrec_gemm_nn": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "seqrec_gemm_tc": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _l, _l, _l, _i, _i, _p],
     "seqrec_gemm_tn_atomic": [_p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_forward": [_i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
@@ -56,6 +57,13 @@ SIGNATURES = {
     "seqrec_topk": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p],
     "seqrec_topk_tc": [_p] * 11 + [_l, _i, _i, _i, _i, _p],
     "seqrec_topk_merge": [_p, _p, _i, _l, _p, _p, _l, _i, _p],
+    "seqrec_add_rows": [_p, _p, _p, _p, _l, _i, _p],
+    "seqrec_softmax_rows_stats": [_p, _p, _p, _p, _p, _l, _i, _p],
+    "seqrec_softmax_rows_dlogit": [_p, _p, _p, _p, _p, _l, _i, _p],
+    "seqrec_softmax_rows_probs": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "seqrec_gemm_nt": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "seqrec_colsum": [_p, _p, _l, _i, _i, _p],
+    "seqrec_diag_constraint": [_p, _i, _i, _p],
     "seqrec_sumsq": [_p, _l, _p, _p],
     "seqrec_sumsq_rows": [_p, _p, _p, _i, _i, _p, _p],
     "seqrec_adagrad": [_p, _p, _p, _l, _f, _f, _f, _p, _p, _p],

@@ -20,6 +20,7 @@ import torch
 from . import callbacks as cb
 from . import optimizers
 from .engine import GATES, HotPath
+from .engine_dense import DensePath
 from .preprocessor import is_one_hot, to_id_batch
 
 _EPSILON = 1e-7
@@ -125,23 +126,24 @@ class _Layer(object):
 class _Net(object):
     """The object behind `BaseRNNModel.model`: the Keras-`Model` methods the reference calls, on top of HotPath."""
 
-    def __init__(self, hot, layers, rnn_bias=True, seed=None):
+    def __init__(self, hot, layers, rnn_bias=True, seed=None, inputs=("y",)):
         self.hot = hot
         self.layers = layers
         self.rnn_bias = rnn_bias
+        self.input_spec = tuple(inputs)           # which arrays the reference passes: ("y",), ("y", "x") or ("x",)
         self.stop_training = False
         self.metrics_names = ["loss"]
         self.optimizer = None
         self.loss = None
-        if not rnn_bias:
+        if not rnn_bias and "b" in hot.trainable:
             hot.trainable["b"] = False
         for l in layers:
             l._net = self
 
     # ---- weights -------------------------------------------------------------------------------------------------
     def _names(self):
-        names = ["W_in", "U"] + (["b"] if self.rnn_bias else []) + ["W_out"] + (["b_out"] if self.hot.out_bias else [])
-        return names
+        """Weight names in `get_weights()` order = the layers' weights in layer order."""
+        return [n for l in self.layers for n in l._weight_names]
 
     def _get(self, name):
         """Full-width array (the column shards of a vocabulary-parallel model are gathered by HotPath)."""
@@ -252,17 +254,30 @@ class _Net(object):
 
     # ---- batches -------------------------------------------------------------------------------------------------
     def _inputs(self, x):
-        """Reference inputs are an ndarray or a one-element list (experiments_methods.py:209-216: `[x]` for ytoz)."""
+        """Reference inputs are an ndarray or a list (experiments_methods.py:209-216: `[x]` for ytoz, `[x, xs]` when a
+        history-feature branch is on, `xs` alone for the x-only NoRecurrenceModel).  Returns (ids, dense features)."""
+        spec = self.input_spec
         if isinstance(x, (list, tuple)):
-            if len(x) != 1:
-                raise NotImplementedError("history-feature inputs (x_to_z / x_to_y) are not built yet (SURVEY §8(f))")
-            x = x[0]
-        x = np.asarray(x)
-        if x.ndim == 3 and x.shape[2] > 1 and not (x.shape[2] == self.hot.F and is_one_hot(x)):
-            if x.shape[2] != self.hot.F:
-                raise ValueError("input feature width %d does not match the model's %d" % (x.shape[2], self.hot.F))
-            return None, np.ascontiguousarray(x, dtype=np.float32)      # dense-feature path (K2)
-        return to_id_batch(x), None                                       # gather path (K1)
+            if len(x) != len(spec):
+                raise ValueError("this model takes %d input array(s) %s, got %d" % (len(spec), spec, len(x)))
+            arrs = list(x)
+        else:
+            if len(spec) != 1:
+                raise ValueError("this model takes a list of %d input arrays %s" % (len(spec), spec))
+            arrs = [x]
+        ids = xd = None
+        for kind, a in zip(spec, arrs):
+            a = np.asarray(a)
+            if kind == "x":
+                xd = np.ascontiguousarray(a, dtype=np.float32)
+            elif (isinstance(self.hot, HotPath) and a.ndim == 3 and a.shape[2] > 1
+                  and not (a.shape[2] == self.hot.F and is_one_hot(a))):
+                if a.shape[2] != self.hot.F:
+                    raise ValueError("input feature width %d does not match the model's %d" % (a.shape[2], self.hot.F))
+                xd = np.ascontiguousarray(a, dtype=np.float32)         # dense-feature path of RNNBaseline (K2)
+            else:
+                ids = to_id_batch(a)                                   # gather path (K1)
+        return ids, xd
 
     def _slice(self, ids, xd, idx):
         return (ids[idx] if ids is not None else None), (xd[idx] if xd is not None else None)
@@ -576,16 +591,120 @@ class RNNBaseline(BaseRNNModel):
         self.model = _Net(hot, layers)
 
 
+class ArrayInitializer(object):
+    """model.py:32-45: an initializer that returns a given array (the Markov log-transition matrix of
+    experiments_server.py:60-68 for the y -> y kernel)."""
+
+    def __init__(self, values=0):
+        self.values = values
+
+    def __call__(self, shape, dtype=None):
+        return self.values
+
+    def get_config(self):
+        return {"value": self.values}
+
+
+class OnlyNonZeroDiagonal(object):
+    """model.py:48-66 (spec object; the arithmetic is seqrec_diag_constraint, applied to the updated kernel)."""
+
+    def __init__(self, input_dim, skip_cols):
+        self.input_dim = input_dim
+        self.skip_cols = skip_cols
+
+    def get_config(self):
+        return {"input_dim": self.input_dim, "skip_cols": self.skip_cols}
+
+
+only_non_zero_diag = OnlyNonZeroDiagonal
+
+
+def gauss_prior(means, var):
+    raise NotImplementedError("GaussPriorRegularizer (model.py:74-91): every driver of the reference passes "
+                              "y_to_y_regularizer=None / toy_regularizer=None, so kernel regularisers are not built")
+
+
+def _init_kernel(init, rng, shape, default="glorot_uniform"):
+    """Keras-2.0.x kernel initialisers as the reference passes them: a name, an ArrayInitializer-like callable
+    (experiments_server.py:66), or an object with minval/maxval or mean/stddev attributes (tune_params.py:80, :91)."""
+    if init is None:
+        init = default
+    if isinstance(init, str):
+        if init == "glorot_uniform":
+            return _glorot_uniform(rng, shape)
+        if init == "glorot_normal":
+            return _glorot_normal(rng, shape)
+        if init == "random_uniform":
+            return rng.uniform(-0.05, 0.05, size=shape).astype(np.float32)
+        if init == "zeros":
+            return np.zeros(shape, dtype=np.float32)
+        raise NotImplementedError("initializer %r" % (init,))
+    if hasattr(init, "minval") and hasattr(init, "maxval"):
+        return rng.uniform(init.minval, init.maxval, size=shape).astype(np.float32)
+    if hasattr(init, "stddev"):
+        return (getattr(init, "mean", 0.0) + init.stddev * rng.standard_normal(size=shape)).astype(np.float32)
+    if callable(init):
+        v = np.asarray(init(shape), dtype=np.float32)
+        if tuple(v.shape) != tuple(shape):
+            raise ValueError("initializer returned shape %s, the kernel has %s" % (v.shape, tuple(shape)))
+        return v.copy()
+    raise NotImplementedError("initializer %r" % (init,))
+
+
 class NoRecurrenceModel(BaseRNNModel):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("NoRecurrenceModel (model.py:264-319) has no recurrence and is outside the hot path; "
-                                  "it is a SURVEY §8(f) 'next' row")
+    """model.py:264-319: softmax(f(B x_t) + g(A y_{t-1} + c)) without recurrence -- `y_output` = Dense(A) on the masked
+    one-hot y input (a row lookup of A), `x_to_y_output` = Dense(B) on the history features with the diagonal
+    constraint.  Runs on engine_dense.DensePath (materialised logits: these are small-catalog models)."""
+
+    def __init__(self, timesteps, x_dim, y_dim, model_name="y_to_y_model",
+                 y_to_y_activation="linear", x_to_y_activation="linear", y_to_y_w_initializer=None,
+                 out_activation="softmax", mask_value=0.0,
+                 y_bias=False, xy_bias=False, y_to_y_regularizer=None, z_dim=10, z_bias=True, connect_x=True,
+                 connect_y=True, embed_y=False, diag_b=True, seed=None):
+        BaseRNNModel.__init__(self, y_dim, model_name=model_name, rnn_type=None)
+        if not (connect_x or connect_y):
+            raise ValueError("ERROR: the model needs an input! either x or y should be added.")
+        if out_activation != "softmax" or y_to_y_activation != "linear" or x_to_y_activation != "linear":
+            raise NotImplementedError("only linear -> softmax outputs (every driver of the reference) are built")
+        if y_to_y_regularizer is not None:
+            raise NotImplementedError("y_to_y_regularizer is None in every driver of the reference")
+        if embed_y:
+            raise NotImplementedError("embed_y=True is never used by the reference's drivers (run_model_no_recurrence "
+                                      "leaves it False)")
+        if mask_value != 0.0:
+            raise NotImplementedError("mask_value other than 0.0 is never used by the reference")
+        self.timesteps = timesteps
+        rng = np.random.default_rng(seed)
+        ws, layers, inputs = {}, [], []
+        if connect_y:
+            ws["A"] = _init_kernel(y_to_y_w_initializer, rng, (y_dim, y_dim), default="random_uniform")
+            if y_bias:
+                ws["a_bias"] = np.zeros(y_dim, dtype=np.float32)
+            inputs.append("y")
+            layers += [_Layer(None, "y_input", []), _Layer(None, "mask1", []),
+                       _Layer(None, "y_output", ["A"] + (["a_bias"] if y_bias else []))]
+        if connect_x:
+            ws["W_toy"] = _glorot_uniform(rng, (x_dim, y_dim))
+            if xy_bias:
+                ws["b_out"] = np.zeros(y_dim, dtype=np.float32)
+            inputs.append("x")
+            layers += [_Layer(None, "x_input", []), _Layer(None, "mask2", []),
+                       _Layer(None, "x_to_y_output", ["W_toy"] + (["b_out"] if xy_bias else []))]
+        layers.append(_Layer(None, "activation_1", []))
+        hot = DensePath(None, "linear", y_dim, x_dim, 0, ws, x_to_y=connect_x, y_to_y=connect_y, diag_b=diag_b,
+                        seed=0 if seed is None else seed)
+        self.model = _Net(hot, layers, inputs=inputs)
 
 
 class RNNFullModel(BaseRNNModel):
-    """model.py:322-403, `y_to_z`-only variant: Input(T,V) one-hot -> Masking -> Dropout(y_to_z_dropout) ->
-    SimpleRNN/LSTM/GRU(z_dim, activation=z_to_z_activation) -> Dropout(z_to_y_dropout) -> TimeDistributed(Dense(V,
-    linear, use_bias=toy_bias)) -> softmax."""
+    """model.py:322-403.  Input(T,V) one-hot y [and Input(T,x_dim) history features x] -> Masking -> [concatenate] ->
+    Dropout(y_to_z_dropout) -> SimpleRNN/LSTM/GRU(z_dim, activation=z_to_z_activation, recurrent_dropout=z_to_z_dropout)
+    -> Dropout(z_to_y_dropout) -> [concatenate with x] -> TimeDistributed(Dense(V, linear, use_bias=toy_bias)) [+
+    TimeDistributed(Dense(V))(y_input)] -> softmax.
+
+    The `y_to_z`-only variant ("ytoz", experiments_server.py:106-114) is the hot path: engine.HotPath, fused kernels that
+    never materialise the logits, data / vocabulary parallel.  Any other branch combination (x_to_z, x_to_y, y_to_y: the
+    other six recurrent variants of experiments_server.py:116-191) runs on engine_dense.DensePath."""
 
     def __init__(self, timesteps, x_dim, y_dim, z_dim=20, model_name="y_to_y_model", rnn_type='simpleRNN',
                  z_to_z_activation="relu",
@@ -599,27 +718,61 @@ class RNNFullModel(BaseRNNModel):
         BaseRNNModel.__init__(self, y_dim, model_name=model_name, rnn_type=rnn_type)
         if not (x_to_z or y_to_z):
             raise ValueError("ERROR: the model needs an input into z's! either x or y should be added.")
-        if y_to_y or x_to_y or x_to_z or not y_to_z:
-            raise NotImplementedError(
-                "only the y_to_z recurrent path (y_to_z=True, y_to_y=False, x_to_y=False, x_to_z=False; "
-                "experiments_server.py:106-114) is built; the history-feature / skip branches are SURVEY §8(f) rows")
-        if out_activation != "softmax" or xz_to_y_activation != "linear":
+        if out_activation != "softmax" or xz_to_y_activation != "linear" or y_to_y_activation != "linear":
             raise NotImplementedError("only linear -> softmax outputs (the reference's experiments) are built")
-        if toy_regularizer is not None:
-            raise NotImplementedError("kernel regularisers are only used by non-hot-path branches")
+        if toy_regularizer is not None or y_to_y_regularizer is not None:
+            raise NotImplementedError("kernel regularisers are None in every driver of the reference "
+                                      "(experiments_server.py, tune_params*.py)")
         self.timesteps = timesteps
+        rnn_w = ["W_in", "U"] + (["b"] if z_bias else [])
         kinit = y_to_z_initializer if rnn_type == "LSTM" else "glorot_uniform"
-        ws = _init_weights(rnn_type, y_dim, z_dim, y_dim, bool(toy_bias), kernel_init=kinit, seed=seed)
-        hot = HotPath(rnn_type, z_to_z_activation, y_dim, z_dim, y_dim, out_bias=bool(toy_bias), weights=ws, comm=comm,
-                      seed=0 if seed is None else seed, vocab_parallel=vocab_parallel)
+        if y_to_z and not (y_to_y or x_to_y or x_to_z):
+            # ---- the hot path
+            ws = _init_weights(rnn_type, y_dim, z_dim, y_dim, bool(toy_bias), kernel_init=kinit, seed=seed)
+            hot = HotPath(rnn_type, z_to_z_activation, y_dim, z_dim, y_dim, out_bias=bool(toy_bias), weights=ws,
+                          comm=comm, seed=0 if seed is None else seed, vocab_parallel=vocab_parallel)
+            out_w = ["W_out"] + (["b_out"] if toy_bias else [])
+            layers = [_Layer(None, "y_input", []), _Layer(None, "mask1", []), _Layer(None, "dropout_1", []),
+                      _Layer(None, "z_to_z_output", rnn_w), _Layer(None, "dropout_2", []),
+                      _Layer(None, "to_y_output", out_w), _Layer(None, "activation_1", [])]
+            self.model = _Net(hot, layers, rnn_bias=bool(z_bias))
+            if not z_bias:
+                hot.b.zero_()
+        else:
+            # ---- history-feature / skip branches
+            if comm is not None and comm.enabled:
+                raise NotImplementedError("the history-feature variants run in one process (as in the reference)")
+            rng = np.random.default_rng(seed)
+            G = GATES[rnn_type]
+            F_in = (y_dim if y_to_z else 0) + (x_dim if x_to_z else 0)
+            ws = {"W_in": _init_kernel(kinit, rng, (F_in, G * z_dim)),
+                  "U": np.concatenate([_orthogonal(rng, z_dim) for _ in range(G)], axis=1)}
+            if z_bias:
+                ws["b"] = np.zeros(G * z_dim, dtype=np.float32)
+                if rnn_type == "LSTM":
+                    ws["b"][z_dim:2 * z_dim] = 1.0
+            ws["W_toy"] = _glorot_uniform(rng, (z_dim + (x_dim if x_to_y else 0), y_dim))
+            if toy_bias:
+                ws["b_out"] = np.zeros(y_dim, dtype=np.float32)
+            if y_to_y:
+                ws["A"] = _init_kernel(y_to_y_w_initializer, rng, (y_dim, y_dim), default="glorot_uniform")
+                if ytoy_bias:
+                    ws["a_bias"] = np.zeros(y_dim, dtype=np.float32)
+            hot = DensePath(rnn_type, z_to_z_activation, y_dim, x_dim, z_dim, ws, y_to_z=y_to_z, x_to_z=x_to_z,
+                            x_to_y=x_to_y, y_to_y=y_to_y, diag_b=diag_b, seed=0 if seed is None else seed)
+            inputs = (["y"] if (y_to_y or y_to_z) else []) + (["x"] if (x_to_y or x_to_z) else [])
+            layers = []
+            if y_to_y or y_to_z:
+                layers += [_Layer(None, "y_input", []), _Layer(None, "mask1", [])]
+            if x_to_y or x_to_z:
+                layers += [_Layer(None, "x_input", []), _Layer(None, "mask2", [])]
+            layers += [_Layer(None, "dropout_1", []), _Layer(None, "z_to_z_output", rnn_w),
+                       _Layer(None, "dropout_2", []),
+                       _Layer(None, "to_y_output", ["W_toy"] + (["b_out"] if toy_bias else []))]
+            if y_to_y:
+                layers.append(_Layer(None, "y_to_y_output", ["A"] + (["a_bias"] if ytoy_bias else [])))
+            layers.append(_Layer(None, "activation_1", []))
+            self.model = _Net(hot, layers, rnn_bias=True, inputs=inputs)
         hot.dropout_in = float(y_to_z_dropout)
         hot.dropout_out = float(z_to_y_dropout)
         hot.dropout_rec = float(z_to_z_dropout)    # recurrent_dropout (model.py:346,351; tune_params.py:83)
-        rnn_w = ["W_in", "U"] + (["b"] if z_bias else [])
-        out_w = ["W_out"] + (["b_out"] if toy_bias else [])
-        layers = [_Layer(None, "y_input", []), _Layer(None, "mask1", []), _Layer(None, "dropout_1", []),
-                  _Layer(None, "z_to_z_output", rnn_w), _Layer(None, "dropout_2", []),
-                  _Layer(None, "to_y_output", out_w), _Layer(None, "activation_1", [])]
-        self.model = _Net(hot, layers, rnn_bias=bool(z_bias))
-        if not z_bias:
-            hot.b.zero_()
