@@ -29,6 +29,7 @@ import torch
 from . import _lib
 from ._lib import ACT, CELL, call, ptr
 from .dist import Comm, embedding_grad_mode
+from .gemm import gemm
 
 GATES = {"simpleRNN": 1, "LSTM": 4, "GRU": 3}
 NUM_SMS = 148
@@ -481,7 +482,8 @@ class HotPath:
             call("seqrec_gather_rows", ptr(self.W_in), ptr(self.b), ptr(w.ids), ptr(w.mask), ptr(w.in_scale),
                  ptr(w.xg), w.N, self.F, self.GH, st)
         else:
-            call("seqrec_gemm_nn", ptr(w.x_dense), ptr(self.W_in), ptr(self.b), ptr(w.xg), w.N, self.GH, self.F, 0, st)
+            # K2: time-batched dense input projection (RNNBaseline with [onehot || xs]) -- tcgen05 GEMM when it fills tiles
+            gemm(self, w.x_dense.view(w.N, self.F), self.W_in, w.xg.view(w.N, self.GH), "nn", bias=self.b)
         self._mark("rnn_fwd")
         w.rec_mask = None
         if training and self.dropout_rec > 0:
@@ -765,7 +767,7 @@ class HotPath:
                 self._scatter_gathered_rows(w)
         else:
             self.dW_in.zero_()
-            call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
+            gemm(self, w.x_dense.view(w.N, self.F), w.xg.view(w.N, self.GH), self.dW_in, "tn")
             dense_in = comm.enabled
         self._mark("rnn_wgrad")
         if branch_wgrad:
@@ -1028,7 +1030,7 @@ class HotPath:
                  ptr(self.touched), ptr(self.rows), ptr(self.n_rows), w.N, self.F, self.GH, st)
         else:
             self.dW_in.zero_()
-            call("seqrec_gemm_tn_atomic", ptr(w.x_dense), ptr(w.xg), ptr(self.dW_in), self.F, self.GH, w.N, st)
+            gemm(self, w.x_dense.view(w.N, self.F), w.xg.view(w.N, self.GH), self.dW_in, "tn")
         self.check_errors()
         # the kernels leave un-normalised gradients (the optimiser divides by n_valid): normalise here for the caller
         n_valid = float(self.n_valid_f.item())

@@ -23,6 +23,7 @@ from . import _lib
 from ._lib import ACT, CELL, call, ptr
 from .dist import Comm
 from .engine import GATES, _align
+from .gemm import gemm
 
 NAMES = ["W_in", "U", "b", "W_toy", "b_out", "A", "a_bias"]
 
@@ -175,43 +176,7 @@ class DensePath:
 
     # ------------------------------------------------------------------------------------------------ products
     def _gemm(self, A, Bm, C, form, bias=None, accumulate=False):
-        """C (+)= op(A) . op(Bm) (+ bias) on contiguous 2-D fp32 tensors.  form: 'nn' A(M,K).B(K,N); 'nt' A(M,K).B(N,K)^T;
-        'tn' A(K,M)^T.B(K,N) (accumulating: C must hold zeros or a partial sum).  Large products run on the tcgen05 GEMM
-        with operands staged as K-major bf16 hi/lo pairs, small ones on the fp32 SIMT kernels."""
-        st = self.stream
-        if form == "nn":
-            M, K = A.shape
-            N = Bm.shape[1]
-        elif form == "nt":
-            M, K = A.shape
-            N = Bm.shape[0]
-        else:
-            K, M = A.shape
-            N = Bm.shape[1]
-        if self.tc_mode != "off" and M >= 128 and N >= 64 and K >= 32 and M * N * K >= (1 << 24):
-            Kp = (K + 63) // 64 * 64
-            bf = torch.bfloat16
-            x3 = self.tc_x3
-
-            def stage(src, transpose, rows_out):
-                hi = torch.zeros((rows_out, Kp), dtype=bf, device=self.device)
-                lo = torch.zeros((rows_out, Kp), dtype=bf, device=self.device) if x3 else None
-                call("seqrec_split_bf16", ptr(src), None, ptr(hi), ptr(lo), src.shape[0], src.shape[1], Kp,
-                     1 if transpose else 0, st)
-                return hi, lo
-            a_hi, a_lo = stage(A, form == "tn", M)
-            b_hi, b_lo = stage(Bm, form != "nt", N)
-            call("seqrec_gemm_tc", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), ptr(bias), ptr(C), M, N, K, Kp, Kp, N,
-                 1 if (accumulate or form == "tn") else 0, 1 if x3 else 0, st)
-            return
-        if form == "nn":
-            call("seqrec_gemm_nn", ptr(A), ptr(Bm), ptr(bias), ptr(C), M, N, K, 1 if accumulate else 0, st)
-        elif form == "nt":
-            call("seqrec_gemm_nt", ptr(A), ptr(Bm), ptr(C), M, N, K, K, K, N, 1 if accumulate else 0, st)
-            if bias is not None:
-                call("seqrec_add_rows", ptr(C), None, ptr(bias), None, M, N, st)
-        else:
-            call("seqrec_gemm_tn_atomic", ptr(A), ptr(Bm), ptr(C), M, N, K, st)
+        gemm(self, A, Bm, C, form, bias=bias, accumulate=accumulate)
 
     # ------------------------------------------------------------------------------------------------ staging
     def work(self, B, T):

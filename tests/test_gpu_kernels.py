@@ -302,11 +302,12 @@ def test_recurrent_dropout_matches_oracle_with_the_same_masks(cell, act, V, H, T
     assert not torch.equal(seen[-1], seen[-2])
 
 
-def test_dense_feature_inputs_match_oracle():
-    """RNNBaseline with [onehot || xs] features: K2 GEMM input projection instead of the gather."""
+@pytest.mark.parametrize("V,F,H,T,B", [(12, 24, 16, 6, 10), (300, 600, 64, 20, 64)])
+def test_dense_feature_inputs_match_oracle(V, F, H, T, B):
+    """RNNBaseline with [onehot || xs] features: K2 GEMM input projection instead of the gather -- fp32 SIMT at the
+    small shape, the tcgen05 GEMM (csrc/gemm_tc.cu, 3-pass split) at the large one, forward and weight gradient."""
     from seq_recommendations_b200.engine import HotPath
     rng = np.random.default_rng(23)
-    V, F, H, T, B = 12, 24, 16, 6, 10
     ws = synthetic.make_weights("LSTM", V, H, seed=24, out_bias=True, F=F)
     x = (rng.random((B, T, F)) < 0.3).astype(np.float32) * rng.random((B, T, F)).astype(np.float32)
     x[:, :2] = 0.0
