@@ -256,6 +256,19 @@ int seqrec_colsum(const float* in, float* out, int64_t rows, int cols, int ld, v
  * first skip_rows rows of the (skip_rows + dim, dim) kernel W; Keras applies it to the updated weights */
 int seqrec_diag_constraint(float* W, int skip_rows, int dim, void* stream);
 
+/* ---- scoring metrics on the device (csrc/likelihood.cu): P (n_seqs, T) per-step probabilities p(true next item),
+ * right-aligned (a sequence of L steps fills the last L columns); lengths (n_seqs, may be NULL = whole rows);
+ * skip_first drops the first step of every window (count_first_prob=False of the reference).
+ * utils.py:166-178 compute_likelihood: out2[0] += sum over sequences of mean_t -log(clip(p, 1e-7, 1-1e-7)),
+ * out2[1] += sequences with a non-empty window (out2 pre-zeroed; the metric is out2[0] / out2[1]). */
+int seqrec_likelihood(const float* P, const int32_t* lengths, int64_t n_seqs, int T, int skip_first, double* out2,
+                      void* stream);
+/* utils.py:145-163 compute_likelihood_cut (ValLossHistoryCut, model.py:106-112): per sequence the first
+ * ceil(train_percent*L) steps and the last floor((1-train_percent)*L) steps; out4 = {sum, count} of the train parts,
+ * {sum, count} of the val parts (pre-zeroed). */
+int seqrec_likelihood_cut(const float* P, const int32_t* lengths, int64_t n_seqs, int T, int skip_first,
+                          double train_percent, double* out4, void* stream);
+
 /* ---- K8: global-norm clip + Adagrad (experiments_methods.py:41) -------------------------------------------------
  * sumsq[0] (double, pre-zeroed) += sum g^2 */
 int seqrec_sumsq(const float* g, int64_t n, double* sumsq, void* stream);

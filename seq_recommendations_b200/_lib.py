@@ -64,6 +64,8 @@ SIGNATURES = {
     "seqrec_gemm_nt": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_colsum": [_p, _p, _l, _i, _i, _p],
     "seqrec_diag_constraint": [_p, _i, _i, _p],
+    "seqrec_likelihood": [_p, _p, _l, _i, _i, _p, _p],
+    "seqrec_likelihood_cut": [_p, _p, _l, _i, _i, ctypes.c_double, _p, _p],
     "seqrec_sumsq": [_p, _l, _p, _p],
     "seqrec_sumsq_rows": [_p, _p, _p, _i, _i, _p, _p],
     "seqrec_adagrad": [_p, _p, _p, _l, _f, _f, _f, _p, _p, _p],

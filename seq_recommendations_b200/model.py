@@ -21,9 +21,9 @@ from . import callbacks as cb
 from . import optimizers
 from .engine import GATES, HotPath
 from .engine_dense import DensePath
+from .likelihood import compute_likelihood, compute_likelihood_cut  # noqa: F401  (utils.py:145-178, on the device)
 from .preprocessor import is_one_hot, to_id_batch
 
-_EPSILON = 1e-7
 
 
 class ModelResults():
@@ -31,39 +31,6 @@ class ModelResults():
         self.val_loss = val_loss
         self.train_loss = train_loss
         self.epoch = epoch
-
-
-def compute_likelihood_cut(predictions, train_percent, orig_lengths=None, count_first_prob=False):
-    """utils.py:145-163 (per-sequence mean NLL with a within-sequence 70/30 cut)."""
-    assert train_percent <= 1.0, "ERROR: train_percent should be <= 1.0"
-    train_lls, val_lls = [], []
-    for i, pred in enumerate(predictions):
-        sort_pred = pred[:]
-        if not count_first_prob:
-            sort_pred = sort_pred[1:]
-        if orig_lengths is not None:
-            sort_pred = pred[-int(orig_lengths[i]):]
-        seq_length = len(sort_pred)
-        train_elems = int(np.ceil(train_percent * seq_length))
-        val_elems = int(np.floor((1.0 - train_percent) * seq_length))
-        if train_elems > 0:
-            train_lls.append(-np.sum(np.log(sort_pred[0:train_elems])) / train_elems)
-        if val_elems > 0:
-            val_lls.append(-np.sum(np.log(sort_pred[-val_elems:])) / val_elems)
-    return np.sum(train_lls) / len(train_lls), np.sum(val_lls) / len(val_lls)
-
-
-def compute_likelihood(predictions, count_first_prob=False):
-    """utils.py:166-178."""
-    lls = []
-    for pred in predictions:
-        sort_pred = pred[:]
-        if not count_first_prob:
-            sort_pred = sort_pred[1:]
-        sort_pred = np.clip(sort_pred, _EPSILON, 1.0 - _EPSILON)
-        if len(sort_pred) > 0:
-            lls.append(-np.sum(np.log(sort_pred)) / len(sort_pred))
-    return np.mean(lls)
 
 
 class ValLossHistoryCut(cb.Callback):
@@ -81,7 +48,7 @@ class ValLossHistoryCut(cb.Callback):
             logs["my_loss"] = 0.0
 
     def on_epoch_end(self, epoch, logs=None):
-        p = self.model.predict_target_prob(self.val_data[0], self.val_data[1])
+        p = self.model.predict_target_prob(self.val_data[0], self.val_data[1], device=True)   # stays in HBM
         _, val_neg_ll = compute_likelihood_cut(p, 0.7, orig_lengths=self.orig_seqs_lengths)
         self.val_lossses.append(val_neg_ll)
         if logs is not None:
@@ -437,16 +404,19 @@ class _Net(object):
         return np.concatenate(out, axis=0)
 
     # ---- additive scoring API --------------------------------------------------------------------------------------
-    def predict_target_prob(self, x, y, batch_size=1024):
-        """(N,T) p(true next item), clipped to [1e-7, 1-1e-7]; pads give 1e-7 (model.py:108-110 semantics)."""
+    def predict_target_prob(self, x, y, batch_size=1024, device=False):
+        """(N,T) p(true next item), clipped to [1e-7, 1-1e-7]; pads give 1e-7 (model.py:108-110 semantics).
+        device=True returns the device tensor (the likelihood metrics reduce it in HBM)."""
         ids, xd = self._inputs(x)
         tgt = to_id_batch(y)
         out = []
         for lo in range(0, len(tgt), batch_size):
             hi = min(len(tgt), lo + batch_size)
             i, d = self._slice(ids, xd, slice(lo, hi))
-            out.append(self.hot.target_prob_batch(i, tgt[lo:hi], d).cpu().numpy())
-        return np.concatenate(out, axis=0)
+            out.append(self.hot.target_prob_batch(i, tgt[lo:hi], d).clone())
+        out = torch.cat(out, dim=0)
+        self.hot.check_errors()
+        return out if device else out.cpu().numpy()
 
     def predict_topk(self, x, k=20, last_step_only=True, batch_size=1024):
         """Top-k next-item ids (int32) and probabilities; ties broken by the lower item id."""

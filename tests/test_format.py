@@ -87,6 +87,9 @@ def test_to_id_batch_edge_cases():
 
 
 def test_likelihood_metrics_match_reference(golden_dir):
+    """The numpy restatement (oracle/likelihood.py: the checker of the device reductions) against the reference's own
+    utils.py."""
+    from oracle import likelihood as m
     g = load(golden_dir, "likelihood.npz")
     preds = unragged(g["preds"], g["offs"])
     assert np.isclose(m.compute_likelihood(preds, count_first_prob=False), g["ll"], rtol=1e-12)

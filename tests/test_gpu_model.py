@@ -175,11 +175,50 @@ def test_baseline_model_with_history_features():
 
 
 def test_unsupported_branches_raise():
+    M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4)                 # reference defaults (y_to_y / x_to_y branches) build
+    M.NoRecurrenceModel(5, 4, 4)
+    with pytest.raises(NotImplementedError):                      # what no driver of the reference ever passes
+        M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4, toy_regularizer=object())
     with pytest.raises(NotImplementedError):
-        M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4)             # reference defaults: y_to_y / x_to_y branches
-    with pytest.raises(NotImplementedError):
-        M.NoRecurrenceModel(5, 4, 4)
+        M.NoRecurrenceModel(5, 4, 4, embed_y=True)
+    with pytest.raises(ValueError):
+        M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4, y_to_z=False, x_to_z=False)
     m = M.RNNFullModel(timesteps=5, x_dim=4, y_dim=4, y_to_z=True, y_to_y=False, x_to_y=False, x_to_z=False)
     m.compile_model()                                              # 'adam' string is accepted at compile time ...
     with pytest.raises(NotImplementedError):
         m.fit_model(np.zeros((2, 5, 4)), np.zeros((2, 5, 4)), verbose=0)   # ... but the reference never trains with it
+
+
+def test_device_likelihood_metrics_match_golden_and_oracle(golden_dir):
+    """compute_likelihood / compute_likelihood_cut (utils.py:145-178) as device reductions: against the fixture produced
+    by the REFERENCE's own utils.py (tests/golden/likelihood.npz) and against the numpy restatement on random ragged and
+    padded inputs; probabilities travel as float32 (what the scoring kernels produce), hence 1e-6."""
+    import os
+    from oracle import likelihood as ol
+    g = np.load(os.path.join(golden_dir, "likelihood.npz"))
+    preds = [g["preds"][g["offs"][i]:g["offs"][i + 1]] for i in range(len(g["offs"]) - 1)]
+    assert np.isclose(M.compute_likelihood(preds, count_first_prob=False), g["ll"], rtol=1e-6)
+    assert np.isclose(M.compute_likelihood(preds, count_first_prob=True), g["ll_first"], rtol=1e-6)
+    tr, va = M.compute_likelihood_cut(preds, 0.7, count_first_prob=False)
+    assert np.isclose(tr, g["cut_tr"], rtol=1e-6) and np.isclose(va, g["cut_va"], rtol=1e-6)
+    tr, va = M.compute_likelihood_cut(g["padded"], 0.7, orig_lengths=g["lengths"])
+    assert np.isclose(tr, g["cut_tr_l"], rtol=1e-6) and np.isclose(va, g["cut_va_l"], rtol=1e-6)
+    rng = np.random.default_rng(2)
+    n, T = 300, 37
+    lengths = rng.integers(1, T + 1, size=n)
+    padded = np.full((n, T), 1e-7, dtype=np.float32)
+    for i, L in enumerate(lengths):
+        padded[i, T - L:] = rng.uniform(1e-4, 0.999, size=L)
+    for tp in (0.7, 0.5, 1.0):
+        a = M.compute_likelihood_cut(padded, tp, orig_lengths=lengths)
+        b = ol.compute_likelihood_cut(padded.astype(np.float64), tp, orig_lengths=lengths)
+        assert np.allclose(a, b, rtol=1e-6, equal_nan=True), (tp, a, b)
+        a = M.compute_likelihood_cut(torch.tensor(padded).cuda(), tp, orig_lengths=lengths)      # device tensor in
+        assert np.allclose(a, b, rtol=1e-6, equal_nan=True)
+    ragged = [padded[i, T - L:] for i, L in enumerate(lengths)]
+    for first in (False, True):
+        assert np.isclose(M.compute_likelihood(ragged, count_first_prob=first),
+                          ol.compute_likelihood([r.astype(np.float64) for r in ragged], count_first_prob=first), rtol=1e-6)
+        a = M.compute_likelihood_cut(ragged, 0.7, count_first_prob=first)
+        b = ol.compute_likelihood_cut([r.astype(np.float64) for r in ragged], 0.7, count_first_prob=first)
+        assert np.allclose(a, b, rtol=1e-6)

@@ -199,7 +199,12 @@ def test_reference_facing_classes_run_the_experiment_variants():
     from seq_recommendations_b200.preprocessor import FullModelPreprocessor
     rng = np.random.default_rng(3)
     V, T = 9, 8
-    seqs = [rng.integers(0, V, size=rng.integers(3, T + 2)).tolist() for _ in range(40)]
+    seqs = []
+    for _ in range(40):                                # a learnable chain: next = cur + 1 (mod V) with probability 0.8
+        s = [int(rng.integers(0, V))]
+        for _ in range(int(rng.integers(2, T + 1))):
+            s.append((s[-1] + 1) % V if rng.random() < 0.8 else int(rng.integers(0, V)))
+        seqs.append(s)
     xs = []
     for s in seqs:                                     # datasets.build_xs(freq=True) + log(x + 1)
         cnt, rows = np.zeros(V), []
