@@ -153,10 +153,12 @@ int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const float* zy, co
 /* seqrec_ce_finalize plus the masked mean Keras reports (weighted loss / number of unmasked steps, training.py
  * `_weighted_masked_objective` as used by model.py:397): n_valid[0] = unmasked tokens (int32, device);
  * n_valid_f[0] = (float)n_valid (the denominator the optimiser divides the un-normalised gradients by -- summed over
- * ranks in a data-parallel step), loss_mean[0] = loss_sum / n_valid. */
+ * ranks in a data-parallel step), loss_mean[0] = loss_sum / n_valid.  n_tokens_dev (may be NULL): compacted token axis --
+ * the number of tokens to process is read on the device and n_tokens is only the upper bound (splits must be 1). */
 int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
                             float* s_out, float* ce, float* py, float* coef, float* loss_sum, const int32_t* n_valid,
-                            float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits, void* stream);
+                            float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits,
+                            const int32_t* n_tokens_dev, void* stream);
 
 /* ---- K6: backward of K5 with recomputed logits ------------------------------------------------------------------
  * dlogit[n,v] = (exp(z-m)/s - [v==tgt]) * coef[n] * inv_nvalid[0];
@@ -189,7 +191,8 @@ int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint
                           const int32_t* tgt, const float* m, const float* s, const float* coef,
                           const float* inv_nvalid, const float* hscale, float* dh, float* dW_out, int64_t n_tokens,
                           int H, int Hk, int V, int Vp, int64_t Np, int v_begin, int v_end, int ldw,
-                          int accumulate_dh, int x3, const float* b_out, float* db_out, void* stream);
+                          int accumulate_dh, int x3, const float* b_out, float* db_out, const int32_t* n_tokens_dev,
+                          void* stream);
 /* ---- K5 + K6 (dH half) from ONE logits pass (csrc/ce_tc.cu, TS_FUSED) -----------------------------------------
  * The softmax is evaluated against a per-token REFERENCE logit ref[n] (the exact fp32 target logit from
  * seqrec_target_logit) instead of the running row maximum -- exp(z - ref) needs no rescaling (ref is one of the row's
@@ -197,18 +200,33 @@ int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo, const uint
  *     acc[n,:] += sum_v exp(z[n,v] - ref[n]) . W_out[:,v]          s[n] += sum_v exp(z[n,v] - ref[n])
  * against the same reference and both leave through reductions: acc (N,H) and s (N) must be ZERO on entry.
  * Then seqrec_ce_finalize(ws_m = ref, ws_s = s, splits = 1) gives loss / clip coefficient, and seqrec_ce_dh_finish
- *     dh[n,:] = coef[n] . (acc[n,:] / s[n] - W_out[:, tgt[n]]) (. hscale[n,:])          in place over acc
+ *     dh[n,:] = coef[n] . (acc[n,:] / s[n] - W_out[:, tgt[n]]) (. hscale[n,:])          (dh may alias acc)
  * (tgt[n] < 0: no one-hot term -- the target belongs to another item shard; coef[n] == 0: zeros).  With the
  * item-stationary dW kernel (seqrec_ce_tc_backward with dh = NULL, m = ref) a training step issues 4 logits-sized GEMMs
  * for 3 algorithmic ones instead of 5.  Operands as for seqrec_ce_tc_backward. */
 int seqrec_ce_tc_fused(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
                        const uint16_t* W_hi, const uint16_t* W_lo, const float* ref, const uint8_t* mask,
                        const float* b_out, float* acc, float* s, int64_t n_tokens, int H, int Hk, int V, int Vp,
-                       int v_begin, int v_end, int x3, void* stream);
-int seqrec_ce_dh_finish(float* dh, const float* s, const float* coef, const int32_t* tgt, const uint16_t* Bt_hi,
-                        const uint16_t* Bt_lo, const float* hscale, int64_t n_tokens, int H, int Hk, void* stream);
+                       int v_begin, int v_end, int x3, const int32_t* n_tokens_dev, void* stream);
+int seqrec_ce_dh_finish(const float* acc, float* dh, const float* s, const float* coef, const int32_t* tgt,
+                        const uint16_t* Bt_hi, const uint16_t* Bt_lo, const float* hscale, int64_t n_tokens, int H,
+                        int Hk, const int32_t* orig, const int32_t* n_tokens_dev, void* stream);
+
+/* ---- token compaction: pad tokens carry neither loss nor gradient, so the logits kernels of a training step run on
+ * the VALID tokens only (a quarter fewer rows in all three logits GEMMs at the synthetic BASELINE workloads, whose
+ * lengths are uniform in [T/2, T]).  orig[c] = time-major index of the c-th valid token in ascending order, tgt_c[c] =
+ * its target, count[0] = number of valid tokens; block_counts: scratch of ceil(n_tokens / 256) int32.  The kernels
+ * above take the count as `n_tokens_dev` (read on the device; their n_tokens argument is then the upper bound the TMA
+ * descriptors are built for) and `orig` where a compacted row maps back to a row of hout / dh; mask may then be NULL.
+ * seqrec_split_bf16_both_rows stages the compacted operand rows: output row r < n_rows[0] is source row orig[r]. */
+int seqrec_compact_tokens(const uint8_t* mask, const int32_t* tgt, int64_t n_tokens, int32_t* orig, int32_t* tgt_c,
+                          int32_t* count, int32_t* block_counts, void* stream);
+int seqrec_split_bf16_both_rows(const float* src, const float* scale, const int32_t* orig, const int32_t* n_rows,
+                                uint16_t* hi, uint16_t* lo, uint16_t* hi_t, uint16_t* lo_t, int64_t max_rows,
+                                int64_t cols, int64_t ld_out, int64_t ld_t, void* stream);
 int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
-                        const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream);
+                        const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, const int32_t* orig,
+                        const int32_t* n_tokens_dev, void* stream);
 
 /* ---- K9: scoring (model.py:194-195 predict; model.py:106-112 consumer) ------------------------------------------
  * full probabilities, batch-major (B,T,V) float32, for catalogs small enough to materialise */

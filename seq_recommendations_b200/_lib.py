@@ -45,14 +45,16 @@ SIGNATURES = {
     "seqrec_transpose": [_p, _p, _i, _i, _p],
     "seqrec_ce_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_finalize": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
-    "seqrec_ce_finalize_mean": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
+    "seqrec_ce_finalize_mean": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p, _p],
     "seqrec_ce_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_tc_forward": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
     "seqrec_ce_tc_partials": [_l, _i, _i],
-    "seqrec_ce_tc_backward": [_p] * 16 + [_l, _i, _i, _i, _i, _l, _i, _i, _i, _i, _i, _p, _p, _p],
-    "seqrec_ce_tc_fused": [_p] * 11 + [_l, _i, _i, _i, _i, _i, _i, _i, _p],
-    "seqrec_ce_dh_finish": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
-    "seqrec_target_logit": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
+    "seqrec_ce_tc_backward": [_p] * 16 + [_l, _i, _i, _i, _i, _l, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "seqrec_ce_tc_fused": [_p] * 11 + [_l, _i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "seqrec_ce_dh_finish": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p, _p],
+    "seqrec_compact_tokens": [_p, _p, _l, _p, _p, _p, _p, _p],
+    "seqrec_split_bf16_both_rows": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _p],
+    "seqrec_target_logit": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p, _p],
     "seqrec_predict_probs": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "seqrec_topk": [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p],
     "seqrec_topk_tc": [_p] * 11 + [_l, _i, _i, _i, _i, _p],

@@ -167,7 +167,10 @@ ce_finalize_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_
                    const uint8_t* __restrict__ mask, float* __restrict__ m_out, float* __restrict__ s_out,
                    float* __restrict__ ce, float* __restrict__ py, float* __restrict__ coef,
                    float* __restrict__ loss_sum, const int32_t* __restrict__ n_valid, float* __restrict__ n_valid_f,
-                   float* __restrict__ loss_mean, int64_t n_tokens, int splits) {
+                   float* __restrict__ loss_mean, int64_t n_tokens, int splits,
+                   const int32_t* __restrict__ n_tokens_dev) {
+  // compacted token axis (splits == 1 there): the number of tokens is read on the device
+  if (n_tokens_dev) n_tokens = min(n_tokens, (int64_t)n_tokens_dev[0]);
   __shared__ double red[FIN_THREADS / 32];
   __shared__ bool is_last;
   double local = 0.0;
@@ -522,13 +525,14 @@ int ce_backward_simt(const float* hout, const float* hscale, const float* W_out,
 
 static int ce_finalize_launch(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask, float* m_out,
                               float* s_out, float* ce, float* py, float* coef, float* loss_sum, const int32_t* n_valid,
-                              float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits, void* stream) {
+                              float* n_valid_f, float* loss_mean, int64_t n_tokens, int splits,
+                              const int32_t* n_tokens_dev, void* stream) {
   SEQREC_ARG(n_tokens > 0 && splits > 0, 1);
   int blocks = (int)((n_tokens + FIN_THREADS - 1) / FIN_THREADS);   // one token per thread while the grid allows it
   if (blocks > FIN_MAX_BLOCKS) blocks = FIN_MAX_BLOCKS;
   ce_finalize_kernel<<<blocks, FIN_THREADS, 0, as_stream(stream)>>>(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef,
                                                                    loss_sum, n_valid, n_valid_f, loss_mean, n_tokens,
-                                                                   splits);
+                                                                   splits, n_tokens_dev);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -537,16 +541,17 @@ extern "C" int seqrec_ce_finalize(const float* ws_m, const float* ws_s, const fl
                                   float* m_out, float* s_out, float* ce, float* py, float* coef, float* loss_sum,
                                   int64_t n_tokens, int splits, void* stream) {
   return ce_finalize_launch(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef, loss_sum, nullptr, nullptr, nullptr,
-                            n_tokens, splits, stream);
+                            n_tokens, splits, nullptr, stream);
 }
 
 extern "C" int seqrec_ce_finalize_mean(const float* ws_m, const float* ws_s, const float* zy, const uint8_t* mask,
                                        float* m_out, float* s_out, float* ce, float* py, float* coef, float* loss_sum,
                                        const int32_t* n_valid, float* n_valid_f, float* loss_mean, int64_t n_tokens,
-                                       int splits, void* stream) {
+                                       int splits, const int32_t* n_tokens_dev, void* stream) {
   SEQREC_ARG(n_valid != nullptr, 11);
+  SEQREC_ARG(n_tokens_dev == nullptr || splits == 1, 12);
   return ce_finalize_launch(ws_m, ws_s, zy, mask, m_out, s_out, ce, py, coef, loss_sum, n_valid, n_valid_f, loss_mean,
-                            n_tokens, splits, stream);
+                            n_tokens, splits, n_tokens_dev, stream);
 }
 
 extern "C" int seqrec_predict_probs(const float* hout, const float* W_out, const float* b_out, const float* m,

@@ -795,7 +795,11 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
                          const float* __restrict__ inv_nvalid, const float* __restrict__ hscale,
                          float* __restrict__ out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
                          uint32_t smem_bytes, const float* __restrict__ b_out, float* __restrict__ db_out,
-                         const uint8_t* __restrict__ tok_mask, float* __restrict__ s_out) {
+                         const uint8_t* __restrict__ tok_mask, float* __restrict__ s_out,
+                         const int32_t* __restrict__ n_tokens_dev) {
+  // compacted token axis: the number of (valid) tokens is only known on the device; the argument is then the upper bound
+  // the TMA descriptors were built for
+  if (n_tokens_dev) n_tokens = min(n_tokens, (int64_t)n_tokens_dev[0]);
   constexpr bool ITEM_ST = MODE == TS_DW;
   constexpr bool FUSED = MODE == TS_FUSED;
   using C = TsCfg<KB, X3>;
@@ -1017,7 +1021,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         if (FUSED) {                                         // exp(z - ref) un-normalised, no one-hot term
           const int64_t n = (int64_t)sh.outer(w) * BM + row;
           rt.nb = -INFINITY; rt.scale = 0.f; rt.cf = 0.f; rt.tg = -1;
-          if (n < n_tokens && tok_mask[n]) { rt.nb = -mrow[n] * LOG2E; rt.scale = 1.f; }
+          if (n < n_tokens && (tok_mask == nullptr || tok_mask[n])) { rt.nb = -mrow[n] * LOG2E; rt.scale = 1.f; }
           s_acc = 0.f;
         }
         if (ITEM_ST) {
@@ -1130,16 +1134,19 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
 __global__ void __launch_bounds__(256)
 target_logit_kernel(const float* __restrict__ hout, const float* __restrict__ hscale,
                     const float* __restrict__ W_out, const float* __restrict__ b_out,
-                    const int32_t* __restrict__ tgt, float* __restrict__ zy, int64_t n_tokens, int H, int ldw) {
+                    const int32_t* __restrict__ tgt, float* __restrict__ zy, int64_t n_tokens, int H, int ldw,
+                    const int32_t* __restrict__ orig, const int32_t* __restrict__ n_tokens_dev) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n_tokens_dev) n_tokens = min(n_tokens, (int64_t)n_tokens_dev[0]);
   if (n >= n_tokens) return;
   const int32_t t = tgt[n];
-  if (t < 0) return;
+  if (t < 0) { if (orig && lane == 0) zy[n] = 0.f; return; }
+  const int64_t r = orig ? orig[n] : n;                      // compacted token axis: row of hout behind token n
   float acc = 0.f;
   for (int h = lane; h < H; h += 32) {
-    float x = hout[n * H + h];
-    if (hscale) x *= hscale[n * H + h];
+    float x = hout[r * H + h];
+    if (hscale) x *= hscale[r * H + h];
     acc = fmaf(x, __ldg(W_out + (size_t)h * ldw + t), acc);
   }
   acc = warp_sum(acc);
@@ -1178,7 +1185,7 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
                   const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo, const int32_t* tgt,
                   const float* m, const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
                   float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw, const float* b_out,
-                  float* db_out, const uint8_t* tok_mask, float* s_out, cudaStream_t st) {
+                  float* db_out, const uint8_t* tok_mask, float* s_out, const int32_t* n_tokens_dev, cudaStream_t st) {
   using C = TsCfg<KB, X3>;
   size_t smem = (size_t)C::SMEM_NEED + 1024;                 // slack for the 1024-byte alignment of the tiles
   if (smem > 227 * 1024) smem = 227 * 1024;                  // (the kernel traps if the aligned layout does not fit)
@@ -1186,7 +1193,8 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
   k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
-                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out, tok_mask, s_out);
+                                    n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out, tok_mask, s_out,
+                                    n_tokens_dev);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -1195,10 +1203,11 @@ int launch_ts(int KB, bool x3, int mode, int grid, const CUtensorMap& x_hi, cons
               const CUtensorMap& y_hi, const CUtensorMap& y_lo, const CUtensorMap& z_hi, const CUtensorMap& z_lo,
               const int32_t* tgt, const float* m, const float* s, const float* coef, const float* inv_nvalid,
               const float* hscale, float* out, int64_t n_tokens, int H, int v_begin, int v_end, int ldw,
-              const float* b_out, float* db_out, const uint8_t* tok_mask, float* s_out, cudaStream_t st) {
+              const float* b_out, float* db_out, const uint8_t* tok_mask, float* s_out, const int32_t* n_tokens_dev,
+              cudaStream_t st) {
 #define TS3(KBV, X3V, MV)                                                                                          \
   return launch_ts_one<KBV, X3V, MV>(grid, x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, \
-                                     out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, tok_mask, s_out, st)
+                                     out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, tok_mask, s_out, n_tokens_dev, st)
 #define TS2(KBV)                                                                           \
   {                                                                                        \
     if (x3) {                                                                              \
@@ -1291,10 +1300,11 @@ extern "C" int seqrec_topk_merge(const float* cand_v, const int32_t* cand_i, int
 
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int seqrec_target_logit(const float* hout, const float* hscale, const float* W_out, const float* b_out,
-                                   const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw, void* stream) {
+                                   const int32_t* tgt, float* zy, int64_t n_tokens, int H, int ldw,
+                                   const int32_t* orig, const int32_t* n_tokens_dev, void* stream) {
   SEQREC_ARG(n_tokens > 0 && H > 0 && ldw > 0, 1);
   target_logit_kernel<<<ceil_div(n_tokens * 32, 256), 256, 0, as_stream(stream)>>>(hout, hscale, W_out, b_out, tgt, zy,
-                                                                                  n_tokens, H, ldw);
+                                                                                  n_tokens, H, ldw, orig, n_tokens_dev);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }
@@ -1340,7 +1350,7 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
                                      const float* s, const float* coef, const float* inv_nvalid, const float* hscale,
                                      float* dh, float* dW_out, int64_t n_tokens, int H, int Hk, int V, int Vp,
                                      int64_t Np, int v_begin, int v_end, int ldw, int accumulate_dh, int x3,
-                                     const float* b_out, float* db_out, void* stream) {
+                                     const float* b_out, float* db_out, const int32_t* n_tokens_dev, void* stream) {
   SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
   SEQREC_ARG((Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256) && H <= Hk, 2);
   SEQREC_ARG(Vp >= V && Vp % 8 == 0 && Np >= n_tokens && Np % 8 == 0 && ldw >= v_end, 3);
@@ -1362,14 +1372,14 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
     if ((rc = make_tmap(&w_hi, W_hi, Hk, V, Vp, 128))) return rc;
     if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
     if ((rc = launch_ts(KB, x3 != 0, TS_DH, grid_ts, a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, tgt, m, s, coef, inv_nvalid,
-                        hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, nullptr, nullptr, st)))
+                        hscale, dh, n_tokens, H, v_begin, v_end, ldw, b_out, nullptr, nullptr, nullptr, n_tokens_dev, st)))
       return rc;
   }
   if (dW_out) {
     if ((rc = make_tmap(&t_hi, Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     if ((rc = make_tmap(&t_lo, x3 ? Ht_lo : Ht_hi, Hk, n_tokens, Np, 128))) return rc;
     if ((rc = launch_ts(KB, x3 != 0, TS_DW, grid_ts, b_hi, b_lo, a_hi, a_lo, t_hi, t_lo, tgt, m, s, coef, inv_nvalid,
-                        nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, nullptr, nullptr, st)))
+                        nullptr, dW_out, n_tokens, H, v_begin, v_end, ldw, b_out, db_out, nullptr, nullptr, n_tokens_dev, st)))
       return rc;
   }
   return 0;
@@ -1387,10 +1397,10 @@ extern "C" int seqrec_ce_tc_backward(const uint16_t* A_hi, const uint16_t* A_lo,
 extern "C" int seqrec_ce_tc_fused(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* Bt_hi, const uint16_t* Bt_lo,
                                   const uint16_t* W_hi, const uint16_t* W_lo, const float* ref, const uint8_t* mask,
                                   const float* b_out, float* acc, float* s, int64_t n_tokens, int H, int Hk, int V,
-                                  int Vp, int v_begin, int v_end, int x3, void* stream) {
+                                  int Vp, int v_begin, int v_end, int x3, const int32_t* n_tokens_dev, void* stream) {
   SEQREC_ARG(n_tokens > 0 && V > 0 && v_begin >= 0 && v_begin < v_end && v_end <= V, 1);
   SEQREC_ARG((Hk == 64 || Hk == 128 || Hk == 192 || Hk == 256) && H <= Hk, 2);
-  SEQREC_ARG(Vp >= V && Vp % 8 == 0 && ref && mask && acc && s, 3);
+  SEQREC_ARG(Vp >= V && Vp % 8 == 0 && ref && acc && s, 3);
   SEQREC_ARG(A_hi && Bt_hi && W_hi && (!x3 || (A_lo && Bt_lo && W_lo)), 4);
   cudaStream_t st = as_stream(stream);
   CUtensorMap a_hi, a_lo, b_hi, b_lo, w_hi, w_lo;
@@ -1403,21 +1413,26 @@ extern "C" int seqrec_ce_tc_fused(const uint16_t* A_hi, const uint16_t* A_lo, co
   if ((rc = make_tmap(&w_lo, x3 ? W_lo : W_hi, Hk, V, Vp, 128))) return rc;
   const int64_t total = ((n_tokens + BM - 1) / BM) * ceil_div(v_end - v_begin, BN);
   return launch_ts(Hk / KBLK, x3 != 0, TS_FUSED, persistent_grid(total), a_hi, a_lo, b_hi, b_lo, w_hi, w_lo, nullptr, ref,
-                   nullptr, nullptr, nullptr, nullptr, acc, n_tokens, H, v_begin, v_end, V, b_out, nullptr, mask, s, st);
+                   nullptr, nullptr, nullptr, nullptr, acc, n_tokens, H, v_begin, v_end, V, b_out, nullptr, mask, s,
+                   n_tokens_dev, st);
 }
 
 namespace {
 // one warp per token row
 __global__ void __launch_bounds__(256)
-ce_dh_finish_kernel(float* __restrict__ dh, const float* __restrict__ srow, const float* __restrict__ coef,
-                    const int32_t* __restrict__ tgt, const __nv_bfloat16* __restrict__ Bt_hi,
-                    const __nv_bfloat16* __restrict__ Bt_lo, const float* __restrict__ hscale, int64_t n_tokens, int H,
-                    int Hk) {
+ce_dh_finish_kernel(const float* __restrict__ acc, float* __restrict__ dh, const float* __restrict__ srow,
+                    const float* __restrict__ coef, const int32_t* __restrict__ tgt,
+                    const __nv_bfloat16* __restrict__ Bt_hi, const __nv_bfloat16* __restrict__ Bt_lo,
+                    const float* __restrict__ hscale, int64_t n_tokens, int H, int Hk,
+                    const int32_t* __restrict__ orig, const int32_t* __restrict__ n_tokens_dev) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n_tokens_dev) n_tokens = min(n_tokens, (int64_t)n_tokens_dev[0]);
   if (n >= n_tokens) return;
+  const int64_t r = orig ? orig[n] : n;                      // compacted token axis: dh row behind token n
   const float cf = coef[n];
-  float* row = dh + n * H;
+  const float* src = acc + n * H;
+  float* row = dh + r * H;
   if (cf == 0.f) {
     for (int h = lane; h < H; h += 32) row[h] = 0.f;
     return;
@@ -1430,20 +1445,21 @@ ce_dh_finish_kernel(float* __restrict__ dh, const float* __restrict__ srow, cons
       wy = __bfloat162float(Bt_hi[(size_t)y * Hk + h]);
       if (Bt_lo) wy += __bfloat162float(Bt_lo[(size_t)y * Hk + h]);
     }
-    float v = cf * (row[h] * inv_s - wy);
-    if (hscale) v *= hscale[n * H + h];
+    float v = cf * (src[h] * inv_s - wy);
+    if (hscale) v *= hscale[r * H + h];
     row[h] = v;
   }
 }
 }  // namespace
 
-extern "C" int seqrec_ce_dh_finish(float* dh, const float* s, const float* coef, const int32_t* tgt,
+extern "C" int seqrec_ce_dh_finish(const float* acc, float* dh, const float* s, const float* coef, const int32_t* tgt,
                                    const uint16_t* Bt_hi, const uint16_t* Bt_lo, const float* hscale, int64_t n_tokens,
-                                   int H, int Hk, void* stream) {
-  SEQREC_ARG(dh && s && coef && tgt && Bt_hi && n_tokens > 0 && H > 0 && Hk >= H, 1);
+                                   int H, int Hk, const int32_t* orig, const int32_t* n_tokens_dev, void* stream) {
+  SEQREC_ARG(acc && dh && s && coef && tgt && Bt_hi && n_tokens > 0 && H > 0 && Hk >= H, 1);
+  SEQREC_ARG(orig == nullptr || acc != dh, 2);               // a compacted accumulator cannot be finished in place
   ce_dh_finish_kernel<<<ceil_div(n_tokens * 32, 256), 256, 0, as_stream(stream)>>>(
-      dh, s, coef, tgt, reinterpret_cast<const __nv_bfloat16*>(Bt_hi), reinterpret_cast<const __nv_bfloat16*>(Bt_lo),
-      hscale, n_tokens, H, Hk);
+      acc, dh, s, coef, tgt, reinterpret_cast<const __nv_bfloat16*>(Bt_hi),
+      reinterpret_cast<const __nv_bfloat16*>(Bt_lo), hscale, n_tokens, H, Hk, orig, n_tokens_dev);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }

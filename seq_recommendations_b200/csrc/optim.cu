@@ -334,6 +334,119 @@ extern "C" int seqrec_split_bf16_both(const float* src, const float* scale, uint
   return 0;
 }
 
+// ---- token compaction --------------------------------------------------------------------------------------------
+// Pad tokens carry neither loss nor gradient, so the logits kernels of a training step run on the VALID tokens only:
+// orig[c] = time-major index of the c-th valid token IN ASCENDING ORDER (deterministic: every rank of a
+// vocabulary-parallel step must number the gathered tokens identically), tgt_c[c] = its target, count[0] = number of
+// valid tokens.  Two launches: per-block counts, then every block sums the counts in front of it and scatters.
+__global__ void __launch_bounds__(256)
+compact_count_kernel(const uint8_t* __restrict__ mask, int64_t n_tokens, int32_t* __restrict__ block_counts) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c = __syncthreads_count(n < n_tokens && mask[n] != 0);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(256)
+compact_scatter_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ tgt, int64_t n_tokens,
+                       const int32_t* __restrict__ block_counts, int32_t* __restrict__ orig,
+                       int32_t* __restrict__ tgt_c, int32_t* __restrict__ count) {
+  __shared__ int warp_base[8];
+  __shared__ int block_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // exclusive prefix of the block counts (a few hundred values)
+  int part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += blockDim.x) part += block_counts[i];
+  part = (int)warp_sum((float)part);            // exact: counts are far below 2^24 per warp partial
+  if (lane == 0) warp_base[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += warp_base[i];
+    block_base = t;
+  }
+  __syncthreads();
+  const int base0 = block_base;
+  __syncthreads();
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool on = n < n_tokens && mask[n] != 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) warp_base[warp] = __popc(bal);
+  __syncthreads();
+  int wb = 0;
+  for (int i = 0; i < warp; ++i) wb += warp_base[i];
+  if (on) {
+    const int c = base0 + wb + __popc(bal & ((1u << lane) - 1u));
+    orig[c] = (int32_t)n;
+    if (tgt_c) tgt_c[c] = tgt[n];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += warp_base[i];
+    count[0] = base0 + t;
+  }
+}
+
+extern "C" int seqrec_compact_tokens(const uint8_t* mask, const int32_t* tgt, int64_t n_tokens, int32_t* orig,
+                                     int32_t* tgt_c, int32_t* count, int32_t* block_counts, void* stream) {
+  SEQREC_ARG(mask && orig && count && block_counts && n_tokens > 0 && n_tokens < (1ll << 30), 1);
+  const unsigned blocks = (unsigned)((n_tokens + 255) / 256);
+  compact_count_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mask, n_tokens, block_counts);
+  SEQREC_CHECK_LAUNCH();
+  compact_scatter_kernel<<<blocks, 256, 0, as_stream(stream)>>>(mask, tgt, n_tokens, block_counts, orig, tgt_c, count);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// split_bf16_both over the compacted rows: output row r (r < n_rows[0], read on the device) is source row orig[r]
+__global__ void split_bf16_both_rows_kernel(const float* __restrict__ src, const float* __restrict__ scale,
+                                            const int32_t* __restrict__ orig, const int32_t* __restrict__ n_rows,
+                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                            __nv_bfloat16* __restrict__ hi_t, __nv_bfloat16* __restrict__ lo_t,
+                                            int64_t cols, int64_t ld_out, int64_t ld_t) {
+  __shared__ float tile[32][33];
+  const int64_t rows = n_rows[0];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  if (r0 >= rows) return;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    float x = 0.f;
+    if (r < rows && c < cols) {
+      const int64_t sr = orig[r];
+      x = src[sr * cols + c];
+      if (scale) x *= scale[sr * cols + c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[r * ld_out + c] = h;
+      if (lo) lo[r * ld_out + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+    tile[i][threadIdx.x] = x;
+  }
+  __syncthreads();
+  if (!hi_t) return;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float x = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi_t[c * ld_t + r] = h;
+      if (lo_t) lo_t[c * ld_t + r] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+extern "C" int seqrec_split_bf16_both_rows(const float* src, const float* scale, const int32_t* orig,
+                                           const int32_t* n_rows, uint16_t* hi, uint16_t* lo, uint16_t* hi_t,
+                                           uint16_t* lo_t, int64_t max_rows, int64_t cols, int64_t ld_out, int64_t ld_t,
+                                           void* stream) {
+  SEQREC_ARG(src && orig && n_rows && hi && max_rows > 0 && cols > 0 && ld_out >= cols && ld_t >= max_rows, 1);
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((max_rows + 31) / 32)), block(32, 8);
+  SEQREC_ARG(grid.y <= 65535, 2);
+  split_bf16_both_rows_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      src, scale, orig, n_rows, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
+      reinterpret_cast<__nv_bfloat16*>(hi_t), reinterpret_cast<__nv_bfloat16*>(lo_t), cols, ld_out, ld_t);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
 // split + column sums in one pass over src (the dU GEMM's dxp operand and db = sum_n dxp[n,:] both come from it):
 // thread <-> column, blockIdx.y <-> a chunk of rows; partial column sums leave through atomicAdd
 __global__ void __launch_bounds__(256)

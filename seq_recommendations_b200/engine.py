@@ -72,6 +72,7 @@ class _Work:
         self.in_scale = None
         self.rec_mask = None
         self.rd_scratch = None
+        self.orig = self.tgt_c = self.n_c = self.blk = self.acc = self.ce_tgt = self.ce_n = None
         self.x_dense = None
         self.pin_event = None
         self.pin_dirty = False
@@ -219,6 +220,8 @@ class HotPath:
         # training: forward statistics and dH from ONE logits pass (seqrec_ce_tc_fused); SEQREC_CE_FUSED=0 falls back to
         # the separate forward + token-stationary backward kernels
         self.ce_fused = os.environ.get("SEQREC_CE_FUSED", "1") != "0"
+        # ... on the valid tokens only (pads compacted away); SEQREC_CE_COMPACT=0 keeps the full token axis
+        self.ce_compact = os.environ.get("SEQREC_CE_COMPACT", "1") != "0"
         self.Hk = (self.H + 63) // 64 * 64
         self.Vp = (self.V + 7) // 8 * 8
         self._w_version = 0
@@ -585,7 +588,7 @@ class HotPath:
             if with_targets:                      # the target logit is not needed before the finalize kernel
                 with self._branch():
                     call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out),
-                         ptr(w.tgt), ptr(w.zy), w.N, self.H, self.V, self.stream)
+                         ptr(w.tgt), ptr(w.zy), w.N, self.H, self.V, None, None, self.stream)
             call("seqrec_ce_tc_forward", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.b_out),
                  ptr(w.ws_m), ptr(w.ws_s), w.N, self.Hk, self.V, 0, self.V, 1 if self.tc_x3 else 0, st)
             self._join()
@@ -605,7 +608,7 @@ class HotPath:
         if train:
             call("seqrec_ce_finalize_mean", ptr(ws_m), ptr(ws_s), ptr(w.zy), ptr(w.mask), ptr(w.m), ptr(w.s), ptr(w.ce),
                  ptr(w.py), ptr(w.coef), ptr(self.step_loss_sum), ptr(w.n_valid_i), ptr(self.n_valid_f),
-                 ptr(w.loss_mean), w.N, n_splits, self.stream)
+                 ptr(w.loss_mean), w.N, n_splits, None, self.stream)
         else:
             call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
                  ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
@@ -615,40 +618,72 @@ class HotPath:
         """Training-step logits pass on the tensor cores, fused: statistics + dh from ONE logits computation
         (seqrec_ce_tc_fused), finalize, dh finish.  Leaves w.m (= the per-token reference logit), w.s, w.coef ready for
         the item-stationary dW kernel.  zy_reduce / s_reduce: vocabulary-parallel hooks that sum the target logit and
-        the partial sum-exp over the item shards."""
+        the partial sum-exp over the item shards.
+
+        The token axis is COMPACTED first (self.ce_compact): pad tokens carry neither loss nor gradient, so operands and
+        per-token arrays hold the valid tokens only (ascending time-major order) and every logits-sized GEMM of the step
+        shrinks by the padding fraction; dh is scattered back to the full [T][B][H] layout by the finish kernel.  The
+        valid count lives on the device (w.n_c): a captured step replays with any amount of padding."""
         st = self.stream
+        cp = self.ce_compact
         self._mark("stage_operands")
         self._stage_weight_operands()
-        call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
-             ptr(w.Ht_lo), w.N, self.H, self.Hk, w.Np, st)
-        w.tc_operands_fresh = True
+        if cp:
+            if w.orig is None:
+                i32 = torch.int32
+                w.orig = torch.zeros(w.N, dtype=i32, device=self.device)
+                w.tgt_c = torch.zeros(w.N, dtype=i32, device=self.device)
+                w.n_c = torch.zeros(1, dtype=i32, device=self.device)
+                w.blk = torch.zeros((w.N + 255) // 256, dtype=i32, device=self.device)
+                w.acc = torch.empty((w.N, self.H), dtype=torch.float32, device=self.device)
+            call("seqrec_compact_tokens", ptr(w.mask), ptr(w.tgt), w.N, ptr(w.orig), ptr(w.tgt_c), ptr(w.n_c),
+                 ptr(w.blk), st)
+            call("seqrec_split_bf16_both_rows", ptr(w.hout), ptr(w.hscale), ptr(w.orig), ptr(w.n_c), ptr(w.A_hi),
+                 ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), w.N, self.H, self.Hk, w.Np, st)
+            w.tc_operands_fresh = False           # A holds compacted rows: not the dU GEMM's hout operand
+            tgt, mask, orig, n_c, acc = w.tgt_c, None, w.orig, w.n_c, w.acc
+        else:
+            call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
+                 ptr(w.Ht_lo), w.N, self.H, self.Hk, w.Np, st)
+            w.tc_operands_fresh = True
+            tgt, mask, orig, n_c, acc = w.tgt, w.mask, None, None, w.dh
+        w.ce_tgt, w.ce_n = tgt, n_c               # what the dW kernel indexes with
         self._join()                              # W_out operands staged on the branch by the caller
         self._mark("ce_fwd")
-        call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
-             ptr(w.zy), w.N, self.H, self.V, st)
+        call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(tgt),
+             ptr(w.zy), w.N, self.H, self.V, ptr(orig), ptr(n_c), st)
         if zy_reduce is not None:
             zy_reduce(w.zy)
         w.dh.zero_()
+        if cp:
+            acc.zero_()
         w.s.zero_()
         call("seqrec_ce_tc_fused", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.Wb_hi),
-             ptr(self.Wb_lo), ptr(w.zy), ptr(w.mask), ptr(self.b_out), ptr(w.dh), ptr(w.s), w.N, self.H, self.Hk,
-             self.V, self.Vp, 0, self.V, 1 if self.tc_x3 else 0, st)
+             ptr(self.Wb_lo), ptr(w.zy), ptr(mask), ptr(self.b_out), ptr(acc), ptr(w.s), w.N, self.H, self.Hk,
+             self.V, self.Vp, 0, self.V, 1 if self.tc_x3 else 0, ptr(n_c), st)
         if s_reduce is not None:
             s_reduce(w.s)
-        self._finalize_ce(w, w.zy, w.s, 1, True, train=True)
-        call("seqrec_ce_dh_finish", ptr(w.dh), ptr(w.s), ptr(w.coef), ptr(w.tgt), ptr(self.Bt_hi), ptr(self.Bt_lo),
-             ptr(w.hscale), w.N, self.H, self.Hk, st)
+        call("seqrec_ce_finalize_mean", ptr(w.zy), ptr(w.s), ptr(w.zy), ptr(mask), ptr(w.m), ptr(w.s), ptr(w.ce),
+             ptr(w.py), ptr(w.coef), ptr(self.step_loss_sum), ptr(w.n_valid_i), ptr(self.n_valid_f), ptr(w.loss_mean),
+             w.N, 1, ptr(n_c), st)
+        self._mark("misc")
+        call("seqrec_ce_dh_finish", ptr(acc), ptr(w.dh), ptr(w.s), ptr(w.coef), ptr(tgt), ptr(self.Bt_hi),
+             ptr(self.Bt_lo), ptr(w.hscale), w.N, self.H, self.Hk, ptr(orig), ptr(n_c), st)
 
     def _backward_ce(self, w, dh=True):
         """K6.  Gradients leave UN-normalised (dlogit = (p - onehot) * coef, no 1/n_valid): everything downstream is
         linear in that factor, so the optimiser kernels apply 1/n_valid_global once -- which is what lets a
-        data-parallel step run its backward pass before the token counts of the other ranks are known."""
+        data-parallel step run its backward pass before the token counts of the other ranks are known.
+        dh=False: after the fused pass -- only the item-stationary dW kernel runs, on the (compacted) token axis the
+        fused pass left behind."""
         st = self.stream
         if w.tc["bwd"]:
+            tgt, n_c = (w.tgt, None) if dh else (w.ce_tgt, w.ce_n)
             call("seqrec_ce_tc_backward", ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi), ptr(w.Ht_lo), ptr(self.Bt_hi),
-                 ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(w.tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
+                 ptr(self.Bt_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), ptr(tgt), ptr(w.m), ptr(w.s), ptr(w.coef),
                  None, ptr(w.hscale), ptr(w.dh) if dh else None, ptr(self.dW_out), w.N, self.H, self.Hk, self.V,
-                 self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, ptr(self.b_out), ptr(self.db_out), st)
+                 self.Vp, w.Np, 0, self.V, self.V, 0, 1 if self.tc_x3 else 0, ptr(self.b_out), ptr(self.db_out),
+                 ptr(n_c), st)
         else:
             call("seqrec_ce_backward", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
                  ptr(w.m), ptr(w.s), ptr(w.coef), None, ptr(w.dh), ptr(self.dW_out), ptr(self.db_out),
@@ -709,7 +744,7 @@ class HotPath:
         """Everything a captured step bakes in BY VALUE (kernel arguments and which kernels are launched at all)."""
         o = self.opt
         return (o["lr"], o["eps"], o["clipnorm"], tuple(sorted(self.trainable.items())), self.dropout_in,
-                self.dropout_out, self.dropout_rec, self.overlap, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
+                self.dropout_out, self.dropout_rec, self.overlap, self.ce_fused, self.ce_compact, self.rnn_tc, self.wgrad_tc, self.tc_mode, self.tc_x3)
 
     def _train_core(self, w):
         """forward + backward + exchange + update on the staged batch (everything after the host->device copy).

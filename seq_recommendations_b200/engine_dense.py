@@ -296,7 +296,7 @@ class DensePath:
         if train:
             call("seqrec_ce_finalize_mean", ptr(w.m), ptr(w.s), ptr(w.zy), ptr(w.mask_o), ptr(w.m), ptr(w.s), ptr(w.ce),
                  ptr(w.py), ptr(w.coef), ptr(self.step_loss_sum), ptr(self.scal[0:1]), ptr(self.n_valid_f),
-                 ptr(w.loss_mean), w.N, 1, st)
+                 ptr(w.loss_mean), w.N, 1, None, st)
         else:
             call("seqrec_ce_finalize", ptr(w.m), ptr(w.s), ptr(w.zy), ptr(w.mask_o), ptr(w.m), ptr(w.s), ptr(w.ce),
                  ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, 1, st)

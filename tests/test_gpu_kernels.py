@@ -343,7 +343,7 @@ def test_finalize_mean_matches_finalize_and_numpy(N, splits):
         inv, lm = torch.zeros(1, dtype=torch.float32, device="cuda"), torch.zeros(1, dtype=torch.float32, device="cuda")
         if mean:
             call("seqrec_ce_finalize_mean", ptr(ws_m), ptr(ws_s), ptr(zy), ptr(mask), ptr(m), ptr(s), ptr(ce), ptr(py),
-                 ptr(coef), ptr(loss_sum), ptr(n_valid), ptr(inv), ptr(lm), N, splits, stream())
+                 ptr(coef), ptr(loss_sum), ptr(n_valid), ptr(inv), ptr(lm), N, splits, None, stream())
         else:
             call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(zy), ptr(mask), ptr(m), ptr(s), ptr(ce), ptr(py),
                  ptr(coef), ptr(loss_sum), N, splits, stream())

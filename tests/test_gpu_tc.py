@@ -141,11 +141,18 @@ def test_fused_statistics_and_dh_match_the_two_pass_kernels(V, H, T, B):
     ws = synthetic.make_weights("GRU", V, H, seed=7)
     ids, tgt = synthetic.make_batch(V, T, B, seed=8, min_len=1)
     res = {}
-    for key, m, fused in (("fused", "x3", True), ("two_pass", "x3", False), ("simt", "off", False)):
+    for key, m, fused, compact in (("fused", "x3", True, True), ("fused_full_axis", "x3", True, False),
+                                   ("two_pass", "x3", False, False), ("simt", "off", False, False)):
         hot = HotPath("GRU", "tanh", V, H, V, weights=ws, tc=m)
+        hot.ce_compact = compact                   # True: the logits kernels see the valid tokens only (pads compacted)
         loss, grads, extra = hot.grad_batch(ids, tgt, fused=fused)
         res[key] = (loss, extra["dh"], grads[3])
-    for key in ("fused", "two_pass"):
+        if fused and compact:
+            w = hot.work(B, T)
+            assert int(w.n_c.item()) == int((ids >= 0).sum())
+            orig = w.orig[:int(w.n_c.item())].cpu().numpy()
+            assert np.array_equal(orig, np.flatnonzero((ids >= 0).T.reshape(-1)))      # ascending time-major order
+    for key in ("fused", "fused_full_axis", "two_pass"):
         assert abs(res[key][0] / res["simt"][0] - 1) <= 1e-5
         assert rel_err(res[key][1], res["simt"][1]) <= 1e-4, key
         assert rel_err(res[key][2], res["simt"][2]) <= 1e-4, key
