@@ -58,15 +58,21 @@ def model_surface_checks(comm, dev):
 
 
 def main():
+    import faulthandler
     comm = dist.init_from_env("nccl")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     ok = True
+    # a hang (a collective only some ranks reach) must end quickly and say where: every rank dumps its Python stack and
+    # exits if a case takes longer than this
+    limit = int(os.environ.get("SEQREC_DP_CASE_LIMIT_S", "150"))
     # (V, H, T, B_global, cell): dense dW_in exchange (small V) and row exchange (V*GH > N*GH), TC and SIMT logits
     # (100, ...) and (300, ... B=512) take the dense dW_in all-reduce (V <= N_global); the others the row exchange
     # the last two run the vocabulary-parallel logits (W_out column shards, reduce-scattered dh)
     for V, H, T, B, cell, tc, vp in ((900, 64, 10, 64, "GRU", "x3", False), (60000, 32, 4, 48, "LSTM", "off", False),
                                      (100, 32, 6, 30, "GRU", "off", False), (300, 64, 8, 512, "GRU", "x3", False),
                                      (4096, 128, 8, 64, "GRU", "x3", True), (998, 32, 5, 40, "LSTM", "off", True)):
+        faulthandler.dump_traceback_later(limit, exit=True)
+        print("rank %d: case V=%d %s tc=%s vp=%s" % (comm.rank, V, cell, tc, vp), flush=True)
         act = "tanh" if cell == "GRU" else "relu"
         ws = synthetic.make_weights(cell, V, H, seed=3)
         steps = [synthetic.make_batch(V, T, B, seed=50 + s, min_len=1) for s in range(3)]
@@ -125,7 +131,10 @@ def main():
         if (dense and spread != 0.0) or spread > 2e-5:
             print("rank %d: replicas diverged (dense=%s, spread %.2e)" % (comm.rank, dense, spread), flush=True)
             ok = False
+    faulthandler.dump_traceback_later(limit, exit=True)
+    print("rank %d: model surface checks" % comm.rank, flush=True)
     ok = model_surface_checks(comm, dev) and ok
+    faulthandler.cancel_dump_traceback_later()
     flag = torch.tensor([1 if ok else 0], device=dev)
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
     comm.barrier()
