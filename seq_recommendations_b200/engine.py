@@ -73,6 +73,7 @@ class _Work:
         self.rec_mask = None
         self.rd_scratch = None
         self.orig = self.tgt_c = self.n_c = self.blk = self.acc = self.ce_tgt = self.ce_n = None
+        self.pz = self.pz_hi = self.pz_lo = self.pzt_hi = self.pzt_lo = None
         self.x_dense = None
         self.pin_event = None
         self.pin_dirty = False
@@ -84,12 +85,12 @@ class _Work:
         self.tc_operands_fresh = False         # A_hi / A_lo hold the split of the CURRENT hout
         # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
         self.tc = hp._tc_plan(N)
-        if self.tc["fwd"]:
+        if self.tc["fwd"] or self.tc["panel"]:
             bf = torch.bfloat16
             self.Np = (N + 7) // 8 * 8
             self.A_hi = torch.zeros((N, hp.Hk), dtype=bf, device=dev)
             self.A_lo = torch.zeros((N, hp.Hk), dtype=bf, device=dev) if hp.tc_x3 else None
-            if self.tc["bwd"]:
+            if self.tc["bwd"] or self.tc["panel"]:
                 self.Ht_hi = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev)
                 self.Ht_lo = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev) if hp.tc_x3 else None
             if self.tc["splits"] > self.splits:
@@ -276,10 +277,16 @@ class HotPath:
 
     def _tc_plan(self, N):
         """Which logits kernels serve a batch of N tokens."""
-        fwd = (self.tc_mode != "off" and self.Hk <= 256 and self.V >= 256 and N >= 128)
+        big = self.tc_mode != "off" and self.V >= 256 and N >= 128
+        fwd = big and self.Hk <= 256
         bwd = fwd
         splits = _lib.load().seqrec_ce_tc_partials(N, 0, self.V) if fwd else 0   # partial rows the TC forward writes
-        return dict(fwd=fwd, bwd=bwd, splits=splits)
+        # hidden sizes above 256 (tune_params_msnbc.py:53 sweeps z_dim up to 1000): the fused kernels keep a [128 x Hk]
+        # fp32 accumulator in tensor memory, which ends at Hk = 256 next to the logits tile -- wider layers run the
+        # logits path as plain tcgen05 GEMMs over token PANELS (seqrec_gemm_tc, K-looped over any Hk): a panel of logits
+        # is materialised, never the (N,V) matrix
+        panel = big and not fwd and not self.vocab_parallel
+        return dict(fwd=fwd, bwd=bwd, splits=splits, panel=panel)
 
     def _stage_weight_operands(self):
         """bf16 hi/lo copies of W_out (as W and as W^T), refreshed whenever the weights changed."""
@@ -566,6 +573,8 @@ class HotPath:
              w.T, w.B, self.H, st)
 
     def _forward_ce(self, w, with_targets=True, training=False, train=False):
+        if w.tc["panel"]:
+            return self._ce_panels(w, with_targets, train=train, backward=False)
         n_splits = self._ce_partials(w, with_targets, training)
         self._finalize_ce(w, w.ws_m, w.ws_s, n_splits, with_targets, train)
 
@@ -612,6 +621,73 @@ class HotPath:
         else:
             call("seqrec_ce_finalize", ptr(ws_m), ptr(ws_s), ptr(w.zy) if with_targets else None, ptr(w.mask),
                  ptr(w.m), ptr(w.s), ptr(w.ce), ptr(w.py), ptr(w.coef), ptr(w.loss_sum), w.N, n_splits, self.stream)
+        self._mark("misc")
+
+    def _ce_panels(self, w, with_targets=True, train=False, backward=False):
+        """Logits path for hidden sizes above 256, on the tcgen05 GEMM (csrc/gemm_tc.cu, K-looped): the tokens are walked
+        in PANELS of `nb` rows; per panel  Z = hs . W_out (+ b_out)  is materialised (nb x V fp32, <= 256 MB), reduced to
+        the per-token softmax statistics, turned into dlogit in place and consumed by  dh = dZ . W_out^T  and
+        dW_out += hs^T . dZ  -- three logits-sized GEMMs per step, none recomputed.  The full (N,V) matrix never exists."""
+        st = self.stream
+        N, H, Hk, V = w.N, self.H, self.Hk, self.V
+        x3 = 1 if self.tc_x3 else 0
+        self._mark("stage_operands")
+        self._stage_weight_operands()
+        call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
+             ptr(w.Ht_lo), N, H, Hk, w.Np, st)
+        w.tc_operands_fresh = False
+        self._join()
+        self._mark("ce_fwd")
+        if with_targets:
+            call("seqrec_target_logit", ptr(w.hout), ptr(w.hscale), ptr(self.W_out), ptr(self.b_out), ptr(w.tgt),
+                 ptr(w.zy), N, H, V, None, None, st)
+        nb_max = max(128, min((N + 127) // 128 * 128, ((256 << 20) // (4 * V)) // 128 * 128))
+        if w.pz is None or w.pz.shape[0] < nb_max:
+            bf = torch.bfloat16
+            Vk, nbk = (V + 63) // 64 * 64, nb_max
+            w.pz = torch.empty((nb_max, V), dtype=torch.float32, device=self.device)
+            w.pz_hi = torch.zeros((nb_max, Vk), dtype=bf, device=self.device)
+            w.pz_lo = torch.zeros((nb_max, Vk), dtype=bf, device=self.device) if x3 else None
+            w.pzt_hi = torch.zeros((V, nbk), dtype=bf, device=self.device)
+            w.pzt_lo = torch.zeros((V, nbk), dtype=bf, device=self.device) if x3 else None
+        Vk, nbk = w.pz_hi.shape[1], w.pzt_hi.shape[1]
+        n_panels = (N + nb_max - 1) // nb_max
+        parts = torch.zeros(n_panels, dtype=torch.float32, device=self.device)
+        el = 2                                                       # bytes per bf16
+        for p, n0 in enumerate(range(0, N, nb_max)):
+            nb = min(nb_max, N - n0)
+            off = lambda t, elems, size: ctypes.c_void_p(t.data_ptr() + elems * size) if t is not None else None
+            Z = w.pz[:nb]
+            call("seqrec_gemm_tc", off(w.A_hi, n0 * Hk, el), off(w.A_lo, n0 * Hk, el), ptr(self.Bt_hi), ptr(self.Bt_lo),
+                 ptr(self.b_out), ptr(Z), nb, V, Hk, Hk, Hk, V, 0, x3, st)
+            sl = slice(n0, n0 + nb)
+            m, s_, zy, mask = w.m[sl], w.s[sl], w.zy[sl], w.mask.view(-1)[sl]
+            tg = w.tgt.view(-1)[sl]
+            call("seqrec_softmax_rows_stats", ptr(Z), None, ptr(m), ptr(s_), None, nb, V, st)
+            call("seqrec_ce_finalize", ptr(m), ptr(s_), ptr(zy) if with_targets else None, ptr(mask), ptr(m), ptr(s_),
+                 ptr(w.ce[sl]), ptr(w.py[sl]), ptr(w.coef[sl]), ptr(parts[p:p + 1]), nb, 1, st)
+            if not backward:
+                continue
+            call("seqrec_softmax_rows_dlogit", ptr(Z), ptr(tg), ptr(m), ptr(s_), ptr(w.coef[sl]), nb, V, st)
+            if self.db_out is not None:
+                call("seqrec_colsum", ptr(Z), ptr(self.db_out), nb, V, V, st)
+            call("seqrec_split_bf16_both", ptr(Z), None, ptr(w.pz_hi), ptr(w.pz_lo), ptr(w.pzt_hi), ptr(w.pzt_lo), nb, V,
+                 Vk, nbk, st)
+            # dh[panel] = dZ . W_out^T   (K = V; W_out rows are K-major over the items: the Wb operand)
+            dh = w.dh.view(N, H)[sl]
+            call("seqrec_gemm_tc", ptr(w.pz_hi), ptr(w.pz_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), None, ptr(dh), nb, H, V,
+                 Vk, self.Vp, H, 0, x3, st)
+            if w.hscale is not None:
+                dh.mul_(w.hscale.view(N, H)[sl])
+            # dW_out += hs[panel]^T . dZ   (K = the panel's tokens: Ht columns [n0, n0 + nb), dZ^T rows)
+            call("seqrec_gemm_tc", off(w.Ht_hi, n0, el), off(w.Ht_lo, n0, el), ptr(w.pzt_hi), ptr(w.pzt_lo), None,
+                 ptr(self.dW_out), H, V, nb, w.Np, nbk, V, 1, x3, st)
+        if train:
+            torch.sum(parts, dim=0, keepdim=True, out=self.step_loss_sum)
+            self.n_valid_f.copy_(w.n_valid_i)
+            torch.div(self.step_loss_sum, self.n_valid_f, out=w.loss_mean)
+        else:
+            torch.sum(parts, dim=0, keepdim=True, out=w.loss_sum)
         self._mark("misc")
 
     def _ce_train_fused(self, w, zy_reduce=None, s_reduce=None):
@@ -767,14 +843,17 @@ class HotPath:
                 self._stage_weight_operands()
         self._forward_hidden(w, training=True)
         fused = self.ce_fused and w.tc["bwd"]
-        if fused:
+        if w.tc["panel"]:
+            self._ce_panels(w, True, train=True, backward=True)      # statistics, dh and dW_out panel by panel
+        elif fused:
             self._ce_train_fused(w)
         else:
             self._forward_ce(w, training=True, train=True)
 
         # ---- backward (the gradient buffer was cleared with the step scalars when the batch was staged)
         self._mark("ce_bwd")
-        self._backward_ce(w, dh=not fused)
+        if not w.tc["panel"]:
+            self._backward_ce(w, dh=not fused)
         # dW_out / db_out are final here: their all-reduce runs on NCCL's stream behind the recurrent backward pass
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
@@ -1052,11 +1131,14 @@ class HotPath:
         self._stage(w, ids, tgt, x_dense, grads=True)
         self._forward_hidden(w, training=True)
         use_fused = (self.ce_fused if fused is None else bool(fused)) and w.tc["bwd"]
-        if use_fused:
+        if w.tc["panel"]:
+            self._ce_panels(w, True, train=True, backward=True)
+        elif use_fused:
             self._ce_train_fused(w)
         else:
             self._forward_ce(w, training=True, train=True)
-        self._backward_ce(w, dh=not use_fused)
+        if not w.tc["panel"]:
+            self._backward_ce(w, dh=not use_fused)
         dh = w.dh.clone()
         self._rnn_backward(w)
         self._rnn_weight_grad(w)

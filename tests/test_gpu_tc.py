@@ -184,6 +184,34 @@ def test_fused_pass_with_extreme_logits_matches_oracle(scale):
             assert rel_err(g, r.numpy()) <= tol, (name, rel_err(g, r.numpy()))
 
 
+@pytest.mark.parametrize("cell,act,V,H,T,B", [("LSTM", "relu", 1500, 500, 6, 40), ("GRU", "tanh", 2077, 1000, 5, 60),
+                                              ("LSTM", "tanh", 700, 320, 9, 30)])
+def test_hidden_sizes_above_256_run_on_the_tensor_core_gemm(cell, act, V, H, T, B):
+    """z_dim 500 / 1000 of tune_params_msnbc.py:53: the fused kernels end at Hk = 256 (TMEM accumulator), wider layers run
+    the logits path as K-looped tcgen05 GEMMs over token panels (engine._ce_panels).  Loss, all gradients, p(target) and
+    a training step against the float64 oracle, 1e-4; the SIMT kernels on the same problem as a second witness."""
+    hot, ora, ws = make_pair(cell, act, V, H, seed=41, bias_scale=0.1, tc="x3")
+    ids, tgt = synthetic.make_batch(V, T, B, seed=42, min_len=1)
+    w = hot.work(B, T)
+    assert w.tc["panel"] and not w.tc["fwd"]
+    loss, grads, extra = hot.grad_batch(ids, tgt)
+    rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+    assert abs(loss - float(rl)) <= 1e-4 * abs(float(rl))
+    for name, g, r in zip(["W_in", "U", "b", "W_out"], grads, rg):
+        assert rel_err(g, r.numpy()) <= 1e-4, (name, rel_err(g, r.numpy()))
+    simt = HotPath(cell, act, V, H, V, weights=ws, tc="off")
+    _, g2, e2 = simt.grad_batch(ids, tgt)
+    assert rel_err(extra["dh"], e2["dh"]) <= 1e-4 and rel_err(grads[3], g2[3]) <= 1e-4
+    py = hot.target_prob_batch(ids, tgt).cpu().numpy()
+    ref = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)
+    assert np.abs(py - ks.target_prob(ref, as_t(tgt), as_t(ids) >= 0).numpy()).max() <= 1e-4
+    hot.set_optimizer("adagrad", lr=0.05, epsilon=1e-8, clipnorm=1.0)
+    for step in range(3):                                        # eager, then captured + replayed
+        l1 = float(hot.train_batch(ids, tgt).item())
+        l2, _, _ = ora.train_step(as_t(ids), as_t(tgt), as_t(ids) >= 0, lr=0.05, epsilon=1e-8, clipnorm=1.0)
+        assert abs(l1 - float(l2)) <= 2e-4 * abs(float(l2)), (step, l1, float(l2))
+
+
 def test_cfg2_full_size_properties():
     """BASELINE configs[1] at full size (V=10k, GRU-128, T=50, B=256): size-independent checks -- probabilities of a
     row sum to one, the step lowers the loss on the same batch, x3 and SIMT agree, the dW_in invariant is restored."""
