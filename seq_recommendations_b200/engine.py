@@ -85,12 +85,12 @@ class _Work:
         self.tc_operands_fresh = False         # A_hi / A_lo hold the split of the CURRENT hout
         # bf16 hi/lo operands of the tensor-core logits kernels (zero padding of Hk / Np is never written)
         self.tc = hp._tc_plan(N)
-        if self.tc["fwd"] or self.tc["panel"]:
+        if self.tc["fwd"] or self.tc["panel_tc"]:
             bf = torch.bfloat16
             self.Np = (N + 7) // 8 * 8
             self.A_hi = torch.zeros((N, hp.Hk), dtype=bf, device=dev)
             self.A_lo = torch.zeros((N, hp.Hk), dtype=bf, device=dev) if hp.tc_x3 else None
-            if self.tc["bwd"] or self.tc["panel"]:
+            if self.tc["bwd"] or self.tc["panel_tc"]:
                 self.Ht_hi = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev)
                 self.Ht_lo = torch.zeros((hp.Hk, self.Np), dtype=bf, device=dev) if hp.tc_x3 else None
             if self.tc["splits"] > self.splits:
@@ -285,8 +285,8 @@ class HotPath:
         # fp32 accumulator in tensor memory, which ends at Hk = 256 next to the logits tile -- wider layers run the
         # logits path as plain tcgen05 GEMMs over token PANELS (seqrec_gemm_tc, K-looped over any Hk): a panel of logits
         # is materialised, never the (N,V) matrix
-        panel = big and not fwd and not self.vocab_parallel
-        return dict(fwd=fwd, bwd=bwd, splits=splits, panel=panel)
+        panel = self.Hk > 256 and not self.vocab_parallel
+        return dict(fwd=fwd, bwd=bwd, splits=splits, panel=panel, panel_tc=panel and big)
 
     def _stage_weight_operands(self):
         """bf16 hi/lo copies of W_out (as W and as W^T), refreshed whenever the weights changed."""
@@ -631,10 +631,15 @@ class HotPath:
         st = self.stream
         N, H, Hk, V = w.N, self.H, self.Hk, self.V
         x3 = 1 if self.tc_x3 else 0
-        self._mark("stage_operands")
-        self._stage_weight_operands()
-        call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
-             ptr(w.Ht_lo), N, H, Hk, w.Np, st)
+        tc = w.tc["panel_tc"]                     # False: shapes that do not fill tensor-core tiles (e.g. the 17-item
+        hs_all = None                             # MSNBC catalog), or tc='off': the same panels on the fp32 SIMT GEMMs
+        if tc:
+            self._mark("stage_operands")
+            self._stage_weight_operands()
+            call("seqrec_split_bf16_both", ptr(w.hout), ptr(w.hscale), ptr(w.A_hi), ptr(w.A_lo), ptr(w.Ht_hi),
+                 ptr(w.Ht_lo), N, H, Hk, w.Np, st)
+        else:
+            hs_all = w.hout.view(N, H) if w.hscale is None else w.hout.view(N, H) * w.hscale.view(N, H)
         w.tc_operands_fresh = False
         self._join()
         self._mark("ce_fwd")
@@ -646,21 +651,26 @@ class HotPath:
             bf = torch.bfloat16
             Vk, nbk = (V + 63) // 64 * 64, nb_max
             w.pz = torch.empty((nb_max, V), dtype=torch.float32, device=self.device)
-            w.pz_hi = torch.zeros((nb_max, Vk), dtype=bf, device=self.device)
-            w.pz_lo = torch.zeros((nb_max, Vk), dtype=bf, device=self.device) if x3 else None
-            w.pzt_hi = torch.zeros((V, nbk), dtype=bf, device=self.device)
-            w.pzt_lo = torch.zeros((V, nbk), dtype=bf, device=self.device) if x3 else None
-        Vk, nbk = w.pz_hi.shape[1], w.pzt_hi.shape[1]
+            if tc:
+                w.pz_hi = torch.zeros((nb_max, Vk), dtype=bf, device=self.device)
+                w.pz_lo = torch.zeros((nb_max, Vk), dtype=bf, device=self.device) if x3 else None
+                w.pzt_hi = torch.zeros((V, nbk), dtype=bf, device=self.device)
+                w.pzt_lo = torch.zeros((V, nbk), dtype=bf, device=self.device) if x3 else None
+        if tc:
+            Vk, nbk = w.pz_hi.shape[1], w.pzt_hi.shape[1]
         n_panels = (N + nb_max - 1) // nb_max
         parts = torch.zeros(n_panels, dtype=torch.float32, device=self.device)
         el = 2                                                       # bytes per bf16
         for p, n0 in enumerate(range(0, N, nb_max)):
             nb = min(nb_max, N - n0)
             off = lambda t, elems, size: ctypes.c_void_p(t.data_ptr() + elems * size) if t is not None else None
-            Z = w.pz[:nb]
-            call("seqrec_gemm_tc", off(w.A_hi, n0 * Hk, el), off(w.A_lo, n0 * Hk, el), ptr(self.Bt_hi), ptr(self.Bt_lo),
-                 ptr(self.b_out), ptr(Z), nb, V, Hk, Hk, Hk, V, 0, x3, st)
             sl = slice(n0, n0 + nb)
+            Z = w.pz[:nb]
+            if tc:
+                call("seqrec_gemm_tc", off(w.A_hi, n0 * Hk, el), off(w.A_lo, n0 * Hk, el), ptr(self.Bt_hi),
+                     ptr(self.Bt_lo), ptr(self.b_out), ptr(Z), nb, V, Hk, Hk, Hk, V, 0, x3, st)
+            else:
+                call("seqrec_gemm_nn", ptr(hs_all[sl]), ptr(self.W_out), ptr(self.b_out), ptr(Z), nb, V, H, 0, st)
             m, s_, zy, mask = w.m[sl], w.s[sl], w.zy[sl], w.mask.view(-1)[sl]
             tg = w.tgt.view(-1)[sl]
             call("seqrec_softmax_rows_stats", ptr(Z), None, ptr(m), ptr(s_), None, nb, V, st)
@@ -671,17 +681,21 @@ class HotPath:
             call("seqrec_softmax_rows_dlogit", ptr(Z), ptr(tg), ptr(m), ptr(s_), ptr(w.coef[sl]), nb, V, st)
             if self.db_out is not None:
                 call("seqrec_colsum", ptr(Z), ptr(self.db_out), nb, V, V, st)
-            call("seqrec_split_bf16_both", ptr(Z), None, ptr(w.pz_hi), ptr(w.pz_lo), ptr(w.pzt_hi), ptr(w.pzt_lo), nb, V,
-                 Vk, nbk, st)
-            # dh[panel] = dZ . W_out^T   (K = V; W_out rows are K-major over the items: the Wb operand)
             dh = w.dh.view(N, H)[sl]
-            call("seqrec_gemm_tc", ptr(w.pz_hi), ptr(w.pz_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), None, ptr(dh), nb, H, V,
-                 Vk, self.Vp, H, 0, x3, st)
+            if tc:
+                call("seqrec_split_bf16_both", ptr(Z), None, ptr(w.pz_hi), ptr(w.pz_lo), ptr(w.pzt_hi), ptr(w.pzt_lo), nb,
+                     V, Vk, nbk, st)
+                # dh[panel] = dZ . W_out^T   (K = V; W_out rows are K-major over the items: the Wb operand)
+                call("seqrec_gemm_tc", ptr(w.pz_hi), ptr(w.pz_lo), ptr(self.Wb_hi), ptr(self.Wb_lo), None, ptr(dh), nb, H,
+                     V, Vk, self.Vp, H, 0, x3, st)
+                # dW_out += hs[panel]^T . dZ   (K = the panel's tokens: Ht columns [n0, n0 + nb), dZ^T rows)
+                call("seqrec_gemm_tc", off(w.Ht_hi, n0, el), off(w.Ht_lo, n0, el), ptr(w.pzt_hi), ptr(w.pzt_lo), None,
+                     ptr(self.dW_out), H, V, nb, w.Np, nbk, V, 1, x3, st)
+            else:
+                call("seqrec_gemm_nt", ptr(Z), ptr(self.W_out), ptr(dh), nb, H, V, V, V, H, 0, st)
+                call("seqrec_gemm_tn_atomic", ptr(hs_all[sl]), ptr(Z), ptr(self.dW_out), H, V, nb, st)
             if w.hscale is not None:
                 dh.mul_(w.hscale.view(N, H)[sl])
-            # dW_out += hs[panel]^T . dZ   (K = the panel's tokens: Ht columns [n0, n0 + nb), dZ^T rows)
-            call("seqrec_gemm_tc", off(w.Ht_hi, n0, el), off(w.Ht_lo, n0, el), ptr(w.pzt_hi), ptr(w.pzt_lo), None,
-                 ptr(self.dW_out), H, V, nb, w.Np, nbk, V, 1, x3, st)
         if train:
             torch.sum(parts, dim=0, keepdim=True, out=self.step_loss_sum)
             self.n_valid_f.copy_(w.n_valid_i)
@@ -1179,8 +1193,13 @@ class HotPath:
         w = self.work(int(B), int(T))
         self._stage(w, ids, None, x_dense)
         self._forward_hidden(w, training=False)
-        self._forward_ce(w, with_targets=False)
         probs = torch.empty((w.B, w.T, self.V), dtype=torch.float32, device=self.device)
+        if w.tc["panel"]:
+            # hidden sizes above 256: logits through the plain GEMM (model.predict materialises (N,V) by definition)
+            Z, m, s_ = self._wide_logits(w.hout.view(w.N, self.H))
+            call("seqrec_softmax_rows_probs", ptr(Z), ptr(m), ptr(s_), ptr(probs), w.T, w.B, self.V, self.stream)
+            return probs
+        self._forward_ce(w, with_targets=False)
         call("seqrec_predict_probs", ptr(w.hout), ptr(self.W_out), ptr(self.b_out), ptr(w.m), ptr(w.s), ptr(probs),
              w.T, w.B, self.H, self.V, self.stream)
         return probs
@@ -1199,6 +1218,17 @@ class HotPath:
         self._forward_ce(w)
         return w.py.view(w.T, w.B).t().contiguous()
 
+    def _wide_logits(self, rows):
+        """Hidden sizes above 256: logits of `rows` (n, H) materialised through the plain GEMM (tcgen05 when it fills
+        tiles) with their per-row softmax statistics.  Scoring helper: n is a batch of rows, never the training set."""
+        n = rows.shape[0]
+        Z = torch.empty((n, self.V), dtype=torch.float32, device=self.device)
+        gemm(self, rows.contiguous(), self.W_out, Z, "nn", bias=self.b_out)
+        m = torch.empty(n, dtype=torch.float32, device=self.device)
+        s_ = torch.empty(n, dtype=torch.float32, device=self.device)
+        call("seqrec_softmax_rows_stats", ptr(Z), None, ptr(m), ptr(s_), None, n, self.V, self.stream)
+        return Z, m, s_
+
     def topk_batch(self, ids, k, last_step_only=True, x_dense=None):
         """Top-k next items: (B,k) ids and probabilities for the last step, or (B,T,k) for every step."""
         B, T = (ids.shape if ids is not None else x_dense.shape[:2])
@@ -1207,6 +1237,16 @@ class HotPath:
         self._forward_hidden(w, training=False)
         if self.vocab_parallel:
             return self._topk_vp(w, int(k), last_step_only)
+        if w.tc["panel"]:
+            rows = w.hout[w.T - 1] if last_step_only else w.hout.view(w.N, self.H)
+            Z, m, s_ = self._wide_logits(rows)
+            order = torch.sort(Z, dim=1, descending=True, stable=True)      # ties: the lower item id first
+            top_i = order.indices[:, :k].to(torch.int32).contiguous()
+            top_p = torch.exp(order.values[:, :k] - m.unsqueeze(1)) / s_.unsqueeze(1)
+            if last_step_only:
+                return top_i, top_p.contiguous()
+            return (top_i.view(w.T, w.B, k).permute(1, 0, 2).contiguous(),
+                    top_p.view(w.T, w.B, k).permute(1, 0, 2).contiguous())
         if last_step_only:
             # softmax statistics of the last step only: a (B, 1) problem over the rows hout[T-1]
             wl = self.work(int(B), 1)

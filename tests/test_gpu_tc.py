@@ -193,14 +193,16 @@ def test_hidden_sizes_above_256_run_on_the_tensor_core_gemm(cell, act, V, H, T, 
     hot, ora, ws = make_pair(cell, act, V, H, seed=41, bias_scale=0.1, tc="x3")
     ids, tgt = synthetic.make_batch(V, T, B, seed=42, min_len=1)
     w = hot.work(B, T)
-    assert w.tc["panel"] and not w.tc["fwd"]
+    assert w.tc["panel"] and w.tc["panel_tc"] and not w.tc["fwd"]
     loss, grads, extra = hot.grad_batch(ids, tgt)
     rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
     assert abs(loss - float(rl)) <= 1e-4 * abs(float(rl))
     for name, g, r in zip(["W_in", "U", "b", "W_out"], grads, rg):
         assert rel_err(g, r.numpy()) <= 1e-4, (name, rel_err(g, r.numpy()))
-    simt = HotPath(cell, act, V, H, V, weights=ws, tc="off")
-    _, g2, e2 = simt.grad_batch(ids, tgt)
+    simt = HotPath(cell, act, V, H, V, weights=ws, tc="off")       # same panels on the fp32 SIMT GEMMs
+    assert simt.work(B, T).tc["panel"]
+    l2, g2, e2 = simt.grad_batch(ids, tgt)
+    assert abs(l2 - float(rl)) <= 1e-5 * abs(float(rl))
     assert rel_err(extra["dh"], e2["dh"]) <= 1e-4 and rel_err(grads[3], g2[3]) <= 1e-4
     py = hot.target_prob_batch(ids, tgt).cpu().numpy()
     ref = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)
@@ -210,6 +212,25 @@ def test_hidden_sizes_above_256_run_on_the_tensor_core_gemm(cell, act, V, H, T, 
         l1 = float(hot.train_batch(ids, tgt).item())
         l2, _, _ = ora.train_step(as_t(ids), as_t(tgt), as_t(ids) >= 0, lr=0.05, epsilon=1e-8, clipnorm=1.0)
         assert abs(l1 - float(l2)) <= 2e-4 * abs(float(l2)), (step, l1, float(l2))
+
+
+def test_msnbc_tuning_shapes_with_wide_hidden_layers():
+    """tune_params_msnbc.py:53 sweeps z_dim in {100, 200, 500, 1000} on the 17-item MSNBC catalog: the wide layers take
+    the panel path with the fp32 SIMT products (17 items do not fill a tensor-core tile); oracle parity, LSTM/relu."""
+    V, T, B = 17, 12, 20
+    for H in (500, 1000):
+        hot, ora, _ = make_pair("LSTM", "relu", V, H, seed=51, tc="x3")
+        ids, tgt = synthetic.make_batch(V, T, B, seed=52, min_len=1, zipf_s=0.5)
+        w = hot.work(B, T)
+        assert w.tc["panel"] and not w.tc["panel_tc"]
+        loss, grads, _ = hot.grad_batch(ids, tgt)
+        rl, rg = ora.grads(as_t(ids), as_t(tgt), as_t(ids) >= 0)
+        assert abs(loss - float(rl)) <= 1e-4 * abs(float(rl))
+        for name, g, r in zip(["W_in", "U", "b", "W_out"], grads, rg):
+            assert rel_err(g, r.numpy()) <= 1e-4, (H, name, rel_err(g, r.numpy()))
+        ti, _ = hot.topk_batch(ids, 5, last_step_only=True)
+        probs = ora.predict_proba(ids=as_t(ids), mask=as_t(ids) >= 0)[:, -1]
+        assert np.array_equal(ti.cpu().numpy(), ks.topk_items(probs, 5))
 
 
 def test_cfg2_full_size_properties():
