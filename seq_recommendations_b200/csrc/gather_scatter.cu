@@ -103,48 +103,25 @@ gather_rows_kernel(const float* __restrict__ W, const float* __restrict__ bias, 
                    const uint8_t* __restrict__ mask, const float* __restrict__ in_scale, float* __restrict__ xp,
                    int64_t n_tokens, int GH) {
   if (VEC4) {
-    // Four independent 16-byte row reads in flight per thread (ids / mask first, then the four table loads, then the four
-    // streaming stores): with one load per iteration the kernel sat at ~62 % of the DRAM peak at cfg3 (ncu r2a), bound by
-    // the dependent id -> row round trip of every chunk.
     const int chunks = GH >> 2;
     const int64_t total = n_tokens * chunks;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-      int64_t nn[4];
-      int cc[4];
-      const float4* src[4];
-      float sc[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * stride;
-        src[u] = nullptr;
-        sc[u] = 1.f;
-        nn[u] = -1;
-        cc[u] = 0;
-        if (i < total) {
-          const int64_t n = i / chunks;
-          nn[u] = n;
-          cc[u] = (int)(i - n * chunks);
-          if (mask[n]) {
-            src[u] = reinterpret_cast<const float4*>(W + (int64_t)ids[n] * GH) + cc[u];
-            if (in_scale) sc[u] = in_scale[n];
-          }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t n = i / chunks;
+      const int c = (int)(i - n * chunks);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mask[n]) {
+        const int32_t id = ids[n];
+        v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)id * GH) + c);
+        if (in_scale) {
+          const float s = in_scale[n];
+          v.x *= s; v.y *= s; v.z *= s; v.w *= s;
         }
       }
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = src[u] ? __ldg(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (nn[u] < 0) continue;
-        float4 o = v[u];
-        o.x *= sc[u]; o.y *= sc[u]; o.z *= sc[u]; o.w *= sc[u];
-        if (bias) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + cc[u]);
-          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-        }
-        st_stream_f4(reinterpret_cast<float4*>(xp + nn[u] * GH) + cc[u], o);
+      if (bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
       }
+      st_stream_f4(reinterpret_cast<float4*>(xp + n * GH) + c, v);
     }
   } else {
     const int64_t total = n_tokens * GH;

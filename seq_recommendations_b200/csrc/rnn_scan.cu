@@ -11,8 +11,6 @@
 #define RNN_THREADS 512
 
 // acc[r] += sum_{k in [k0,k1)} vec[r*ldv + k] * mat[k*ldm + col]      (vec in shared memory, mat shared or global)
-// Four independent partial sums per row: one accumulator made the H-long FFMA chain (4 cycles each, dependent) the
-// latency of a timestep; with four the step is bound by reading U from shared memory.
 template <int RB>
 __device__ __forceinline__ void mv_accum(float (&acc)[RB], const float* __restrict__ vec, int ldv,
                                          const float* __restrict__ mat, int ldm, int col, int k0, int k1) {
@@ -23,10 +21,6 @@ __device__ __forceinline__ void mv_accum(float (&acc)[RB], const float* __restri
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = fmaf(vec[r * ldv + k], u, acc[r]);
   }
-  float p1[RB], p2[RB], p3[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) { p1[r] = 0.f; p2[r] = 0.f; p3[r] = 0.f; }
-#pragma unroll 2
   for (; k + 4 <= k1; k += 4) {
     const float u0 = mat[(size_t)(k + 0) * ldm + col];
     const float u1 = mat[(size_t)(k + 1) * ldm + col];
@@ -36,33 +30,17 @@ __device__ __forceinline__ void mv_accum(float (&acc)[RB], const float* __restri
     for (int r = 0; r < RB; ++r) {
       const float4 h = *reinterpret_cast<const float4*>(vec + r * ldv + k);
       acc[r] = fmaf(h.x, u0, acc[r]);
-      p1[r] = fmaf(h.y, u1, p1[r]);
-      p2[r] = fmaf(h.z, u2, p2[r]);
-      p3[r] = fmaf(h.w, u3, p3[r]);
+      acc[r] = fmaf(h.y, u1, acc[r]);
+      acc[r] = fmaf(h.z, u2, acc[r]);
+      acc[r] = fmaf(h.w, u3, acc[r]);
     }
   }
-#pragma unroll
-  for (int r = 0; r < RB; ++r) acc[r] += (p1[r] + p2[r]) + p3[r];
   for (; k < k1; ++k) {
     const float u = mat[(size_t)k * ldm + col];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = fmaf(vec[r * ldv + k], u, acc[r]);
   }
 }
-
-__device__ __forceinline__ void scan_cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void scan_cp_async16(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void scan_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void scan_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }
 
@@ -85,9 +63,7 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
   float* c_s = h_s + RB * Hp;        // [RB][Hp]   LSTM cell state / GRU r*h
   float* a_s = c_s + RB * Hp;        // [RB][GHp]  pre-activations (GRU: z,r post-activation after phase 1b)
   float* hm_s = a_s + RB * GHp;      // [G][RB][Hp] h * rm[g] (RD only)
-  float* x_s = hm_s + (RD ? G * RB * Hp : 0);   // [2][RB][GHp] input projection of this / the next step (cp.async)
-  int* m_s = reinterpret_cast<int*>(x_s + 2 * RB * GHp);   // [2][RB] mask of this / the next step
-  float* U_s = reinterpret_cast<float*>(m_s + 2 * RB + ((2 * RB) & 3 ? 4 - ((2 * RB) & 3) : 0));   // [H][GH] (USMEM only)
+  float* U_s = hm_s + (RD ? G * RB * Hp : 0);   // [H][GH]    (USMEM only)
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * RB;
 
@@ -98,37 +74,16 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
   if (USMEM) {
     for (int i = tid; i < H * GH; i += RNN_THREADS) U_s[i] = U[i];
   }
-  // everything a step reads from global memory (its rows of xp, its mask bytes) is fetched ONE STEP AHEAD into shared
-  // memory, so no global-load latency sits on the sequential path
-  const bool vec16 = (GH & 3) == 0;
-  auto prefetch = [&](int t) {
-    if (t < T) {
-      float* dst = x_s + (t & 1) * RB * GHp;
-      for (int r = 0; r < RB; ++r) {
-        if (b0 + r >= B) break;
-        const float* src = xg + ((size_t)t * B + b0 + r) * GH;
-        if (vec16) { for (int j = tid * 4; j < GH; j += RNN_THREADS * 4) scan_cp_async16(dst + r * GHp + j, src + j); }
-        else       { for (int j = tid; j < GH; j += RNN_THREADS) scan_cp_async4(dst + r * GHp + j, src + j); }
-      }
-      if (tid < RB) m_s[(t & 1) * RB + tid] = (b0 + tid < B) ? (mask[(size_t)t * B + b0 + tid] != 0) : 0;
-    }
-    scan_cp_commit();
-  };
-  prefetch(0);
   __syncthreads();
   const int J1 = (CELL == SEQREC_CELL_GRU) ? 2 * H : GH;
 
   for (int t = 0; t < T; ++t) {
     const size_t tok0 = (size_t)t * B + b0;
-    const float* xc = x_s + (t & 1) * RB * GHp;
-    prefetch(t + 1);                               // lands behind this step's products
-    scan_cp_wait<1>();                             // this step's rows (issued one step ago) have landed ...
-    __syncthreads();                               // ... for every thread
     // ---- phase 1: a = xp + h.U (GRU: z and r blocks only)
     for (int j = tid; j < J1; j += RNN_THREADS) {
       float acc[RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) acc[r] = xc[r * GHp + j];
+      for (int r = 0; r < RB; ++r) acc[r] = (b0 + r < B) ? xg[(tok0 + r) * GH + j] : 0.f;
       const float* hv_s = RD ? hm_s + (j / H) * RB * Hp : h_s;   // gate block of column j
       if (USMEM) mv_accum<RB>(acc, hv_s, Hp, U_s, GH, j, 0, H);
       else       mv_accum<RB>(acc, hv_s, Hp, U, GH, j, 0, H);
@@ -151,7 +106,7 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
       for (int j = tid; j < H; j += RNN_THREADS) {
         float acc[RB];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r] = xc[r * GHp + 2 * H + j];
+        for (int r = 0; r < RB; ++r) acc[r] = (b0 + r < B) ? xg[(tok0 + r) * GH + 2 * H + j] : 0.f;
         if (USMEM) mv_accum<RB>(acc, c_s, Hp, U_s, GH, 2 * H + j, 0, H);
         else       mv_accum<RB>(acc, c_s, Hp, U, GH, 2 * H + j, 0, H);
 #pragma unroll
@@ -164,7 +119,7 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
       const int r = i / H, u = i - r * H;
       if (b0 + r >= B) continue;
       const size_t tok = tok0 + r;
-      const bool m = m_s[(t & 1) * RB + r] != 0;
+      const bool m = mask[tok] != 0;
       const float hp = h_s[r * Hp + u];
       float hn;
       if (CELL == SEQREC_CELL_LSTM) {
@@ -201,7 +156,6 @@ rnn_forward_kernel(float* __restrict__ xg, const float* __restrict__ U, const ui
     }
     __syncthreads();
   }
-  scan_cp_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -222,10 +176,7 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
   float* dd_s = dc_s + RB * Hp;       // [RB][Hp]  direct (non-matmul) part of dL/dh_{t-1}
   float* hp_s = dd_s + RB * Hp;       // [RB][Hp]  GRU: h_{t-1}
   float* da_s = hp_s + RB * Hp;       // [RB][GHp] pre-activation gradients of this step
-  constexpr int NI = (CELL == SEQREC_CELL_LSTM) ? 7 : (CELL == SEQREC_CELL_GRU ? 5 : 2);
-  float* in_s = da_s + RB * GHp;      // [2][RB][NI][Hp] per-step inputs of this / the next (earlier) step (cp.async)
-  int* m_s = reinterpret_cast<int*>(in_s + 2 * RB * NI * Hp);   // [2][RB]
-  float* Ut_s = reinterpret_cast<float*>(m_s + ((2 * RB + 3) & ~3));   // [GH][H]   (USMEM only)
+  float* Ut_s = da_s + RB * GHp;      // [GH][H]   (USMEM only)
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * RB;
 
@@ -234,52 +185,17 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
   if (USMEM) {
     for (int i = tid; i < H * GH; i += RNN_THREADS) Ut_s[i] = Ut[i];
   }
-  // Everything step t reads from global memory -- dL/dhout, the saved gates, c_t / c_{t-1} (LSTM), h_{t-1} (GRU), the
-  // mask -- is fetched while step t+1 is processed:
-  //   in_s[buf][r][0] = dL/dhout; LSTM [1..4] = i, f, g, o, [5] = c_t, [6] = c_{t-1};
-  //   GRU [1..3] = z, r, hh, [4] = h_{t-1}; SimpleRNN [1] = y_t
-  auto prefetch = [&](int t) {
-    if (t >= 0) {
-      float* dst = in_s + (size_t)(t & 1) * RB * NI * Hp;
-      for (int i = tid; i < RB * H; i += RNN_THREADS) {
-        const int r = i / H, u = i - r * H;
-        if (b0 + r >= B) continue;
-        const size_t tok = (size_t)t * B + b0 + r;
-        float* d = dst + (size_t)r * NI * Hp + u;
-        scan_cp_async4(d, dhout + tok * H + u);
-        if (CELL == SEQREC_CELL_LSTM) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) scan_cp_async4(d + (1 + g) * Hp, xg + tok * GH + g * H + u);
-          scan_cp_async4(d + 5 * Hp, cst + tok * H + u);
-          if (t > 0) scan_cp_async4(d + 6 * Hp, cst + (tok - B) * H + u);
-        } else if (CELL == SEQREC_CELL_GRU) {
-#pragma unroll
-          for (int g = 0; g < 3; ++g) scan_cp_async4(d + (1 + g) * Hp, xg + tok * GH + g * H + u);
-          if (t > 0) scan_cp_async4(d + 4 * Hp, hout + (tok - B) * H + u);
-        } else {
-          scan_cp_async4(d + Hp, hout + tok * H + u);
-        }
-      }
-      if (tid < RB) m_s[(t & 1) * RB + tid] = (b0 + tid < B) ? (mask[(size_t)t * B + b0 + tid] != 0) : 0;
-    }
-    scan_cp_commit();
-  };
-  prefetch(T - 1);
   __syncthreads();
 
   for (int t = T - 1; t >= 0; --t) {
     const size_t tok0 = (size_t)t * B + b0;
-    const float* ic = in_s + (size_t)(t & 1) * RB * NI * Hp;
-    prefetch(t - 1);
-    scan_cp_wait<1>();                             // this step's inputs (own elements) have landed
-    // ---- phase 1: elementwise gate gradients (the (r, u) -> thread mapping of the prefetch: own elements only)
+    // ---- phase 1: elementwise gate gradients
     for (int i = tid; i < RB * H; i += RNN_THREADS) {
       const int r = i / H, u = i - r * H;
       if (b0 + r >= B) continue;
       const size_t tok = tok0 + r;
-      const bool m = m_s[(t & 1) * RB + r] != 0;
-      const float* in = ic + (size_t)r * NI * Hp + u;
-      const float dh = in[0] + dh_s[r * Hp + u];
+      const bool m = mask[tok] != 0;
+      const float dh = dhout[tok * H + u] + dh_s[r * Hp + u];
       float* da = da_s + r * GHp;
       if (!m) {
         // masked step: h_t = h_{t-1}, c_t = c_{t-1}; the candidate is discarded, so no gate gradient
@@ -289,10 +205,11 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
         if (CELL == SEQREC_CELL_GRU) { dc_s[r * Hp + u] = 0.f; hp_s[r * Hp + u] = 0.f; cst[tok * H + u] = 0.f; }
         continue;
       }
+      const float* gp = xg + tok * GH;
       if (CELL == SEQREC_CELL_LSTM) {
-        const float ig = in[Hp], fg = in[2 * Hp], gg = in[3 * Hp], og = in[4 * Hp];
-        const float ct = in[5 * Hp];
-        const float cp = (t > 0) ? in[6 * Hp] : 0.f;
+        const float ig = gp[u], fg = gp[H + u], gg = gp[2 * H + u], og = gp[3 * H + u];
+        const float ct = cst[tok * H + u];
+        const float cp = (t > 0) ? cst[(tok - B) * H + u] : 0.f;
         const float ac = act_f<ACT>(ct);
         const float d_o = dh * ac;
         const float dc = dc_s[r * Hp + u] + dh * og * act_grad_from_y<ACT>(ac);
@@ -303,8 +220,8 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
         dc_s[r * Hp + u] = dc * fg;
         dd_s[r * Hp + u] = 0.f;
       } else if (CELL == SEQREC_CELL_GRU) {
-        const float z = in[Hp], rr = in[2 * Hp], hh = in[3 * Hp];
-        const float hp = (t > 0) ? in[4 * Hp] : 0.f;
+        const float z = gp[u], rr = gp[H + u], hh = gp[2 * H + u];
+        const float hp = (t > 0) ? hout[(tok - B) * H + u] : 0.f;
         const float dz = dh * (hp - hh);
         const float dhh = dh * (1.0f - z);
         da[u] = dz * hard_sigmoid_grad_from_y(z);
@@ -315,7 +232,7 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
         // operand of dU's candidate block (with recurrent dropout: r * h_{t-1} * rm[2])
         cst[tok * H + u] = rr * hp * (RD ? rm[((size_t)2 * B + b0 + r) * H + u] : 1.0f);
       } else {
-        const float y = in[Hp];
+        const float y = hout[tok * H + u];
         da[u] = dh * act_grad_from_y<ACT>(y);
         dd_s[r * Hp + u] = 0.f;
       }
@@ -372,7 +289,6 @@ rnn_backward_kernel(float* __restrict__ xg, const float* __restrict__ Ut, const 
     }
     __syncthreads();
   }
-  scan_cp_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -391,8 +307,7 @@ static int launch_fwd_rd(float* xg, const float* U, const uint8_t* mask, float* 
                          const float* rm, cudaStream_t st) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H, Hp = round_up4(H), GHp = round_up4(GH);
-  const size_t base = sizeof(float) * (size_t)(2 * RB * Hp + RB * GHp + (RD ? G * RB * Hp : 0) + 2 * RB * GHp) +
-                      sizeof(int) * (size_t)((2 * RB + 3) & ~3);
+  const size_t base = sizeof(float) * (size_t)(2 * RB * Hp + RB * GHp + (RD ? G * RB * Hp : 0));
   const size_t with_u = base + sizeof(float) * (size_t)H * GH;
   const int grid = ceil_div(B, RB);
   if (with_u <= kMaxDynSmem) {
@@ -421,9 +336,7 @@ static int launch_bwd_rd(float* xg, const float* Ut, const uint8_t* mask, const 
                          const float* dhout, int T, int B, int H, const float* rm, cudaStream_t st) {
   constexpr int G = (CELL == SEQREC_CELL_LSTM) ? 4 : (CELL == SEQREC_CELL_GRU ? 3 : 1);
   const int GH = G * H, Hp = round_up4(H), GHp = round_up4(GH);
-  constexpr int NI = (CELL == SEQREC_CELL_LSTM) ? 7 : (CELL == SEQREC_CELL_GRU ? 5 : 2);
-  const size_t base = sizeof(float) * (size_t)(4 * RB * Hp + RB * GHp + 2 * RB * NI * Hp) +
-                      sizeof(int) * (size_t)((2 * RB + 3) & ~3);
+  const size_t base = sizeof(float) * (size_t)(4 * RB * Hp + RB * GHp);
   const size_t with_u = base + sizeof(float) * (size_t)H * GH;
   const int grid = ceil_div(B, RB);
   if (with_u <= kMaxDynSmem) {

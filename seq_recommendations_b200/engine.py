@@ -840,10 +840,11 @@ class HotPath:
         """forward + backward + exchange + update on the staged batch (everything after the host->device copy).
 
         Data parallel: no collective sits between the forward and the backward pass.  The backward runs
-        un-normalised; [n_valid, loss_sum] ride in the step-float block in front of dU | db and are summed over the
-        ranks by the SAME all-reduce (plus the dense dW_in when the catalog is small enough for the dense exchange:
-        the three live in one allocation).  dW_out / db_out are reduced behind the recurrent backward pass.  The
-        optimiser kernels then divide by the global n_valid."""
+        un-normalised; [n_valid, loss_sum] ride in the step-float block that sits between dW_in and dU | db in ONE
+        gradient allocation and are summed over the ranks together with a neighbour: with dW_in (dense exchange of a
+        small catalog; started right after the scatter-add, it travels behind the dU GEMMs) or with dU | db.  dW_out /
+        db_out are reduced behind the recurrent backward pass.  The optimiser kernels then divide by the global
+        n_valid.  Three all-reduces per step (two in the row-exchange mode), none of them blocking a kernel launch."""
         st = self.stream
         comm = self.comm
         self._split_version = -1                  # a training step always follows a weight update: re-stage W_out
@@ -897,6 +898,10 @@ class HotPath:
             self.dW_in.zero_()
             gemm(self, w.x_dense.view(w.N, self.F), w.xg.view(w.N, self.GH), self.dW_in, "tn")
             dense_in = comm.enabled
+        if comm.enabled and dense_in:
+            # dense dW_in (small catalogs) and the step floats [n_valid, loss_sum] are adjacent in the gradient buffer:
+            # ONE all-reduce, started as soon as the scatter-add is done -- it travels while the dU GEMMs still run
+            pending.append(comm.all_reduce_sum(self._gbuf[:self._fgh + 64], async_op=True))
         self._mark("rnn_wgrad")
         if branch_wgrad:
             self._join()
@@ -904,7 +909,8 @@ class HotPath:
             self._rnn_weight_grad(w)
         self._mark("allreduce")
         if comm.enabled:
-            lo = 0 if dense_in else self._fgh
+            # dU | db (and the step floats in front of them when they did not travel with dW_in)
+            lo = self._fgh + 64 if dense_in else self._fgh
             pending.append(comm.all_reduce_sum(self._gbuf[lo:self._fgh + 64 + head], async_op=True))
 
         # ---- global-norm clip + Adagrad (needs every reduced gradient: clipnorm is global)

@@ -19,6 +19,11 @@ TOL = 1e-4
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def make_ids(V, T, n, seed):
+    from seq_recommendations_b200 import synthetic
+    return synthetic.make_batch(V, T, n, seed=seed, min_len=1)
+
+
 def mc_data(n=120, T=20):
     g = np.load(os.path.join(ROOT, "tests", "golden", "mc_sequences.npz"))
     seqs = [g["flat"][g["offs"][i]:g["offs"][i + 1]].tolist() for i in range(n)]
@@ -222,3 +227,59 @@ def test_device_likelihood_metrics_match_golden_and_oracle(golden_dir):
         a = M.compute_likelihood_cut(ragged, 0.7, count_first_prob=first)
         b = ol.compute_likelihood_cut([r.astype(np.float64) for r in ragged], 0.7, count_first_prob=first)
         assert np.allclose(a, b, rtol=1e-6)
+
+
+def test_state_checkpoint_resumes_with_adagrad_accumulators(tmp_path):
+    """save_state / load_state (weights + Adagrad accumulators + epoch): a resumed model continues EXACTLY like the
+    uninterrupted one; a weights-only checkpoint (the reference's, model.py:201-218) restarts the accumulators and does
+    not.  A path that claims to be HDF5 gets '.npz' appended; a real HDF5 file is refused with a clear message."""
+    V, H, T, B = 400, 32, 8, 64
+    ids, tgt = make_ids(V, T, 4 * B, seed=3)
+
+    def build():
+        m = M.RNNFullModel(T, V, V, z_dim=H, rnn_type="GRU", z_to_z_activation="tanh", y_to_y=False, x_to_y=False, seed=5)
+        m.compile_model(optimizer=Adagrad(lr=0.05, epsilon=1e-8, clipnorm=1.0))
+        return m
+
+    def steps(m, lo, hi):
+        return [m.model.train_on_batch(ids[b * B:(b + 1) * B], tgt[b * B:(b + 1) * B]) for b in range(lo, hi)]
+
+    a = build()
+    steps(a, 0, 2)
+    ck = str(tmp_path / "state.hdf5")
+    a.model.save_state(ck, epoch=7)
+    assert os.path.exists(ck + ".npz") and not os.path.exists(ck)
+    wk = str(tmp_path / "weights_only")
+    a.model.save_weights(wk)
+    rest = steps(a, 2, 4)
+    b = build()
+    assert b.model.load_state(ck) == 7
+    assert steps(b, 2, 4) == rest                                   # bit-identical continuation
+    for x, y in zip(a.model.get_weights(), b.model.get_weights()):
+        assert np.array_equal(x, y)
+    c = build()
+    c.model.load_weights(wk)
+    assert steps(c, 2, 4)[1] != rest[1]                             # accumulators restarted: a different trajectory
+    fake = tmp_path / "keras.h5"
+    fake.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(IOError, match="HDF5"):
+        c.model.load_weights(str(fake))
+
+
+def test_fit_epoch_from_hbm_equals_fit_from_host_batches(monkeypatch):
+    """fit keeps the id arrays in HBM and gathers each shuffled batch on the device; the losses must equal the host-slicing
+    path batch for batch (same shuffle)."""
+    V, H, T, B = 300, 24, 7, 32
+    ids, tgt = make_ids(V, T, 5 * B + 7, seed=9)
+    hist = []
+    for resident in (True, False):
+        m = M.RNNFullModel(T, V, V, z_dim=H, rnn_type="LSTM", y_to_y=False, x_to_y=False, seed=2)
+        m.compile_model(optimizer=Adagrad(lr=0.05, epsilon=1e-8, clipnorm=1.0))
+        if not resident:
+            monkeypatch.setattr(type(m.model), "_resident", lambda self, a: None)
+        np.random.seed(11)
+        h = m.fit_model(ids, tgt, validation_data=(ids, tgt), n_epochs=2, batch_size=B, verbose=0)
+        hist.append((h.history["loss"], h.history["val_loss"], m.model.get_weights()))
+    assert hist[0][0] == hist[1][0] and hist[0][1] == hist[1][1]
+    for x, y in zip(hist[0][2], hist[1][2]):
+        assert np.array_equal(x, y)
