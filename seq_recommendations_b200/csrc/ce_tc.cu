@@ -189,43 +189,101 @@ __device__ __forceinline__ int cta_of(int64_t w, int64_t total) { return (int)((
 // With the contiguous split above the G CTAs sit at G different positions of the streamed operand at any instant, so
 // every streamed tile is fetched from HBM by almost every CTA that needs it (ncu, cfg3: 46 GB of DRAM reads for 0.3 GB
 // of operands).  Here CTA c takes the WHOLE outer tiles c, c+G, c+2G, ... and walks the inner (streamed) index from 0
-// in each of them: all CTAs stream the same tiles at the same time and the L2 serves G-1 of every G reads.  Only the
-// n_outer % G outer tiles of the last, partial wave are split stream-K style so that no SM idles.
-// Same interface as Share, over a CTA-local item index w in [w0 = 0, w1).
+// in each of them: all CTAs stream the same tiles at the same time and the L2 serves G-1 of every G reads.
+// The R = n_outer % G outer tiles of the last, partial wave are cut into p PARTS of the inner range each (p chosen so
+// that R*p work units fill the G CTAs in as few rounds as possible) and handed out part-major: the CTAs of a round
+// work on at most two different parts, i.e. they still walk the streamed operand in (two) lock-step fronts.  (Round 1
+// split the partial wave stream-K style, which put every CTA at its own inner position: at cfg3 the item-stationary dW
+// kernel -- 95 of 391 outer tiles in the partial wave -- read 8.2 GB from DRAM per launch for 0.26 GB of operands,
+// ncu r2b.)  Same interface as Share, over a CTA-local item index w in [w0 = 0, w1).
 struct WaveShare {
   int w0, w1, n_inner;
   int full_items;          // items of the full waves owned by this CTA = rounds * n_inner
   int tail_o0;             // first outer tile of the partial wave
-  int t0, t1;              // this CTA's contiguous share of the partial wave's (outer, inner) pairs
-  FastDiv fd;
+  int R, L, n_units;       // partial wave: outer tiles, inner tiles per part, work units = R * parts
+  FastDiv fd, fdR;
+  __device__ __forceinline__ int part_len(int part) const { return min(L, n_inner - part * L); }
   __device__ __forceinline__ WaveShare(int n_outer, int n_inner_) : n_inner(n_inner_) {
     const int G = (int)gridDim.x, c = (int)blockIdx.x;
     const int rounds = n_outer / G;
     full_items = rounds * n_inner;
     tail_o0 = rounds * G;
-    const int64_t tail_total = (int64_t)(n_outer - tail_o0) * n_inner;
-    t0 = (int)(tail_total * c / G);
-    t1 = (int)(tail_total * (c + 1) / G);
+    R = n_outer - tail_o0;
+    L = n_inner;
+    n_units = 0;
     w0 = 0;
-    w1 = full_items + (t1 - t0);
+    w1 = full_items;
     fd.init((uint32_t)n_inner);
+    fdR.init((uint32_t)(R > 0 ? R : 1));
+    if (R > 0) {
+      int best_p = 1;
+      long long best_cost = -1;
+      for (int p = 1; p <= 128 && p <= n_inner; ++p) {
+        const int len = (n_inner + p - 1) / p;
+        const int parts = (n_inner + len - 1) / len;
+        const long long cost = (long long)((R * parts + G - 1) / G) * len;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_p = p; }
+      }
+      L = (n_inner + best_p - 1) / best_p;
+      const int parts = (n_inner + L - 1) / L;
+      n_units = R * parts;
+      for (int u = c; u < n_units; u += G) {
+        uint32_t q, r;
+        fdR.divmod((uint32_t)u, q, r);
+        w1 += part_len((int)q);
+      }
+    }
+  }
+  // work item w >= full_items -> (unit u of the partial wave, position i inside the unit)
+  __device__ __forceinline__ void tail_locate(int w, int& part, int& o, int& i) const {
+    int tw = w - full_items;
+    const int G = (int)gridDim.x;
+    int u = (int)blockIdx.x;
+    uint32_t q, r;
+    for (;;) {
+      fdR.divmod((uint32_t)u, q, r);
+      const int len = part_len((int)q);
+      if (tw < len || u + G >= n_units) break;
+      tw -= len;
+      u += G;
+    }
+    part = (int)q;
+    o = tail_o0 + (int)r;
+    i = tw;
   }
   __device__ __forceinline__ int outer(int w) const {
-    uint32_t q, r;
     if (w < full_items) {
+      uint32_t q, r;
       fd.divmod((uint32_t)w, q, r);
       return (int)q * (int)gridDim.x + (int)blockIdx.x;
     }
-    fd.divmod((uint32_t)(t0 + (w - full_items)), q, r);
-    return tail_o0 + (int)q;
+    int part, o, i;
+    tail_locate(w, part, o, i);
+    return o;
   }
   __device__ __forceinline__ int inner(int w) const {
-    uint32_t q, r;
-    fd.divmod((uint32_t)(w < full_items ? w : t0 + (w - full_items)), q, r);
-    return (int)r;
+    if (w < full_items) {
+      uint32_t q, r;
+      fd.divmod((uint32_t)w, q, r);
+      return (int)r;
+    }
+    int part, o, i;
+    tail_locate(w, part, o, i);
+    return part * L + i;
   }
-  __device__ __forceinline__ bool seg_first(int w) const { return w == full_items || inner(w) == 0; }
-  __device__ __forceinline__ bool seg_last(int w) const { return w + 1 == w1 || inner(w) == n_inner - 1; }
+  __device__ __forceinline__ bool seg_first(int w) const {
+    if (w < full_items) return inner(w) == 0;
+    int part, o, i;
+    tail_locate(w, part, o, i);
+    return i == 0;
+  }
+  __device__ __forceinline__ bool seg_last(int w) const {
+    if (w + 1 == w1) return true;
+    if (w < full_items) return inner(w) == n_inner - 1;
+    int part, o, i;
+    tail_locate(w, part, o, i);
+    return i == part_len(part) - 1;
+  }
 };
 
 // ================================================================================================================
