@@ -223,6 +223,7 @@ class HotPath:
         self.ce_fused = os.environ.get("SEQREC_CE_FUSED", "1") != "0"
         # ... on the valid tokens only (pads compacted away); SEQREC_CE_COMPACT=0 keeps the full token axis
         self.ce_compact = os.environ.get("SEQREC_CE_COMPACT", "1") != "0"
+        self.ids_wait_early = os.environ.get("SEQREC_IDS_WAIT_EARLY", "1") != "0"
         self.Hk = (self.H + 63) // 64 * 64
         self.Vp = (self.V + 7) // 8 * 8
         self._w_version = 0
@@ -857,6 +858,12 @@ class HotPath:
             with self._branch():                  # bf16 operands of the updated W_out, behind gather + scan
                 self._stage_weight_operands()
         self._forward_hidden(w, training=True)
+        if ids_handle is not None and self.ids_wait_early:
+            # The logits kernels are persistent (one CTA per SM, all of its shared memory): a collective kernel that is
+            # still resident on a few SMs -- waiting for a slower rank -- keeps their last CTAs out and doubles their
+            # time.  So the ids exchange is joined HERE, behind gather + scan and before the logits kernels start.
+            ids_handle.wait()
+            ids_handle = None
         fused = self.ce_fused and w.tc["bwd"]
         if w.tc["panel"]:
             self._ce_panels(w, True, train=True, backward=True)      # statistics, dh and dW_out panel by panel
