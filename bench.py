@@ -473,7 +473,7 @@ def measure_training(args, name, cfg, comm, rank, local, steps, warmup, full=Tru
     # dominant phase: the logits kernels.  `fused` = forward statistics + dH from ONE logits pass (flash-style), then the
     # item-stationary dW kernel: 4 GEMM passes for 3 algorithmic GEMMs (x3: 12 bf16 passes); otherwise forward +
     # two recompute kernels: 5 GEMMs (x3: 15 passes)
-    ce_ms = per_step.get("ce_fwd", 0.0) + per_step.get("ce_bwd", 0.0)
+    ce_ms = sum(v for k, v in per_step.items() if k.startswith("ce_fwd")) + per_step.get("ce_bwd", 0.0)
     ce_flops = work["ce_fwd_flops"] + work["ce_bwd_flops"]
     achieved = ce_flops / (ce_ms * 1e-3) / 1e12 if ce_ms > 0 else 0.0
     gemms_issued = (4 if fused else 5) * (3 if tc_x3 else 1) if tc_bwd else 5

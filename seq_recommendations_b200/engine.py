@@ -745,13 +745,16 @@ class HotPath:
              ptr(w.zy), w.N, self.H, self.V, ptr(orig), ptr(n_c), st)
         if zy_reduce is not None:
             zy_reduce(w.zy)
+        self._mark("ce_fwd:zero")
         w.dh.zero_()
         if cp:
             acc.zero_()
         w.s.zero_()
+        self._mark("ce_fwd:fused")
         call("seqrec_ce_tc_fused", ptr(w.A_hi), ptr(w.A_lo), ptr(self.Bt_hi), ptr(self.Bt_lo), ptr(self.Wb_hi),
              ptr(self.Wb_lo), ptr(w.zy), ptr(mask), ptr(self.b_out), ptr(acc), ptr(w.s), w.N, self.H, self.Hk,
              self.V, self.Vp, 0, self.V, 1 if self.tc_x3 else 0, ptr(n_c), st)
+        self._mark("ce_fwd:finalize")
         if s_reduce is not None:
             s_reduce(w.s)
         call("seqrec_ce_finalize_mean", ptr(w.zy), ptr(w.s), ptr(w.zy), ptr(mask), ptr(w.m), ptr(w.s), ptr(w.ce),
