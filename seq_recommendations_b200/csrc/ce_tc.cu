@@ -190,20 +190,29 @@ __device__ __forceinline__ int cta_of(int64_t w, int64_t total) { return (int)((
 // every streamed tile is fetched from HBM by almost every CTA that needs it (ncu, cfg3: 46 GB of DRAM reads for 0.3 GB
 // of operands).  Here CTA c takes the WHOLE outer tiles c, c+G, c+2G, ... and walks the inner (streamed) index from 0
 // in each of them: all CTAs stream the same tiles at the same time and the L2 serves G-1 of every G reads.
-// The R = n_outer % G outer tiles of the last, partial wave are cut into p PARTS of the inner range each (p chosen so
-// that R*p work units fill the G CTAs in as few rounds as possible) and handed out part-major: the CTAs of a round
-// work on at most two different parts, i.e. they still walk the streamed operand in (two) lock-step fronts.  (Round 1
-// split the partial wave stream-K style, which put every CTA at its own inner position: at cfg3 the item-stationary dW
-// kernel -- 95 of 391 outer tiles in the partial wave -- read 8.2 GB from DRAM per launch for 0.26 GB of operands,
-// ncu r2b.)  Same interface as Share, over a CTA-local item index w in [w0 = 0, w1).
+// The R = n_outer % G outer tiles of the last, partial wave are handled in one of two ways:
+//  * streamed operand L2-resident (`stream_fits_l2`: cfg2, 10 MB): contiguous stream-K split of the R*n_inner pairs --
+//    perfectly balanced, at most two segments (accumulator flushes) per CTA, and the re-reads are L2 hits anyway;
+//  * otherwise: cut into p PARTS of the inner range each and handed out part-major, so the CTAs of a round work on at
+//    most two different parts, i.e. they still walk the streamed operand in (two) lock-step fronts.  p minimises
+//    rounds * (part length + SEG_OVH), SEG_OVH = the cost of one more segment (stationary-operand load + accumulator
+//    flush through red.global) in inner-tile units.  (Round 1 split every partial wave stream-K style, which put every
+//    CTA at its own inner position: at cfg3 the item-stationary dW kernel -- 95 of 391 outer tiles in the partial
+//    wave -- read 8.2 GB from DRAM per launch for 0.26 GB of operands, ncu r2b.  A first version of the part-major
+//    split without the overhead term cut cfg2's single partial wave into one-tile parts: 0.14 -> 0.39 ms.)
+// Same interface as Share, over a CTA-local item index w in [w0 = 0, w1).
 struct WaveShare {
+  static constexpr int SEG_OVH = 4;
   int w0, w1, n_inner;
   int full_items;          // items of the full waves owned by this CTA = rounds * n_inner
   int tail_o0;             // first outer tile of the partial wave
-  int R, L, n_units;       // partial wave: outer tiles, inner tiles per part, work units = R * parts
+  int R, L, n_units;       // part-major tail: outer tiles, inner tiles per part, work units = R * parts
+  int t0;                  // stream-K tail: first (outer, inner) pair of this CTA's contiguous share
+  bool sk;
   FastDiv fd, fdR;
   __device__ __forceinline__ int part_len(int part) const { return min(L, n_inner - part * L); }
-  __device__ __forceinline__ WaveShare(int n_outer, int n_inner_) : n_inner(n_inner_) {
+  __device__ __forceinline__ WaveShare(int n_outer, int n_inner_, bool stream_fits_l2)
+      : n_inner(n_inner_), sk(stream_fits_l2) {
     const int G = (int)gridDim.x, c = (int)blockIdx.x;
     const int rounds = n_outer / G;
     full_items = rounds * n_inner;
@@ -211,17 +220,22 @@ struct WaveShare {
     R = n_outer - tail_o0;
     L = n_inner;
     n_units = 0;
+    t0 = 0;
     w0 = 0;
     w1 = full_items;
     fd.init((uint32_t)n_inner);
     fdR.init((uint32_t)(R > 0 ? R : 1));
-    if (R > 0) {
+    if (R > 0 && sk) {
+      const int64_t tail_total = (int64_t)R * n_inner;
+      t0 = (int)(tail_total * c / G);
+      w1 += (int)(tail_total * (c + 1) / G) - t0;
+    } else if (R > 0) {
       int best_p = 1;
       long long best_cost = -1;
       for (int p = 1; p <= 128 && p <= n_inner; ++p) {
         const int len = (n_inner + p - 1) / p;
         const int parts = (n_inner + len - 1) / len;
-        const long long cost = (long long)((R * parts + G - 1) / G) * len;
+        const long long cost = (long long)((R * parts + G - 1) / G) * (len + SEG_OVH);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_p = p; }
       }
       L = (n_inner + best_p - 1) / best_p;
@@ -234,57 +248,62 @@ struct WaveShare {
       }
     }
   }
-  // work item w >= full_items -> (unit u of the partial wave, position i inside the unit)
-  __device__ __forceinline__ void tail_locate(int w, int& part, int& o, int& i) const {
-    int tw = w - full_items;
-    const int G = (int)gridDim.x;
-    int u = (int)blockIdx.x;
+  // Position of one work item; every warp role walks its items in order with start() / advance(), which costs a few
+  // integer operations per item (no division outside a change of work unit).
+  struct Walk {
+    int o, in;               // outer (stationary) tile, inner (streamed) tile
+    bool first, last;        // first / last item of a segment (= one residency of the stationary operand)
+    int w, u, i, len;        // item index; part-major tail: unit, position inside it, its length
+  };
+  __device__ __forceinline__ void unit_enter(Walk& k) const {
     uint32_t q, r;
-    for (;;) {
-      fdR.divmod((uint32_t)u, q, r);
-      const int len = part_len((int)q);
-      if (tw < len || u + G >= n_units) break;
-      tw -= len;
-      u += G;
-    }
-    part = (int)q;
-    o = tail_o0 + (int)r;
-    i = tw;
+    fdR.divmod((uint32_t)k.u, q, r);
+    k.len = part_len((int)q);
+    k.o = tail_o0 + (int)r;
+    k.in = (int)q * L;
+    k.i = 0;
   }
-  __device__ __forceinline__ int outer(int w) const {
-    if (w < full_items) {
+  __device__ __forceinline__ void tail_start(Walk& k) const {
+    if (sk) {
       uint32_t q, r;
-      fd.divmod((uint32_t)w, q, r);
-      return (int)q * (int)gridDim.x + (int)blockIdx.x;
+      fd.divmod((uint32_t)t0, q, r);
+      k.o = tail_o0 + (int)q;
+      k.in = (int)r;
+      k.i = 0;                                 // the first segment may start mid-tile
+    } else {
+      k.u = (int)blockIdx.x;
+      unit_enter(k);
     }
-    int part, o, i;
-    tail_locate(w, part, o, i);
-    return o;
   }
-  __device__ __forceinline__ int inner(int w) const {
-    if (w < full_items) {
-      uint32_t q, r;
-      fd.divmod((uint32_t)w, q, r);
-      return (int)r;
+  __device__ __forceinline__ void flags(Walk& k) const {
+    if (k.w < full_items) { k.first = k.in == 0; k.last = k.in == n_inner - 1; }
+    else if (sk)          { k.first = k.i == 0;  k.last = k.in == n_inner - 1; }
+    else                  { k.first = k.i == 0;  k.last = k.i == k.len - 1; }
+    k.last = k.last || (k.w + 1 == w1);
+  }
+  __device__ __forceinline__ void start(Walk& k) const {
+    k.w = 0; k.u = 0; k.i = 0; k.len = 0; k.o = (int)blockIdx.x; k.in = 0;
+    if (full_items == 0 && w1 > 0) tail_start(k);
+    flags(k);
+  }
+  __device__ __forceinline__ void advance(Walk& k) const {
+    ++k.w;
+    if (k.w >= w1) return;
+    if (k.w < full_items) {
+      if (++k.in == n_inner) { k.in = 0; k.o += (int)gridDim.x; }
+    } else if (k.w == full_items) {
+      tail_start(k);
+    } else if (sk) {
+      ++k.i;
+      if (++k.in == n_inner) { k.in = 0; ++k.o; k.i = 0; }
+    } else {
+      ++k.in;
+      if (++k.i == k.len) { k.u += (int)gridDim.x; unit_enter(k); }
     }
-    int part, o, i;
-    tail_locate(w, part, o, i);
-    return part * L + i;
-  }
-  __device__ __forceinline__ bool seg_first(int w) const {
-    if (w < full_items) return inner(w) == 0;
-    int part, o, i;
-    tail_locate(w, part, o, i);
-    return i == 0;
-  }
-  __device__ __forceinline__ bool seg_last(int w) const {
-    if (w + 1 == w1) return true;
-    if (w < full_items) return inner(w) == n_inner - 1;
-    int part, o, i;
-    tail_locate(w, part, o, i);
-    return i == part_len(part) - 1;
+    flags(k);
   }
 };
+using Walk = WaveShare::Walk;
 
 // ================================================================================================================
 // forward: per-row (max, sum-exp) partials of logits = A . Bt^T
@@ -880,10 +899,13 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   }
   const int n_vtiles = (v_end - v_begin + BN - 1) / BN;
   const int n_ttiles = (int)((n_tokens + BM - 1) / BM);
-  const WaveShare sh(ITEM_ST ? n_vtiles : n_ttiles, ITEM_ST ? n_ttiles : n_vtiles);
+  // both streamed operands (Y and Z blocks, hi and lo) of one pass over the inner axis: L2-resident below 32 MB
+  const int n_inner_tiles = ITEM_ST ? n_ttiles : n_vtiles;
+  const bool stream_fits_l2 = (int64_t)n_inner_tiles * (2 * NP * KB * TILE_B) <= (32ll << 20);
+  const WaveShare sh(ITEM_ST ? n_vtiles : n_ttiles, n_inner_tiles, stream_fits_l2);
   // first row of the stationary / streamed operand of work item w
-  auto p_row0 = [&](int w) { return ITEM_ST ? v_begin + sh.outer(w) * BN : sh.outer(w) * BM; };
-  auto q_row0 = [&](int w) { return ITEM_ST ? sh.inner(w) * BM : v_begin + sh.inner(w) * BN; };
+  auto p_row0 = [&](const Walk& k) { return ITEM_ST ? v_begin + k.o * BN : k.o * BM; };
+  auto q_row0 = [&](const Walk& k) { return ITEM_ST ? k.in * BM : v_begin + k.in * BN; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -919,10 +941,10 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       if (lane == 0) { ptx::prefetch_tmap(&tmX_hi); ptx::prefetch_tmap(&tmY_hi); ptx::prefetch_tmap(&tmZ_hi); }
       Pipe p;
       int seg = 0;
-      auto load_s_operands = [&](int w) {
-        if (sh.seg_first(w)) {
+      auto load_s_operands = [&](const Walk& k) {
+        if (k.first) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
-          const int row0 = p_row0(w);
+          const int row0 = p_row0(k);
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(bar_a, NP * KB * TILE_B);
             for (int kb = 0; kb < KB; ++kb) {
@@ -932,7 +954,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           }
           ++seg;
         }
-        const int q0 = q_row0(w);
+        const int q0 = q_row0(k);
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           if (ptx::elect_one()) {
@@ -944,8 +966,8 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           p.advance(NS);
         }
       };
-      auto load_z = [&](int w) {
-        const int q0 = q_row0(w);
+      auto load_z = [&](const Walk& k) {
+        const int q0 = q_row0(k);
         for (int j = 0; j < NJ; ++j)
           for (int c = 0; c < NC; ++c) {
             ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
@@ -959,10 +981,15 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             p.advance(NS);
           }
       };
-      load_s_operands(sh.w0);
+      Walk cur, nxt;
+      sh.start(cur);
+      nxt = cur;
+      load_s_operands(cur);
       for (int w = sh.w0; w < sh.w1; ++w) {
-        if (w + 1 < sh.w1) load_s_operands(w + 1);
-        load_z(w);
+        sh.advance(nxt);
+        if (w + 1 < sh.w1) load_s_operands(nxt);
+        load_z(cur);
+        cur = nxt;
       }
     }
   } else if (warp == 1) {
@@ -974,8 +1001,10 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       Pipe p;
       uint32_t ybits = 0;                                   // parity of the Y-block barrier, per slot
       int seg_s = -1, tc_s = 0;
-      for (int w = sh.w0; w < sh.w1; ++w, ++tc_s) {
-        if (sh.seg_first(w)) {
+      Walk k;
+      sh.start(k);
+      for (int w = sh.w0; w < sh.w1; ++w, ++tc_s, sh.advance(k)) {
+        if (k.first) {
           ++seg_s;
           ptx::mbar_wait(bar_a, seg_s & 1);
           ptx::tc_fence_after_sync();
@@ -994,7 +1023,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           p.advance(NS);
         }
         commit_elect(bar_tfull + 8 * buf);
-        if (sh.seg_last(w)) commit_elect(bar_afree);
+        if (k.last) commit_elect(bar_afree);
         if (w > sh.w0)                                      // the stages of G(w-1) follow S(w) in the ring
           for (int i = 0; i < NZ; ++i) p.advance(NS);
       }
@@ -1007,10 +1036,12 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       uint32_t zbits = 0;                                   // parity of the Z-block barrier, per slot
       for (int i = 0; i < KB; ++i) p.advance(NS);           // S(w0)
       int seg_d = -1, tc_d = 0;
-      for (int w = sh.w0; w < sh.w1; ++w) {
+      Walk k;
+      sh.start(k);
+      for (int w = sh.w0; w < sh.w1; ++w, sh.advance(k)) {
         if (w + 1 < sh.w1)
           for (int i = 0; i < KB; ++i) p.advance(NS);       // S(w+1) precedes G(w) in the ring
-        const bool first = sh.seg_first(w);
+        const bool first = k.first;
         if (first) {
           if (seg_d >= 0) {                                 // the epilogue has flushed the previous accumulator
             ptx::mbar_wait(bar_hempty, seg_d & 1);
@@ -1047,7 +1078,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             p.advance(NS);
           }
         commit_elect(bar_dempty);                           // the dS columns may be overwritten
-        if (sh.seg_last(w)) commit_elect(bar_hfull);
+        if (k.last) commit_elect(bar_hfull);
         ++tc_d;
       }
     }
@@ -1064,32 +1095,36 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     float bias_v = 0.f, db_acc = 0.f;                        // ITEM_ST: b_out of this thread's item, its dL/db partial
     float s_acc = 0.f;                                       // FUSED: this thread's share of sum_v exp(z - ref)
     int tc = 0, seg = -1;
+    Walk k, nxt;
+    sh.start(k);
+    nxt = k;
     if (ITEM_ST && sh.w0 < sh.w1) {
       if (e < 128) {
-        rt = load_row_terms((int64_t)sh.inner(sh.w0) * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
+        rt = load_row_terms((int64_t)k.in * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
         sT_gen[e] = make_float4(rt.nb, rt.scale, rt.cf, __int_as_float(rt.tg));
       }
       epi_bar_sync();
     }
-    for (int w = sh.w0; w < sh.w1; ++w, ++tc) {
+    for (int w = sh.w0; w < sh.w1; ++w, ++tc, k = nxt) {
       const int buf = tc % SBUF;
-      if (sh.seg_first(w)) {
+      sh.advance(nxt);
+      if (k.first) {
         ++seg;
-        if (MODE == TS_DH) rt = load_row_terms((int64_t)sh.outer(w) * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
+        if (MODE == TS_DH) rt = load_row_terms((int64_t)k.o * BM + row, n_tokens, mrow, srow, coef, tgt, inv);
         if (FUSED) {                                         // exp(z - ref) un-normalised, no one-hot term
-          const int64_t n = (int64_t)sh.outer(w) * BM + row;
+          const int64_t n = (int64_t)k.o * BM + row;
           rt.nb = -INFINITY; rt.scale = 0.f; rt.cf = 0.f; rt.tg = -1;
           if (n < n_tokens && (tok_mask == nullptr || tok_mask[n])) { rt.nb = -mrow[n] * LOG2E; rt.scale = 1.f; }
           s_acc = 0.f;
         }
         if (ITEM_ST) {
-          const int v = v_begin + sh.outer(w) * BN + row;
+          const int v = v_begin + k.o * BN + row;
           bias_v = (b_out && v < v_end) ? b_out[v] : 0.f;
           db_acc = 0.f;
         }
       }
       if (ITEM_ST && e < 128 && w + 1 < sh.w1)               // next tile's token terms, behind this tile's math
-        rt = load_row_terms((int64_t)sh.inner(w + 1) * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
+        rt = load_row_terms((int64_t)nxt.in * BM + e, n_tokens, mrow, srow, coef, tgt, inv);
       ptx::mbar_wait(bar_tfull + 8 * buf, (tc / SBUF) & 1);
       ptx::tc_fence_after_sync();
       float z[64];
@@ -1098,7 +1133,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * buf);
       if (!ITEM_ST) {
-        const int vc0 = v_begin + sh.inner(w) * BN + half * 64;
+        const int vc0 = v_begin + k.in * BN + half * 64;
         if (b_out) {                                         // warp-uniform: output bias of the items in the columns
 #pragma unroll
           for (int j = 0; j < 64; ++j)
@@ -1112,7 +1147,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           s_acc += (a4[0] + a4[1]) + (a4[2] + a4[3]);
         }
       } else {
-        const int v = v_begin + sh.outer(w) * BN + row;      // this thread's item
+        const int v = v_begin + k.o * BN + row;              // this thread's item
         const bool row_ok = v < v_end;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -1147,17 +1182,17 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         if (e < 128) sT_gen[e] = make_float4(rt.nb, rt.scale, rt.cf, __int_as_float(rt.tg));
         epi_bar_sync();
       }
-      if (sh.seg_last(w)) {
+      if (k.last) {
         ptx::mbar_wait(bar_hfull, seg & 1);
         ptx::tc_fence_after_sync();
         const int h0 = half * (C::ACC_COLS / 2);             // this warp's hidden columns of its 32 rows
         if (!ITEM_ST) {
-          const int64_t n = (int64_t)sh.outer(w) * BM + row;
+          const int64_t n = (int64_t)k.o * BM + row;
           flush_acc_red(tmem_acc + lane_off + h0, C::ACC_COLS / 2, out + n * H + h0, H - h0, n < n_tokens,
                         (H & 3) == 0, (hscale && !FUSED) ? hscale + n * H + h0 : nullptr);
           if (FUSED && n < n_tokens && s_acc != 0.f) atomicAdd(s_out + n, s_acc);
         } else {
-          const int v = v_begin + sh.outer(w) * BN + row;
+          const int v = v_begin + k.o * BN + row;
           const bool row_ok = v < v_end;
           if (db_out && row_ok) atomicAdd(db_out + v, db_acc);
 #pragma unroll 1

@@ -11,53 +11,15 @@
 // Same semantics, inputs and outputs as the generic kernels in rnn_scan.cu (Keras-2.0.x GRU: reset applied BEFORE the
 // recurrent matmul -> two dependent matvec phases per step; Theano K.rnn mask switch).
 #include "common.cuh"
+#include "rnn_reg.cuh"
 
 namespace {
+using namespace regscan;
 
 constexpr int KS = 4;  // K-slices
 
 template <int CELL>
 struct Gates { static constexpr int G = (CELL == SEQREC_CELL_GRU) ? 3 : 1; };
-
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// acc[g][r] += sum_i vec[r*ldv + k0 + i] * u[g0 + g][i] for NG gates sharing the same vector; the float4 loads of the
-// next quad are issued before the FFMAs of the current one (software pipelined, fully unrolled)
-template <int RB, int KPT, int NG, int GT>
-__device__ __forceinline__ void dot_slices(float (&acc)[NG][RB], const float* __restrict__ vec, int ldv, int k0,
-                                           const float (&u)[GT][KPT], int g0) {
-  float4 hq[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) hq[r] = *reinterpret_cast<const float4*>(vec + r * ldv + k0);
-#pragma unroll
-  for (int i = 0; i < KPT; i += 4) {
-    float4 hn[RB];
-    if (i + 4 < KPT) {
-#pragma unroll
-      for (int r = 0; r < RB; ++r) hn[r] = *reinterpret_cast<const float4*>(vec + r * ldv + k0 + i + 4);
-    }
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        acc[g][r] = fmaf(hq[r].x, u[g0 + g][i], acc[g][r]);
-        acc[g][r] = fmaf(hq[r].y, u[g0 + g][i + 1], acc[g][r]);
-        acc[g][r] = fmaf(hq[r].z, u[g0 + g][i + 2], acc[g][r]);
-        acc[g][r] = fmaf(hq[r].w, u[g0 + g][i + 3], acc[g][r]);
-      }
-    if (i + 4 < KPT) {
-#pragma unroll
-      for (int r = 0; r < RB; ++r) hq[r] = hn[r];
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int CELL, int ACT, int RB, int KPT>
@@ -432,14 +394,22 @@ int dispatch_act(int act, int rb, bool fwd, float* xg, const float* U, const uin
 
 }  // namespace
 
-// Is the register-resident scan applicable?  (GRU / SimpleRNN, H <= 128)
+// LSTM variant (rnn_reg_lstm.cu)
+bool lstm_reg_applicable(int H);
+int lstm_reg_launch(int act, int rb, bool fwd, float* xg, const float* U, const uint8_t* mask, float* hout, float* cst,
+                    const float* dhout, int T, int B, int H, cudaStream_t st);
+
+// Is the register-resident scan applicable?  (GRU / SimpleRNN with H <= 128, LSTM with H <= 100)
 bool rnn_reg_applicable(int cell, int H) {
+  if (cell == SEQREC_CELL_LSTM) return lstm_reg_applicable(H);
   return (cell == SEQREC_CELL_GRU || cell == SEQREC_CELL_SIMPLE) && H <= 128;
 }
 
 // rb: batch rows per CTA (1, 2 or 4).  U is the untransposed recurrent kernel (H, G*H) for BOTH directions.
 int rnn_reg_launch(int cell, int act, int rb, bool fwd, float* xg, const float* U, const uint8_t* mask, float* hout,
                    float* cst, const float* dhout, int T, int B, int H, cudaStream_t st) {
+  if (cell == SEQREC_CELL_LSTM)
+    return lstm_reg_launch(act, rb > 2 ? 2 : rb, fwd, xg, U, mask, hout, cst, dhout, T, B, H, st);
   if (cell == SEQREC_CELL_GRU)
     return dispatch_act<SEQREC_CELL_GRU>(act, rb, fwd, xg, U, mask, hout, cst, dhout, T, B, H, st);
   return dispatch_act<SEQREC_CELL_SIMPLE>(act, rb, fwd, xg, U, mask, hout, cst, dhout, T, B, H, st);

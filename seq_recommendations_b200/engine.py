@@ -224,6 +224,7 @@ class HotPath:
         # ... on the valid tokens only (pads compacted away); SEQREC_CE_COMPACT=0 keeps the full token axis
         self.ce_compact = os.environ.get("SEQREC_CE_COMPACT", "1") != "0"
         self.ids_wait_early = os.environ.get("SEQREC_IDS_WAIT_EARLY", "1") != "0"
+        self.dp_serial = os.environ.get("SEQREC_DP_SERIAL", "0") == "1"   # diagnosis: every collective joined at once
         self.Hk = (self.H + 63) // 64 * 64
         self.Vp = (self.V + 7) // 8 * 8
         self._w_version = 0
@@ -856,6 +857,9 @@ class HotPath:
                       embedding_grad_mode(self.F, self.GH, w.N * comm.world) == "dense")
         # union of touched rows for the dense dW_in exchange: the ids of all ranks travel behind the forward pass
         all_ids, ids_handle = comm.all_gather_cat_async(w.ids.view(-1)) if dense_rows else (None, None)
+        if ids_handle is not None and self.dp_serial:
+            ids_handle.wait()
+            ids_handle = None
         if w.tc["fwd"]:
             self._mark("stage_operands")
             with self._branch():                  # bf16 operands of the updated W_out, behind gather + scan
@@ -883,6 +887,8 @@ class HotPath:
         (o_u, s_u), (o_b, s_b) = self._seg[0], self._seg[1]
         head = o_b + s_b
         pending = [comm.all_reduce_sum(self.flat_g[head:], async_op=True)] if comm.enabled else []
+        if self.dp_serial and pending:
+            pending.pop().wait()
         self._mark("rnn_bwd")
         self._rnn_backward(w)
         # ---- input-kernel gradient and recurrent weight-gradient GEMMs as parallel branches (both only read dxp)
@@ -912,6 +918,8 @@ class HotPath:
             # dense dW_in (small catalogs) and the step floats [n_valid, loss_sum] are adjacent in the gradient buffer:
             # ONE all-reduce, started as soon as the scatter-add is done -- it travels while the dU GEMMs still run
             pending.append(comm.all_reduce_sum(self._gbuf[:self._fgh + 64], async_op=True))
+            if self.dp_serial:
+                pending.pop().wait()
         self._mark("rnn_wgrad")
         if branch_wgrad:
             self._join()

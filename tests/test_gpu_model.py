@@ -231,7 +231,7 @@ def test_device_likelihood_metrics_match_golden_and_oracle(golden_dir):
 
 def test_state_checkpoint_resumes_with_adagrad_accumulators(tmp_path):
     """save_state / load_state (weights + Adagrad accumulators + epoch): a resumed model continues EXACTLY like the
-    uninterrupted one; a weights-only checkpoint (the reference's, model.py:201-218) restarts the accumulators and does
+    uninterrupted one (to summation order); a weights-only checkpoint (the reference's, model.py:201-218) restarts the accumulators and does
     not.  A path that claims to be HDF5 gets '.npz' appended; a real HDF5 file is refused with a clear message."""
     V, H, T, B = 400, 32, 8, 64
     ids, tgt = make_ids(V, T, 4 * B, seed=3)
@@ -254,9 +254,11 @@ def test_state_checkpoint_resumes_with_adagrad_accumulators(tmp_path):
     rest = steps(a, 2, 4)
     b = build()
     assert b.model.load_state(ck) == 7
-    assert steps(b, 2, 4) == rest                                   # bit-identical continuation
+    # same continuation (up to the summation order of the logits kernels' red.global accumulations, which is not fixed
+    # from run to run: a few ulps)
+    assert np.allclose(steps(b, 2, 4), rest, rtol=1e-6)
     for x, y in zip(a.model.get_weights(), b.model.get_weights()):
-        assert np.array_equal(x, y)
+        assert np.allclose(x, y, rtol=1e-5, atol=1e-7)
     c = build()
     c.model.load_weights(wk)
     assert steps(c, 2, 4)[1] != rest[1]                             # accumulators restarted: a different trajectory
