@@ -107,7 +107,7 @@ struct FwdCfg {
   static constexpr uint32_t U_PART = UA_BYTES + UB_BYTES;              // one part (hi or lo) of the U slice
   static constexpr uint32_t H_PART = CS * 4096;                        // one part of the h operand: CS K blocks
   static constexpr uint32_t STG = 4096;                                // one part of one staged slice
-  static constexpr uint32_t SMEM = 2 * U_PART + 2 * H_PART + 4 * STG + 64 + 1024;
+  static constexpr uint32_t SMEM = 2 * U_PART + 2 * H_PART + 4 * STG + 128 + 1024;
 };
 
 template <int CELL, int ACT, int CS>
@@ -124,8 +124,11 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
   const uint32_t sH = sU + 2 * C::U_PART;                    // [2 parts][CS K blocks][64 rows][64 B]
   const uint32_t sS = sH + 2 * C::H_PART;                    // [2 buffers][2 parts][4096]
   const uint32_t sBar = sS + 4 * C::STG;
-  const uint32_t bar_u = sBar, bar_hfull = sBar + 8, bar_acc = sBar + 16, bar_staged = sBar + 24,
-                 bar_free = sBar + 32, tmem_slot = sBar + 40;
+  // bar_hfull[p]: the K slice of source CTA p (hi + lo) has landed -- one barrier per source, so the MMA of a round
+  // starts with the first slice and runs behind the exchange instead of after it (the exchange is bound by the
+  // ~20 B/clk of distributed shared memory: 56 KB per CTA and round)
+  const uint32_t bar_u = sBar, bar_acc = sBar + 16, bar_staged = sBar + 24, bar_free = sBar + 32,
+                 tmem_slot = sBar + 40, bar_hfull = sBar + 48;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int b0 = (int)(blockIdx.x / CS) * BMR;
@@ -133,7 +136,7 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar_u, 1);
-    ptx::mbar_init(bar_hfull, 1);
+    for (int p = 0; p < CS; ++p) ptx::mbar_init(bar_hfull + 8 * p, 1);
     ptx::mbar_init(bar_acc, 1);
     ptx::mbar_init(bar_staged, 4);
     ptx::mbar_init(bar_free, CS);
@@ -172,46 +175,62 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
                                2 * H + (int)rank * UPC + hh * 16);
         }
       }
-      if (R > 1) ptx::mbar_arrive_expect_tx(bar_hfull, 2 * C::H_PART);
+      if (R > 1)
+        for (int p = 0; p < CS; ++p) ptx::mbar_arrive_expect_tx(bar_hfull + 8 * p, 2 * C::STG);
     }
     __syncwarp();
     ptx::mbar_wait(bar_u, 0);
     for (int r = 0; r < R; ++r) {
-      if (r > 0) {
-        ptx::mbar_wait_cluster(bar_hfull, (uint32_t)(r - 1) & 1u);      // all CS slices of the operand have landed
-        if (lane == 0) RT_DBG(r, 0);
-        if (r < R - 1 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar_hfull, 2 * C::H_PART);
-        __syncwarp();
-      }
-      ptx::tc_fence_after_sync();
       const bool sub_b = (RPS == 2) && (r & 1);
       const int nh = LSTM ? 64 : (sub_b ? 16 : 32);          // accumulator columns per half = MMA N
       const int nr = sub_b ? C::NB : C::NA;                  // operand rows per K block in this region
       const uint32_t ureg = sU + (sub_b ? C::UA_BYTES : 0u);
       const uint32_t idesc = ptx::umma_idesc_bf16(BMR, nh);
-      if (ptx::elect_one()) {
-        // descriptor bases once per round; every MMA then needs one 32-bit add per operand (the address field never
-        // carries out of its 14 bits), so the single issuing thread keeps up with the tensor pipe
-        const uint64_t a_hi0 = ptx::umma_desc_k_sw64(sH), a_lo0 = ptx::umma_desc_k_sw64(sH + C::H_PART);
-        const uint64_t b_hi0 = ptx::umma_desc_k_sw128(ureg), b_lo0 = ptx::umma_desc_k_sw128(ureg + C::U_PART);
+      // descriptor bases once per round; every MMA then needs one 32-bit add per operand (the address field never
+      // carries out of its 14 bits), so the single issuing thread keeps up with the tensor pipe
+      const uint64_t a_hi0 = ptx::umma_desc_k_sw64(sH), a_lo0 = ptx::umma_desc_k_sw64(sH + C::H_PART);
+      const uint64_t b_hi0 = ptx::umma_desc_k_sw128(ureg), b_lo0 = ptx::umma_desc_k_sw128(ureg + C::U_PART);
+      const uint32_t kstride = (uint32_t)nr * 8u;                      // one K block of the U region, >> 4
+      // K slices in the order they arrive: the own one first, then the sources rank-1, rank-2, ... (every sender
+      // serves its destinations in the order rank, rank+1, ...)
+      // (LSTM: measured SLOWER when the MMAs run behind the exchange -- 1.19 -> 1.35 ms at cfg3: its M64 x N64 MMAs read
+      //  4 KB of operands per ~40 clocks, i.e. they already hold the shared-memory port that the incoming and outgoing
+      //  bulk copies need, and the two streams slow each other down.  The LSTM therefore waits for all slices first;
+      //  the GRU's smaller rounds gain 11 %.)
+      constexpr bool PIPE = !LSTM;
+      for (int pass = PIPE ? 1 : 0; pass < 2; ++pass)
+      for (int i = 0; i < CS; ++i) {
+        const uint32_t p = (rank + (uint32_t)(CS - i)) % (uint32_t)CS;
+        if (r > 0 && pass == (PIPE ? 1 : 0)) {
+          ptx::mbar_wait_cluster(bar_hfull + 8 * p, (uint32_t)(r - 1) & 1u);   // slice p of the operand has landed
+          if (i == (PIPE ? 0 : CS - 1) && lane == 0) RT_DBG(r, 0);
+          if (r < R - 1 && ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar_hfull + 8 * p, 2 * C::STG);
+          __syncwarp();
+        }
+        if (pass == 0) continue;
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t d = tmem_base + ((uint32_t)(hh * 16) << 16);  // second M=64 atom on lanes 16..31 of each quadrant
-          const uint32_t bh = (uint32_t)(hh * nh) * 8u;                // (hh * nh rows * 128 B) >> 4
-          const uint32_t kstride = (uint32_t)nr * 8u;                  // one K block of the U region, >> 4
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t d = tmem_base + ((uint32_t)(hh * 16) << 16);  // second M=64 atom on lanes 16..31 of each quadrant
+            const uint32_t bh = (uint32_t)(hh * nh) * 8u;                // (hh * nh rows * 128 B) >> 4
 #pragma unroll
-          for (int s = 0; s < H / 16; ++s) {
-            const uint32_t a_off = (uint32_t)(s >> 1) * 256u + (uint32_t)(s & 1) * 2u;     // byte offsets >> 4
-            const uint32_t b_off = (uint32_t)(s >> 2) * kstride + bh + (uint32_t)(s & 3) * 2u;
-            ptx::umma_bf16(d, a_hi0 + a_off, b_lo0 + b_off, idesc, s > 0 ? 1u : 0u);
-            ptx::umma_bf16(d, a_lo0 + a_off, b_hi0 + b_off, idesc, 1u);
-            ptx::umma_bf16(d, a_hi0 + a_off, b_hi0 + b_off, idesc, 1u);
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t s = 2u * p + (uint32_t)ks;                  // K = 16 step of the whole operand
+              const uint32_t a_off = (s >> 1) * 256u + (s & 1u) * 2u;    // byte offsets >> 4
+              const uint32_t b_off = (s >> 2) * kstride + bh + (s & 3u) * 2u;
+              ptx::umma_bf16(d, a_hi0 + a_off, b_lo0 + b_off, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              ptx::umma_bf16(d, a_lo0 + a_off, b_hi0 + b_off, idesc, 1u);
+              ptx::umma_bf16(d, a_hi0 + a_off, b_hi0 + b_off, idesc, 1u);
+            }
+          }
+          if (i == CS - 1) {
+            ptx::umma_commit(bar_acc);
+            RT_DBG(r, 1);
           }
         }
-        ptx::umma_commit(bar_acc);
-        RT_DBG(r, 1);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------------------------- exchange (all-gather)
@@ -222,9 +241,10 @@ rnn_tc_forward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_c
       if (lane == 0) RT_DBG(r, 5);
       if (ptx::elect_one()) {
         const uint32_t src = sS + (uint32_t)(r & 1) * 2u * C::STG;
-        for (uint32_t p = 0; p < (uint32_t)CS; ++p) {
+        for (uint32_t i = 0; i < (uint32_t)CS; ++i) {            // own copy first, then rank+1, rank+2, ...
+          const uint32_t p = (rank + i) % (uint32_t)CS;
           const uint32_t dst = ptx::mapa(sH + rank * 4096u, p);
-          const uint32_t bar = ptx::mapa(bar_hfull, p);
+          const uint32_t bar = ptx::mapa(bar_hfull + 8 * rank, p);
           ptx::bulk_copy_to_cluster(dst, src, C::STG, bar);
           ptx::bulk_copy_to_cluster(dst + C::H_PART, src + C::STG, C::STG, bar);
         }
@@ -429,7 +449,7 @@ rnn_tc_backward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sU = base;                                  // [2 parts][G blocks][H rows][64 B]
   const uint32_t sA = sU + 2 * C::U_PART;                    // [2 parts][G blocks][64 rows][64 B]
-  const uint32_t sR = sA + 2 * C::A_PART;                    // [CS][64 rows][128 B], 16-byte chunks XOR (row & 7)
+  const uint32_t sR = sA + 2 * C::A_PART;                    // [CS sources][8 chunks of 16 B][64 rows]
   const uint32_t sBar = sR + C::RECV;
   const uint32_t bar_u = sBar, bar_aready = sBar + 8, bar_acc = sBar + 16, bar_rfull = sBar + 24,
                  bar_rfree = sBar + 32, tmem_slot = sBar + 40;
@@ -506,7 +526,6 @@ rnn_tc_backward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_
     const bool valid = b < B;
     const int u0 = (int)rank * UPC + hh * 16;
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
-    const uint32_t rsw = (uint32_t)(row & 7);
     float rec[16], dcar[16], dd[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { rec[j] = 0.f; dcar[j] = 0.f; dd[j] = 0.f; }
@@ -535,10 +554,12 @@ rnn_tc_backward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_
         ptx::tmem_ld_32x32(taddr + 32 * i, v);
         ptx::tmem_ld_wait();
         const uint32_t p = (uint32_t)(hh * (CS / 2) + i);    // owner of units [hh*H/2 + 32i, +32)
-        const uint32_t dst = ptx::mapa(sR + rank * 8192u + (uint32_t)row * 128u, p);
+        // chunk-major layout: the 16 lanes that address one peer write 256 contiguous bytes per instruction (with a
+        // row-major buffer every lane hit its own 128-byte row: 16-byte pieces, half of every 32-byte sector wasted)
+        const uint32_t dst = ptx::mapa(sR + rank * 8192u + (uint32_t)row * 16u, p);
 #pragma unroll
         for (uint32_t k = 0; k < 8; ++k)
-          ptx::st_cluster_f4(dst + ((k ^ rsw) << 4),
+          ptx::st_cluster_f4(dst + (k << 10),
                              make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]),
                                          __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])));
       }
@@ -556,13 +577,13 @@ rnn_tc_backward_kernel(const __grid_constant__ CUtensorMap tmU_hi, const __grid_
       for (int j = 0; j < 16; ++j) sum[j] = 0.f;
 #pragma unroll 2
       for (uint32_t src = 0; src < (uint32_t)CS; ++src) {
-        const uint32_t a = sR + src * 8192u + (uint32_t)row * 128u;
+        const uint32_t a = sR + src * 8192u + (uint32_t)row * 16u;
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) {
           float4 t;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                        : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                       : "r"(a + ((((uint32_t)hh * 4u + k) ^ rsw) << 4)));
+                       : "r"(a + (((uint32_t)hh * 4u + k) << 10)));
           sum[4 * k] += t.x; sum[4 * k + 1] += t.y; sum[4 * k + 2] += t.z; sum[4 * k + 3] += t.w;
         }
       }
