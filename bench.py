@@ -442,7 +442,9 @@ def measure_training(args, name, cfg, comm, rank, local, steps, warmup, full=Tru
     if world == 1 and full:
         from seq_recommendations_b200.model import RNNFullModel
         from seq_recommendations_b200.optimizers import Adagrad
-        nb = 32 if step_ms < 50 else 8
+        # batches per timed epoch: enough that fit_model's per-call work (id conversion, range check, the one H2D copy of
+        # the training set) is amortised as in a real epoch
+        nb = 256 if step_ms < 2 else (32 if step_ms < 50 else 8)
         big_i, big_t = synthetic.make_batch(V, T, B * nb, seed=7)
         mdl = RNNFullModel(T, V, V, z_dim=H, rnn_type=cfg["cell"], z_to_z_activation=cfg["act"], y_to_y=False,
                            x_to_y=False, seed=0)
