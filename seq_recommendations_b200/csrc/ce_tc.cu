@@ -903,6 +903,17 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   const int n_inner_tiles = ITEM_ST ? n_ttiles : n_vtiles;
   const bool stream_fits_l2 = (int64_t)n_inner_tiles * (2 * NP * KB * TILE_B) <= (32ll << 20);
   const WaveShare sh(ITEM_ST ? n_vtiles : n_ttiles, n_inner_tiles, stream_fits_l2);
+  // Blocks of the second GEMM's streamed operand per tile.  Item-stationary: [128 hidden x 64 tokens] blocks of H^T.
+  // Token-stationary, two forms:
+  //  * K-major [128 hidden x 64 items] blocks of W_out (Hk x V), N = 128 per MMA -- the faster form while W_out stays
+  //    in the L2 (cfg2, cfg3), but its 128 rows lie V*2 bytes apart: at V = 1M that is one 2 MB page and one DRAM row
+  //    per 128-byte piece, and the kernel ran 22 % slower per unit of work than at V = 50k;
+  //  * z_mn: the SAME [128 items x 64 hidden] blocks of W_out^T that fed the logits GEMM, fetched a second time (an L2
+  //    hit on lines loaded microseconds earlier) and read as an MN-MAJOR operand (N = 64 hidden units along the
+  //    128-byte rows, K = the 128 items down the rows).  Twice the MMAs at half the width: 11 % slower at cfg3, 8 %
+  //    faster at cfg4 -- taken when the streamed operand is far beyond the L2 (> 160 MB).
+  const bool z_mn = !ITEM_ST && (int64_t)n_inner_tiles * (2 * NP * KB * TILE_B) > (160ll << 20);
+  const int NZ = z_mn ? KB : NJ * NC;
   // first row of the stationary / streamed operand of work item w
   auto p_row0 = [&](const Walk& k) { return ITEM_ST ? v_begin + k.o * BN : k.o * BM; };
   auto q_row0 = [&](const Walk& k) { return ITEM_ST ? k.in * BM : v_begin + k.in * BN; };
@@ -968,6 +979,20 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       };
       auto load_z = [&](const Walk& k) {
         const int q0 = q_row0(k);
+        if (z_mn) {
+          for (int n = 0; n < KB; ++n) {
+            ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
+            if (ptx::elect_one()) {
+              const uint32_t fb = bar_fullz + 8 * p.stage;
+              ptx::mbar_arrive_expect_tx(fb, NP * TILE_B);
+              const uint32_t dst = sB + p.stage * NP * TILE_B;
+              ptx::tma_load_2d(dst, &tmY_hi, fb, n * KBLK, q0);
+              if (X3) ptx::tma_load_2d(dst + TILE_B, &tmY_lo, fb, n * KBLK, q0);
+            }
+            p.advance(NS);
+          }
+          return;
+        }
         for (int j = 0; j < NJ; ++j)
           for (int c = 0; c < NC; ++c) {
             ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
@@ -997,7 +1022,6 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     // ring positions: S(0) | S(1) G(0) | S(2) G(1) | ... | S(n-1) G(n-2) | G(n-1)   (KB stages per S, NZ per G)
     if (sh.w0 < sh.w1) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
-      constexpr int NZ = NJ * NC;
       Pipe p;
       uint32_t ybits = 0;                                   // parity of the Y-block barrier, per slot
       int seg_s = -1, tc_s = 0;
@@ -1051,6 +1075,36 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         }
         ptx::mbar_wait(bar_dfull, tc_d & 1);                // dS(w) is in tensor memory
         ptx::tc_fence_after_sync();
+        if (z_mn) {
+          // acc[:, 64n .. 64n+64) += dS[128 tokens x 128 items] . W_out^T block n (MN-major: K = items down the rows)
+          constexpr uint32_t idesc_mn = ptx::umma_idesc_bf16_bmn(128, 64);
+          for (int n = 0; n < KB; ++n) {
+            ptx::mbar_wait(bar_fullz + 8 * p.stage, (zbits >> p.stage) & 1u);
+            zbits ^= 1u << p.stage;
+            ptx::tc_fence_after_sync();
+            const uint32_t bb = sB + p.stage * NP * TILE_B;
+            const uint64_t db_hi = ptx::umma_desc_mn_sw128(bb, TILE_B), db_lo = ptx::umma_desc_mn_sw128(bb + TILE_B, TILE_B);
+            const uint32_t d = tmem_acc + n * 64;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < BN / 16; ++ks) {
+                const uint32_t a_hi = tmem_ds + ks * 8, a_lo = a_hi + BN / 2;
+                const uint64_t o = (uint64_t)((ks * 16 * 128) >> 4);   // 16 items = 16 rows of 128 B further down
+                const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                if (X3) {
+                  ptx::umma_bf16_ts(d, a_hi, db_lo + o, idesc_mn, acc);
+                  ptx::umma_bf16_ts(d, a_lo, db_hi + o, idesc_mn, 1u);
+                  ptx::umma_bf16_ts(d, a_hi, db_hi + o, idesc_mn, 1u);
+                } else {
+                  ptx::umma_bf16_ts(d, a_hi, db_hi + o, idesc_mn, acc);
+                }
+              }
+            }
+            __syncwarp();
+            commit_elect(bar_empty + 8 * p.stage);
+            p.advance(NS);
+          }
+        } else
         for (int j = 0; j < NJ; ++j)
           for (int c = 0; c < NC; ++c) {
             ptx::mbar_wait(bar_fullz + 8 * p.stage, (zbits >> p.stage) & 1u);
