@@ -17,6 +17,8 @@
 //     feeds it straight back to the tensor core (dH += dS.W^T  /  dW += H^T.dS).
 //
 // Tiles: 128 tokens x 128 items; K (= hidden, padded to 64) is walked in 64-element blocks (one 128-byte swizzle row).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "tma_host.cuh"
@@ -862,6 +864,19 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 //   the clip passes no gradient (coef = 0) and the finish kernel writes zeros -- the reference's result.
 enum { TS_DH = 0, TS_DW = 1, TS_FUSED = 2 };
 
+// Front throttle of the full waves.  WaveShare starts all CTAs on the same streamed tile, but nothing keeps them
+// together: over the 7813 item tiles of cfg4 the faster SMs run hundreds of tiles ahead -- further than the L2 reaches
+// back (ncu: 36 GB of DRAM reads per launch for 1 GB of W_out^T, L2 hit rate 88 %, tensor pipe 75 % active against 86 %
+// at cfg3, whose W_out stays L2-resident).  The producer warp therefore counts the CTAs that have STARTED each chunk
+// of TS_CHUNK streamed tiles and does not start chunk c before every CTA has started chunk c - TS_AHEAD: the front of
+// the grid stays within TS_AHEAD+1 chunks (24 MB at Hk = 256).  It is a throttle, not a barrier: correctness never
+// depends on it and every wait is bounded (a CTA that has waited ~100 us goes on alone), so a co-scheduled kernel
+// holding an SM cannot hang the grid.  One counter array per variant (cleared by a memset node in front of the launch).
+constexpr int TS_CHUNK = 32, TS_AHEAD = 2, TS_SYNC_SLOTS = 8192;
+__device__ int g_ts_sync[3][TS_SYNC_SLOTS];
+// experiment switch (SEQREC_ZMN = 1: never / 2: always the MN-major form of the second GEMM's operand; 0 = by size)
+__device__ int g_ts_zmn_mode = 0;
+
 template <int KB, bool X3, int MODE>
 __global__ void __launch_bounds__(352, 1)
 ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
@@ -912,7 +927,11 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
   //    hit on lines loaded microseconds earlier) and read as an MN-MAJOR operand (N = 64 hidden units along the
   //    128-byte rows, K = the 128 items down the rows).  Twice the MMAs at half the width: 11 % slower at cfg3, 8 %
   //    faster at cfg4 -- taken when the streamed operand is far beyond the L2 (> 160 MB).
-  const bool z_mn = !ITEM_ST && (int64_t)n_inner_tiles * (2 * NP * KB * TILE_B) > (160ll << 20);
+  const int chunks_per_round = (n_inner_tiles + TS_CHUNK - 1) / TS_CHUNK;
+  const bool throttle = !stream_fits_l2 && sh.full_items > 0 &&
+                        (int64_t)(sh.full_items / n_inner_tiles) * chunks_per_round <= TS_SYNC_SLOTS;
+  const bool z_mn = !ITEM_ST && (g_ts_zmn_mode == 2 ||
+                                 (g_ts_zmn_mode == 0 && (int64_t)n_inner_tiles * (2 * NP * KB * TILE_B) > (160ll << 20)));
   const int NZ = z_mn ? KB : NJ * NC;
   // first row of the stationary / streamed operand of work item w
   auto p_row0 = [&](const Walk& k) { return ITEM_ST ? v_begin + k.o * BN : k.o * BM; };
@@ -952,6 +971,7 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
       if (lane == 0) { ptx::prefetch_tmap(&tmX_hi); ptx::prefetch_tmap(&tmY_hi); ptx::prefetch_tmap(&tmZ_hi); }
       Pipe p;
       int seg = 0;
+      bool gave_up = false;                                 // front throttle: this CTA has timed out once
       auto load_s_operands = [&](const Walk& k) {
         if (k.first) {
           if (seg > 0) ptx::mbar_wait(bar_afree, (seg - 1) & 1);
@@ -966,6 +986,22 @@ ce_tc_backward_ts_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
           ++seg;
         }
         const int q0 = q_row0(k);
+        if (throttle && k.w < sh.full_items && (k.in % TS_CHUNK) == 0) {
+          const int chunk = (k.w / sh.n_inner) * chunks_per_round + k.in / TS_CHUNK;
+          if (lane == 0) {
+            int* cnt = g_ts_sync[MODE];
+            atomicAdd(cnt + chunk, 1);
+            if (chunk >= TS_AHEAD && !gave_up) {
+              const volatile int* behind = cnt + (chunk - TS_AHEAD);
+              const long long t0 = clock64();
+              while (*behind < (int)gridDim.x) {
+                if (clock64() - t0 > 200000ll) { gave_up = true; break; }   // ~100 us: go on alone from here
+                __nanosleep(256);
+              }
+            }
+          }
+          __syncwarp();
+        }
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * p.stage, p.phase ^ 1);
           if (ptx::elect_one()) {
@@ -1339,6 +1375,25 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
   auto k = ce_tc_backward_ts_kernel<KB, X3, MODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(int)e;
+  {
+    // chunk counters of the front throttle (this variant's row); the symbol address is looked up once per device, on an
+    // eager call (the first step of a shape always is), so a captured step only records the memset node
+    static void* sync_ws[64] = {};
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64) return e != cudaSuccess ? -(int)e : -1090;
+    if (!sync_ws[dev]) {
+      e = cudaGetSymbolAddress(&sync_ws[dev], g_ts_sync);
+      if (e != cudaSuccess) return -(int)e;
+      const char* zm = getenv("SEQREC_ZMN");
+      const int mode = zm ? atoi(zm) : 0;
+      e = cudaMemcpyToSymbol(g_ts_zmn_mode, &mode, sizeof(int));
+      if (e != cudaSuccess) return -(int)e;
+    }
+    e = cudaMemsetAsync(static_cast<int*>(sync_ws[dev]) + (size_t)MODE * TS_SYNC_SLOTS, 0, sizeof(int) * TS_SYNC_SLOTS,
+                        st);
+    if (e != cudaSuccess) return -(int)e;
+  }
   k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
                                     n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out, tok_mask, s_out,
                                     n_tokens_dev);
