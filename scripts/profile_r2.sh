@@ -22,7 +22,7 @@ full() {  # name, kernel regex, count, config, ncu selection
 }
 # cfg4's kernels run 80-90 ms: the SASS-patching passes of --set full exceed the kernels' own 2 s mbarrier watchdog on the
 # second launch, so the dW kernel gets the hardware-counter sections only
-full prof3_ce_cfg4 "ce_tc_backward_ts_kernel<4, true, 2>|ce_tc_backward_ts_kernel.*2>" 1 cfg4_gru256_1m "--set full"
+full prof3_ce_cfg4 "ce_tc_backward_ts" 1 cfg4_gru256_1m "--set full"
 LIGHT="--section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section LaunchStats --section Occupancy"
 full prof3_dw_cfg4 "ce_tc_backward_ts" 2 cfg4_gru256_1m "$LIGHT"
 full prof3_ce_cfg3 ce_tc_backward_ts 2 cfg3_lstm256_50k "--set full"

@@ -1390,9 +1390,14 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
       e = cudaMemcpyToSymbol(g_ts_zmn_mode, &mode, sizeof(int));
       if (e != cudaSuccess) return -(int)e;
     }
-    e = cudaMemsetAsync(static_cast<int*>(sync_ws[dev]) + (size_t)MODE * TS_SYNC_SLOTS, 0, sizeof(int) * TS_SYNC_SLOTS,
-                        st);
-    if (e != cudaSuccess) return -(int)e;
+    // (the kernel throttles only when its streamed operand exceeds 32 MB; n_tokens is the upper bound of the device-side
+    //  token count, so "fits" here implies "fits" there and the memset node can be dropped)
+    const int64_t inner_ub = (MODE == TS_DW) ? (n_tokens + BM - 1) / BM : (v_end - v_begin + BN - 1) / BN;
+    if (inner_ub * (int64_t)(2 * C::NP * KB * TILE_B) > (32ll << 20)) {
+      e = cudaMemsetAsync(static_cast<int*>(sync_ws[dev]) + (size_t)MODE * TS_SYNC_SLOTS, 0,
+                          sizeof(int) * TS_SYNC_SLOTS, st);
+      if (e != cudaSuccess) return -(int)e;
+    }
   }
   k<<<grid, C::THREADS, smem, st>>>(x_hi, x_lo, y_hi, y_lo, z_hi, z_lo, tgt, m, s, coef, inv_nvalid, hscale, out,
                                     n_tokens, H, v_begin, v_end, ldw, (uint32_t)smem, b_out, db_out, tok_mask, s_out,
