@@ -40,6 +40,15 @@ int seqrec_launch_count(int reset);
 int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets, int32_t* ids_bt, int32_t* tgt_bt, int64_t n_seqs,
                          int T, void* stream);
 
+/* ---- history features on the device (datasets.py:97-113 build_xs, consumed as c = xs[:-1] by
+ * FullModelPreprocessor.transform_data, preprocessor.py:71,89,92): c (n_seqs, T, V) float32, c[b,t,v] = number of times
+ * (freq != 0) or whether (freq == 0) item v occurred among s[0..j] of sequence b, where input position j lands on column t
+ * of the left-padded / left-truncated row (truncated positions still count); pad columns are 0.  table (may be NULL):
+ * value transform indexed by the count, table_len entries (the drivers' np.log(x + 1), experiments_server.py:35-36).
+ * An item outside [0, V) sets bit 0 of err[0] (int32, may be NULL; the reference raises IndexError). */
+int seqrec_history_features(const int32_t* items, const int64_t* offsets, float* c, int64_t n_seqs, int T, int V,
+                            int freq, const float* table, int table_len, int32_t* err, void* stream);
+
 /* ---- batch format (preprocessor.py:67-94, model.py:335 Masking) ------------------------------------------------
  * (B,T) batch-major ids/targets (pad = negative) -> time-major ids/targets/mask; counts valid tokens into
  * n_valid[0] (int32, must be zeroed by the caller).  Range check: an input id >= n_in, or a target outside [0, n_items)

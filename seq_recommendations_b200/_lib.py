@@ -23,6 +23,7 @@ SIGNATURES = {
     "seqrec_abi_version": [],
     "seqrec_launch_count": [_i],
     "seqrec_pad_sequences": [_p, _p, _p, _p, _l, _i, _p],
+    "seqrec_history_features": [_p, _p, _p, _l, _i, _i, _i, _p, _i, _p, _p],
     "seqrec_format_batch": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p],
     "seqrec_gather_rows": [_p, _p, _p, _p, _p, _p, _l, _i, _i, _p],
     "seqrec_scatter_add_rows": [_p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _p],

@@ -95,6 +95,64 @@ extern "C" int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// History features (datasets.py:97-113 build_xs, then FullModelPreprocessor's c = xs[:-1] left-padded / left-truncated,
+// preprocessor.py:71,89,92): c[b,t,v] = how often (freq) / whether item v occurred among s[0..j] of sequence b, j being
+// the input position that lands on column t; pad columns are 0.  Rows that the left truncation drops still count -- the
+// reference builds xs on the whole sequence and truncates afterwards.  One thread per (sequence, item): it walks the
+// sequence once with the running count in a register; consecutive threads own consecutive items, so each store of a
+// warp is one contiguous run of the (T, V) row block.  HBM-bound: n_seqs * T * V * 4 bytes written.
+// table: optional value transform indexed by the count (the drivers' np.log(x + 1), experiments_server.py:35-36,
+// computed on the host in float64 and rounded once, like the reference's own down-cast at the Theano boundary).
+__global__ void __launch_bounds__(256)
+history_features_kernel(const int32_t* __restrict__ items, const int64_t* __restrict__ offs, float* __restrict__ out,
+                        int64_t n_seqs, int T, int V, int freq, const float* __restrict__ table, int table_len,
+                        int32_t* __restrict__ err) {
+  const int64_t total = n_seqs * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / V;
+    const int v = (int)(i - b * V);
+    const int64_t start = offs[b], len = offs[b + 1] - start;
+    const int64_t rows = len > 0 ? len - 1 : 0;                // xs[:-1]: one row per input position
+    const int64_t keep = rows < T ? rows : T;
+    const int64_t skip = rows - keep;
+    float* o = out + (b * T) * (int64_t)V + v;
+    int cnt = 0;
+    bool bad = false;
+    for (int64_t j = 0; j < skip; ++j) {
+      const int32_t it = items[start + j];
+      bad |= (it < 0) | (it >= V);
+      cnt += (it == v);
+    }
+    const int pad = T - (int)keep;
+    for (int t = 0; t < pad; ++t) o[(int64_t)t * V] = 0.f;
+    for (int64_t j = 0; j < keep; ++j) {
+      const int32_t it = items[start + skip + j];
+      bad |= (it < 0) | (it >= V);
+      cnt += (it == v);
+      int c = freq ? cnt : (cnt > 0 ? 1 : 0);
+      float val = (float)c;
+      if (table) val = table[c < table_len ? c : table_len - 1];
+      o[(pad + j) * (int64_t)V] = val;
+    }
+    // (the reference's xi[s] raises IndexError for s >= V and silently wraps a negative s: both are errors here)
+    if (v == 0 && bad && err) atomicOr(err, 1);
+  }
+}
+
+extern "C" int seqrec_history_features(const int32_t* items, const int64_t* offsets, float* c, int64_t n_seqs, int T,
+                                       int V, int freq, const float* table, int table_len, int32_t* err,
+                                       void* stream) {
+  SEQREC_ARG(items && offsets && c && n_seqs > 0 && T > 0 && V > 0, 1);
+  SEQREC_ARG(!table || table_len > 1, 2);
+  int64_t blocks = (n_seqs * V + 255) / 256;
+  if (blocks > SEQREC_NUM_SMS * 8) blocks = SEQREC_NUM_SMS * 8;
+  history_features_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(items, offsets, c, n_seqs, T, V, freq, table,
+                                                                      table_len, err);
+  SEQREC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // K1: xp[n,:] = (mask ? scale*W_in[id,:] : 0) + b.   One thread per float4 of the output, consecutive threads on
 // consecutive 16-byte chunks of one row (coalesced reads of the table row and coalesced streaming stores).
 template <bool VEC4>

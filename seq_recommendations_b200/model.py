@@ -5,9 +5,9 @@ Same class names, constructor kwargs, method signatures and return conventions a
 (experiments_methods.py:19-50, :188-249) run against this module unchanged.  `self.model` plays the role of the Keras
 `Model` the reference reaches into (`fit`, `evaluate`, `predict`, `get_weights`, `get_layer`, `load_weights`, ...).
 
-Scope: the `y_to_z`-only RNNFullModel ("ytoz", experiments_server.py:106-114) and RNNBaseline, cells
-simpleRNN / LSTM (the reference's) and GRU (north-star).  The x_to_z / x_to_y / y_to_y branches of RNNFullModel and
-NoRecurrenceModel are §8(f) "next" rows and raise NotImplementedError.
+Scope: RNNFullModel -- the `y_to_z`-only form ("ytoz", experiments_server.py:106-114) on the fused hot path
+(engine.HotPath), the x_to_z / x_to_y / y_to_y history-feature and skip branches on engine_dense.DensePath --
+RNNBaseline and NoRecurrenceModel; cells simpleRNN / LSTM (the reference's) and GRU (north-star).
 
 Additive (not in the reference): id-format batches ((N,T) / (N,T,1) integer arrays, pad < 0), `predict_target_prob`,
 `predict_topk`.
@@ -234,6 +234,9 @@ class _Net(object):
             arrs = [x]
         ids = xd = None
         for kind, a in zip(spec, arrs):
+            if kind == "x" and isinstance(a, torch.Tensor):
+                xd = a.to(dtype=torch.float32)             # history features built on the device (datasets.py) stay there
+                continue
             a = np.asarray(a)
             if kind == "x":
                 xd = np.ascontiguousarray(a, dtype=np.float32)
@@ -247,6 +250,8 @@ class _Net(object):
         return ids, xd
 
     def _slice(self, ids, xd, idx):
+        if isinstance(xd, torch.Tensor) and not isinstance(idx, slice):
+            return (ids[idx] if ids is not None else None), xd.index_select(0, torch.as_tensor(idx, device=xd.device))
         return (ids[idx] if ids is not None else None), (xd[idx] if xd is not None else None)
 
     def _epoch_eval(self, ids, xd, tgt, batch_size):

@@ -100,10 +100,36 @@ def ragged(seqs):
     return flat, offs
 
 
+def history_fixture(ref_pre, build_xs):
+    """History features through the reference's own build_xs + FullModelPreprocessor, with the drivers' log(x + 1)
+    (experiments_server.py:33-36); ragged lengths, a length-1 and a length-2 sequence, truncation that drops counted
+    rows.  Written to its own file so that the other fixtures stay byte-identical."""
+    rng = np.random.RandomState(5)
+    V = 7
+    vocab = dict(zip(range(V), range(V)))
+    seqs = [[int(v) for v in rng.randint(0, V, size=n)] for n in (12, 1, 2, 9, 5, 3, 17, 8)]
+    flat, offs = ragged(seqs)
+    out = {"flat": flat, "offs": offs, "V": np.int64(V)}
+    for freq in (False, True):
+        xs = build_xs(seqs, vocab, freq=freq)
+        xs_log = [[[np.log(x + 1) for x in row] for row in rows] for rows in xs]
+        for tag, L in (("full", None), ("trunc", 6)):
+            for name, feats in (("raw", xs), ("log", xs_log)):
+                p = ref_pre.FullModelPreprocessor(vocab=vocab, pad_value=0.0, seq_length=L)
+                _, _, c = p.transform_data(seqs, xs=feats)
+                out["c_%s_%s_%s" % ("freq" if freq else "bin", name, tag)] = c
+                out["T_" + tag] = np.int64(p.seq_length)
+    np.savez_compressed(os.path.join(OUT, "history_features.npz"), **out)
+
+
 def main():
     install_stubs()
     sys.path.insert(0, REF)
     import preprocessor as ref_pre
+    if sys.argv[1:] == ["history"]:
+        history_fixture(ref_pre, load_build_xs())
+        print("wrote history_features.npz")
+        return
     import sampler as ref_sampler
     import utils as ref_utils
 
@@ -175,6 +201,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "likelihood.npz"), preds=np.concatenate(preds), offs=offp, padded=padded,
                         lengths=lengths, ll=ll, ll_first=ll_first, cut_tr=cut_tr, cut_va=cut_va, cut_tr_l=cut_tr_l,
                         cut_va_l=cut_va_l, T_alpha=T_alpha, T_gamma=T_gamma, multi=multi)
+    history_fixture(ref_pre, build_xs)
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -122,3 +122,44 @@ def test_synthetic_batches():
     ws = synthetic.make_weights("LSTM", 50, 8)
     assert [w.shape for w in ws] == [(50, 32), (8, 32), (32,), (8, 50)] and ws[2][8:16].min() == 1.0
     assert np.allclose(ws[1][:, :8].T @ ws[1][:, :8], np.eye(8), atol=1e-5)
+
+
+# ---- history features (datasets.py:97-113 build_xs -> c of FullModelPreprocessor) ------------------------------------
+def _history_cases(g):
+    for freq in (False, True):
+        for tag, L in (("full", None), ("trunc", int(g["T_trunc"]))):
+            for name in ("raw", "log"):
+                yield freq, L, name == "log", g["c_%s_%s_%s" % ("freq" if freq else "bin", name, tag)]
+
+
+def test_history_oracle_matches_reference_fixture(golden_dir):
+    """oracle/history.py against the reference's own build_xs + FullModelPreprocessor (+ the drivers' log(x + 1))."""
+    from oracle import history
+    g = load(golden_dir, "history_features.npz")
+    seqs = unragged(g["flat"], g["offs"])
+    V = int(g["V"])
+    for freq, L, log1p, ref in _history_cases(g):
+        mine = history.history_block(seqs, V, seq_length=L, freq=freq, log1p=log1p)
+        assert mine.shape == ref.shape and np.array_equal(mine, ref)
+    assert int(g["T_full"]) == max(len(s) for s in seqs) - 1
+
+
+def test_host_build_xs_matches_reference_fixture(golden_dir):
+    """The package's build_xs (vectorised) through the drivers' recipe and the package's preprocessor."""
+    from seq_recommendations_b200 import datasets
+    g = load(golden_dir, "history_features.npz")
+    seqs = unragged(g["flat"], g["offs"])
+    V = int(g["V"])
+    vocab = dict(zip(range(V), range(V)))
+    for freq, L, log1p, ref in _history_cases(g):
+        xs = datasets.build_xs(seqs, vocab, freq=freq)
+        assert [np.asarray(x).tolist() for x in xs] == build_xs(seqs, V, freq=freq)
+        if log1p:
+            xs = [[[np.log(x + 1) for x in row] for row in rows] for rows in xs]      # experiments_server.py:35
+        _, _, c = pp.FullModelPreprocessor(vocab=vocab, pad_value=0., seq_length=L).transform_data(seqs, xs=xs)
+        assert c.dtype == np.float64 and np.array_equal(c, ref)
+    try:
+        datasets.build_xs([[0, V]], vocab)
+        assert False, "an id >= V must raise like the reference's list index"
+    except IndexError:
+        pass

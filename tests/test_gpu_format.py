@@ -47,3 +47,64 @@ def test_device_formatter_ragged_edge_cases_and_training_equivalence():
     a, _ = hot.loss_batch(hi, ht)
     b, _ = hot.loss_batch(di, dt)
     assert float(a.item()) == float(b.item())
+
+
+# ---- history features on the device (seqrec_history_features) ---------------------------------------------------------
+def test_device_history_features_match_reference_fixture(golden_dir):
+    """Bit-exact against the reference's own build_xs + FullModelPreprocessor output (float64 -> float32 once, the cast
+    the reference's arrays take at the Theano boundary): binary / counts, raw / log(x + 1), full / left-truncated."""
+    from seq_recommendations_b200 import datasets
+    g = np.load(os.path.join(golden_dir, "history_features.npz"))
+    seqs = [g["flat"][g["offs"][i]:g["offs"][i + 1]].tolist() for i in range(len(g["offs"]) - 1)]
+    V = int(g["V"])
+    for freq in (False, True):
+        for tag, L in (("full", None), ("trunc", int(g["T_trunc"]))):
+            for name in ("raw", "log"):
+                ref = g["c_%s_%s_%s" % ("freq" if freq else "bin", name, tag)]
+                c = datasets.history_features_device(seqs, V, seq_length=L, freq=freq, log1p=(name == "log"))
+                assert tuple(c.shape) == ref.shape
+                assert np.array_equal(c.cpu().numpy(), ref.astype(np.float32)), (freq, tag, name)
+
+
+def test_device_history_features_ragged_corpus_against_oracle():
+    """A corpus with empty / length-1 / heavily truncated sequences and a catalog wider than a warp, against the
+    pure-Python oracle; an out-of-range item raises."""
+    from oracle import history
+    from seq_recommendations_b200 import datasets
+    from seq_recommendations_b200._lib import SeqrecError
+    rng = np.random.default_rng(4)
+    V, T = 333, 9
+    seqs = [rng.integers(0, V, size=int(L)).tolist() for L in rng.integers(0, 40, size=120)]
+    seqs[0], seqs[1], seqs[2] = [], [5], [3] * 30                   # empty, one item (all-pad row), one item 30 times
+    for freq, log1p in ((True, True), (True, False), (False, False)):
+        ref = history.history_block(seqs, V, seq_length=T, freq=freq, log1p=log1p)
+        c = datasets.history_features_device(pp.ragged(seqs), V, seq_length=T, freq=freq, log1p=log1p)
+        assert np.array_equal(c.cpu().numpy(), ref.astype(np.float32))
+    assert float(c[0].abs().sum()) == 0.0 and float(c[1].abs().sum()) == 0.0
+    assert float(c[2, -1, 3]) == 1.0 and float(c[2].sum()) == T
+    with pytest.raises(SeqrecError):
+        datasets.history_features_device([[1, 2, V, 3]], V, seq_length=4)
+
+
+def test_device_history_features_feed_the_history_model_like_the_host_arrays():
+    """x_to_y / x_to_z model (experiments_server.py:116-191 variants): the same losses whether the history features come
+    from the host recipe (numpy, float64) or from the device kernel (a CUDA tensor passed as the `xs` input)."""
+    from seq_recommendations_b200 import datasets
+    from seq_recommendations_b200.model import RNNFullModel
+    from seq_recommendations_b200.optimizers import Adagrad
+    rng = np.random.default_rng(8)
+    V, T = 11, 7
+    seqs = [rng.integers(0, V, size=int(L)).tolist() for L in rng.integers(2, 12, size=48)]
+    vocab = dict(zip(range(V), range(V)))
+    xs = [np.log(x + 1.0) for x in datasets.build_xs(seqs, vocab, freq=True)]
+    x, y, c = pp.FullModelPreprocessor(vocab=vocab, seq_length=T).transform_data(seqs, xs=xs)
+    c_dev = datasets.history_features_device(seqs, V, seq_length=T, freq=True, log1p=True)
+    assert np.array_equal(c_dev.cpu().numpy(), c.astype(np.float32))
+    losses = []
+    for feats in (c, c_dev):
+        m = RNNFullModel(T, V, V, z_dim=8, rnn_type="LSTM", y_to_z=True, y_to_y=False, x_to_y=True, x_to_z=True, seed=1)
+        m.compile_model(optimizer=Adagrad(lr=0.05, epsilon=1e-8, clipnorm=1.0))
+        np.random.seed(3)
+        h = m.fit_model([x, feats], y, validation_data=([x, feats], y), n_epochs=2, batch_size=16, verbose=0)
+        losses.append(h.history["loss"] + h.history["val_loss"] + [m.evaluate([x, feats], y)[1][0]])
+    assert np.allclose(losses[0], losses[1], rtol=1e-5), losses
