@@ -220,6 +220,23 @@ def time_cpu(cfg, steps, warmup, budget_s=25.0, sample_b=None):
                            cfg["T"], cfg["V"], b1, ms1, n1, b2, ms2, n2, fixed, slope, B_full), ms_per_step=ms)
 
 
+def scan_info(cfg, B):
+    """Wave structure of the tensor-core recurrent scan for this shape on THIS device: a cluster owns 64 batch rows for
+    all timesteps, and the part keeps only `clusters_resident` of them on its SMs at once (GPC geometry;
+    cudaOccupancyMaxActiveClusters) -- more row groups than that run as a second wave.  None when the shape runs on the
+    register / generic scans."""
+    from seq_recommendations_b200 import _lib
+    cell = _lib.CELL.get(cfg["cell"], -1)
+    lib = _lib.load()
+    if cell < 0 or not lib.seqrec_rnn_tc_applicable(cell, cfg["H"]) or not (cfg["H"] > 128 or cfg["cell"] == "LSTM"):
+        return None                                # (GRU-128 stays on the register scan: engine.HotPath.rnn_tc)
+    resident = int(lib.seqrec_rnn_tc_max_clusters(cell, cfg["H"]))
+    needed = (B + 63) // 64
+    return {"kernel": "rnn_tc_*_kernel", "rows_per_cluster": 64, "cluster_size": cfg["H"] // 32,
+            "clusters_needed": needed, "clusters_resident": resident,
+            "waves": (needed + resident - 1) // resident if resident > 0 else None}
+
+
 def config_dict(args, name, cfg, world, B, vp, cuda_graph):
     """The `config` object of the JSON line -- ONE function for both arms, so the driver's same-config check compares
     like with like."""
@@ -324,6 +341,7 @@ def run_scoring(args, cfg, name):
                 "h2d_bytes_per_step": B * T * 4, "d2h_bytes_per_step": out["last"]["d2h"],
                 "api": "HotPath.topk_batch(pinned host ids, k, last_step_only=True) -> ids.cpu()"},
         "gpu_launches": out["last"]["launches"],
+        "scan": scan_info(cfg, B),
         "all_steps_target_prob": {"value": B / (out["all"]["ms"] * 1e-3), "unit": "sequences/sec",
                                   "ms_per_step": out["all"]["ms"], "e2e_ms_per_step": out["all"]["e2e_ms"],
                                   "algorithmic_tflops": flops_all / (out["all"]["ms"] * 1e-3) / 1e12,
@@ -513,6 +531,7 @@ def measure_training(args, name, cfg, comm, rank, local, steps, warmup, full=Tru
         "roofline": roofline,
         "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
         "phases_ms": per_step,
+        "scan": scan_info(cfg, B),
         "wall_s_timed_region": wall_s,
         "final_loss": final_loss,
     }
@@ -632,14 +651,15 @@ def main():
                                  full=False)
             if r is not None:
                 sub[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "config", "clocks", "phases_ms",
-                                               "gpu_launches")}
+                                               "gpu_launches", "scan")}
                 sub[name]["e2e"] = r["e2e"]["value"]
                 sub[name]["roofline"] = {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac",
                                                                       "ms_per_launch", "issued_tflops")}
         if world == 1:
             sc = run_scoring(args, dict(synthetic.CONFIGS["cfg5_score_gru256_100k"]), "cfg5_score_gru256_100k")
             sub["cfg5_score_gru256_100k"] = {k: sc[k] for k in ("metric", "value", "unit", "ms_per_step", "config",
-                                                                 "clocks", "gpu_launches", "all_steps_target_prob")}
+                                                                 "clocks", "gpu_launches", "scan",
+                                                                 "all_steps_target_prob")}
             sub["cfg5_score_gru256_100k"]["e2e"] = sc["e2e"]["value"]
             sub["cfg5_score_gru256_100k"]["roofline"] = {k: sc["roofline"][k] for k in ("bound", "achieved", "peak",
                                                                                          "unit", "frac")}

@@ -121,6 +121,9 @@ int seqrec_rnn_needs_ut(int cell, int H);
  * new hidden state is all-gathered through distributed shared memory every step.
  * Ut_hi / Ut_lo = seqrec_split_bf16(U, transpose = 1): U^T (G*H, H) as bf16 hi / lo, leading dimension H. */
 int seqrec_rnn_tc_applicable(int cell, int H);
+/* how many clusters of that scan (64 batch rows each) the current device keeps resident at once
+ * (cudaOccupancyMaxActiveClusters): a batch of more than 64 x this many rows runs in waves; < 0 on error */
+int seqrec_rnn_tc_max_clusters(int cell, int H);
 int seqrec_rnn_tc_forward(int cell, int act, float* xg, const uint16_t* Ut_hi, const uint16_t* Ut_lo,
                           const uint8_t* mask, float* hout, float* cst, int T, int B, int H, void* stream);
 /* K4 on the tensor cores, same contract as seqrec_rnn_backward: each CTA forms the K-split partial product of ITS gate

@@ -38,6 +38,7 @@ SIGNATURES = {
     "seqrec_rnn_weight_grad_rd": [_i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_needs_ut": [_i, _i],
     "seqrec_rnn_tc_applicable": [_i, _i],
+    "seqrec_rnn_tc_max_clusters": [_i, _i],
     "seqrec_rnn_tc_forward": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_tc_backward": [_i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "seqrec_rnn_tc_debug_buffer": [_p],

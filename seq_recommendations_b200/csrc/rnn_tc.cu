@@ -766,6 +766,38 @@ extern "C" int seqrec_rnn_tc_debug_buffer(long long* dev_buf) {
   return 0;
 }
 
+namespace {
+template <int CELL, int CS>
+int max_clusters_fwd() {
+  using C = FwdCfg<CELL, CS>;
+  auto k = rnn_tc_forward_kernel<CELL, SEQREC_ACT_TANH, CS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return -(int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CS * 64));
+  cfg.blockDim = dim3(RT_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  e = cudaOccupancyMaxActiveClusters(&n, k, &cfg);
+  return e == cudaSuccess ? n : -(int)e;
+}
+}  // namespace
+
+/* How many clusters of the tensor-core scan (64 batch rows each) the current device keeps resident at once: a batch of
+ * more than 64 x this many rows runs in waves.  The figure depends on how the part's SMs are spread over its GPCs. */
+extern "C" int seqrec_rnn_tc_max_clusters(int cell, int H) {
+  if (!seqrec_rnn_tc_applicable(cell, H)) return -1001;
+  if (cell == SEQREC_CELL_LSTM) return H == 256 ? max_clusters_fwd<SEQREC_CELL_LSTM, 8>() : max_clusters_fwd<SEQREC_CELL_LSTM, 4>();
+  return H == 256 ? max_clusters_fwd<SEQREC_CELL_GRU, 8>() : max_clusters_fwd<SEQREC_CELL_GRU, 4>();
+}
+
 extern "C" int seqrec_rnn_tc_applicable(int cell, int H) {
   return ((cell == SEQREC_CELL_LSTM || cell == SEQREC_CELL_GRU) && (H == 128 || H == 256)) ? 1 : 0;
 }
