@@ -1385,10 +1385,14 @@ int launch_ts_one(int grid, const CUtensorMap& x_hi, const CUtensorMap& x_lo, co
     if (!sync_ws[dev]) {
       e = cudaGetSymbolAddress(&sync_ws[dev], g_ts_sync);
       if (e != cudaSuccess) return -(int)e;
+      // (experiments only: the default mode 0 is the symbol's initial value, so a production run never issues this
+      //  copy -- which would not be allowed if the first call of this variant happened inside a stream capture)
       const char* zm = getenv("SEQREC_ZMN");
       const int mode = zm ? atoi(zm) : 0;
-      e = cudaMemcpyToSymbol(g_ts_zmn_mode, &mode, sizeof(int));
-      if (e != cudaSuccess) return -(int)e;
+      if (mode != 0) {
+        e = cudaMemcpyToSymbol(g_ts_zmn_mode, &mode, sizeof(int));
+        if (e != cudaSuccess) return -(int)e;
+      }
     }
     // (the kernel throttles only when its streamed operand exceeds 32 MB; n_tokens is the upper bound of the device-side
     //  token count, so "fits" here implies "fits" there and the memset node can be dropped)
