@@ -103,40 +103,182 @@ extern "C" int seqrec_pad_sequences(const int32_t* items, const int64_t* offsets
 // warp is one contiguous run of the (T, V) row block.  HBM-bound: n_seqs * T * V * 4 bytes written.
 // table: optional value transform indexed by the count (the drivers' np.log(x + 1), experiments_server.py:35-36,
 // computed on the host in float64 and rounded once, like the reference's own down-cast at the Theano boundary).
+// The inner loop is a handful of instructions per stored vector: the running counts and their (rarely changing) output
+// values live in registers, a match of the walked item with one of the thread's VEC items is the rare branch, and the
+// items are fetched four steps ahead.  (First version: 25 instructions per scalar store, issue-bound at 0.58 of the HBM
+// peak by ncu; profiles/r2_summary.md.)
+template <int VEC>
+struct HistoryRow {
+  int cnt[VEC];
+  float val[VEC];
+  bool bad;
+  __device__ __forceinline__ float value(int c, int freq, const float* __restrict__ table, int table_len) const {
+    const int e = freq ? c : (c > 0 ? 1 : 0);
+    return table ? __ldg(table + (e < table_len ? e : table_len - 1)) : (float)e;
+  }
+  __device__ __forceinline__ void init(int freq, const float* __restrict__ table, int table_len) {
+    bad = false;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { cnt[k] = 0; val[k] = value(0, freq, table, table_len); }
+  }
+  __device__ __forceinline__ void see(int32_t it, int v0, int V, int freq, const float* __restrict__ table,
+                                      int table_len) {
+    bad |= (unsigned)it >= (unsigned)V;
+    const unsigned d = (unsigned)(it - v0);
+    if (d < (unsigned)VEC) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (d == (unsigned)k) { cnt[k] += 1; val[k] = value(cnt[k], freq, table, table_len); }
+    }
+  }
+  __device__ __forceinline__ void store(float* o) const {
+    if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), make_float4(val[0], val[1 % VEC], val[2 % VEC], val[3 % VEC]));
+    else __stcs(o, val[0]);
+  }
+};
+
+template <int VEC>
 __global__ void __launch_bounds__(256)
 history_features_kernel(const int32_t* __restrict__ items, const int64_t* __restrict__ offs, float* __restrict__ out,
                         int64_t n_seqs, int T, int V, int freq, const float* __restrict__ table, int table_len,
                         int32_t* __restrict__ err) {
-  const int64_t total = n_seqs * V;
+  const int units = V / VEC;                                   // threads per sequence
+  const int64_t total = n_seqs * units;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / V;
-    const int v = (int)(i - b * V);
+    const int64_t b = i / units;
+    const int v0 = (int)(i - b * units) * VEC;
     const int64_t start = offs[b], len = offs[b + 1] - start;
     const int64_t rows = len > 0 ? len - 1 : 0;                // xs[:-1]: one row per input position
-    const int64_t keep = rows < T ? rows : T;
+    const int keep = (int)(rows < T ? rows : T);
     const int64_t skip = rows - keep;
-    float* o = out + (b * T) * (int64_t)V + v;
-    int cnt = 0;
-    bool bad = false;
-    for (int64_t j = 0; j < skip; ++j) {
-      const int32_t it = items[start + j];
-      bad |= (it < 0) | (it >= V);
-      cnt += (it == v);
+    const int32_t* __restrict__ ip = items + start;
+    HistoryRow<VEC> h;
+    h.init(freq, table, table_len);
+    for (int64_t j = 0; j < skip; ++j) h.see(__ldg(ip + j), v0, V, freq, table, table_len);
+    ip += skip;
+    float* o = out + (b * T) * (int64_t)V + v0;
+    const int pad = T - keep;
+    for (int t = 0; t < pad; ++t, o += V) {
+      if (VEC == 4) __stcs(reinterpret_cast<float4*>(o), make_float4(0.f, 0.f, 0.f, 0.f));
+      else __stcs(o, 0.f);
     }
-    const int pad = T - (int)keep;
-    for (int t = 0; t < pad; ++t) o[(int64_t)t * V] = 0.f;
-    for (int64_t j = 0; j < keep; ++j) {
-      const int32_t it = items[start + skip + j];
-      bad |= (it < 0) | (it >= V);
-      cnt += (it == v);
-      int c = freq ? cnt : (cnt > 0 ? 1 : 0);
-      float val = (float)c;
-      if (table) val = table[c < table_len ? c : table_len - 1];
-      o[(pad + j) * (int64_t)V] = val;
+    int j = 0;
+    for (; j + 4 <= keep; j += 4) {
+      const int32_t i0 = __ldg(ip + j), i1 = __ldg(ip + j + 1), i2 = __ldg(ip + j + 2), i3 = __ldg(ip + j + 3);
+      h.see(i0, v0, V, freq, table, table_len); h.store(o); o += V;
+      h.see(i1, v0, V, freq, table, table_len); h.store(o); o += V;
+      h.see(i2, v0, V, freq, table, table_len); h.store(o); o += V;
+      h.see(i3, v0, V, freq, table, table_len); h.store(o); o += V;
+    }
+    for (; j < keep; ++j, o += V) {
+      h.see(__ldg(ip + j), v0, V, freq, table, table_len);
+      h.store(o);
     }
     // (the reference's xi[s] raises IndexError for s >= V and silently wraps a negative s: both are errors here)
-    if (v == 0 && bad && err) atomicOr(err, 1);
+    if (v0 == 0 && h.bad && err) atomicOr(err, 1);
   }
+}
+
+// Small catalogs (V <= 32: MSNBC's 17 page categories -- where the reference's history models actually run): a group of
+// LPS lanes (the next power of two >= V) owns one sequence, lane v its item v; a CTA owns 8 * (32 / LPS) consecutive
+// sequences.  The group fetches LPS items with one coalesced load and hands them round by shuffle; the walk is
+// branch-free (with V this small SOME lane of the warp matches at every step, so a "rare" branch is taken every time and
+// serialises the steps: 0.30 of the HBM peak), the value table sits in shared memory, and the unrolled steps of a chunk
+// overlap.  (Staging the rows in shared memory and writing the CTA's contiguous region with float4 stores was measured
+// SLOWER -- 0.27 ms against 0.20 ms at the MSNBC shape: the walk, not the 68-byte row stores, is what binds.)
+constexpr int HIST_TAB = 512;                                  // value-table entries kept in shared memory
+
+// MODE fixes the value transform at compile time (a run-time choice costs a dozen predicated instructions per step):
+// 0 = presence 0/1, 1 = counts, 2 = table[count] from shared memory, 3 = anything else (run-time flags).
+template <int LPS, int MODE>
+__global__ void __launch_bounds__(256)
+history_features_small_kernel(const int32_t* __restrict__ items, const int64_t* __restrict__ offs,
+                              float* __restrict__ out, int64_t n_seqs, int T, int V, int freq,
+                              const float* __restrict__ table, int table_len, int32_t* __restrict__ err) {
+  __shared__ float tab_s[HIST_TAB];
+  constexpr int GPW = 32 / LPS;                                // sequences per warp
+  constexpr int SPC = 8 * GPW;                                 // sequences per CTA
+  const float* tab = table;
+  if ((MODE == 2 || MODE == 3) && table && table_len <= HIST_TAB) {
+    for (int i = threadIdx.x; i < table_len; i += 256) tab_s[i] = __ldg(table + i);
+    __syncthreads();
+    tab = tab_s;
+  }
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPS, v = lane % LPS;
+  const int local = (threadIdx.x >> 5) * GPW + sub;            // sequence within the CTA
+  const int64_t b_base = (int64_t)blockIdx.x * SPC;
+  const int64_t b = b_base + local;
+  const bool live = b < n_seqs;
+  int64_t start = 0, len = 0;
+  if (live) { start = offs[b]; len = offs[b + 1] - start; }
+  const int64_t rows = len > 0 ? len - 1 : 0;
+  const int keep = (int)(rows < T ? rows : T);
+  const int64_t skip = rows - keep;
+  const int pad = T - keep;
+  const int32_t* __restrict__ ip = items + start;
+  const bool writer = live && v < V;
+  const int last = table_len - 1;
+  int cnt = 0, bad = 0;
+  for (int64_t j = 0; j < skip; ++j) {                         // (rare: rows dropped by the left truncation still count)
+    const int32_t it = __ldg(ip + j);
+    bad |= ((unsigned)it >= (unsigned)V) ? 1 : 0;
+    cnt += (it == v) ? 1 : 0;
+  }
+  ip += skip;
+  float* o = out + (b * T) * (int64_t)V + v;
+  if (writer)
+    for (int t = 0; t < pad; ++t) __stcs(o + (size_t)t * V, 0.f);
+  o += (size_t)pad * V;
+  int kmax = keep;
+#pragma unroll
+  for (int d = LPS; d < 32; d <<= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, kmax, d);
+    kmax = other > kmax ? other : kmax;
+  }
+  for (int j0 = 0; j0 < kmax; j0 += LPS, o += (size_t)LPS * V) {
+    const int left = keep - j0;                                // steps of this chunk that exist for this sequence
+    const int32_t chunk = (v < left) ? __ldg(ip + j0 + v) : 0;
+    bad |= ((unsigned)chunk >= (unsigned)V) ? 1 : 0;           // every item is checked once, by the lane that loaded it
+#pragma unroll
+    for (int jj = 0; jj < LPS; ++jj) {
+      const int32_t it = __shfl_sync(0xffffffffu, chunk, jj, LPS);
+      cnt += (jj < left && it == v) ? 1 : 0;
+      float val;
+      if (MODE == 0) val = cnt > 0 ? 1.f : 0.f;
+      else if (MODE == 1) val = (float)cnt;
+      else if (MODE == 2) val = tab_s[cnt < last ? cnt : last];
+      else {
+        const int e = freq ? cnt : (cnt > 0 ? 1 : 0);
+        val = tab ? tab[e < last ? e : last] : (float)e;
+      }
+      if (writer && jj < left) __stcs(o + (size_t)jj * V, val);
+    }
+  }
+  if (live && bad && err) atomicOr(err, 1);
+}
+
+template <int LPS, int MODE>
+int launch_history_small_mode(const int32_t* items, const int64_t* offsets, float* c, int64_t n_seqs, int T, int V,
+                              int freq, const float* table, int table_len, int32_t* err, cudaStream_t st) {
+  constexpr int SPC = 8 * (32 / LPS);
+  const int64_t ctas = (n_seqs + SPC - 1) / SPC;
+  SEQREC_ARG(ctas <= 0x7fffffff, 3);
+  history_features_small_kernel<LPS, MODE><<<(int)ctas, 256, 0, st>>>(items, offsets, c, n_seqs, T, V, freq, table,
+                                                                      table_len, err);
+  return 0;
+}
+
+template <int LPS>
+int launch_history_small(const int32_t* items, const int64_t* offsets, float* c, int64_t n_seqs, int T, int V,
+                         int freq, const float* table, int table_len, int32_t* err, cudaStream_t st) {
+  if (!table && !freq)
+    return launch_history_small_mode<LPS, 0>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+  if (!table)
+    return launch_history_small_mode<LPS, 1>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+  if (freq && table_len <= HIST_TAB)
+    return launch_history_small_mode<LPS, 2>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+  return launch_history_small_mode<LPS, 3>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
 }
 
 extern "C" int seqrec_history_features(const int32_t* items, const int64_t* offsets, float* c, int64_t n_seqs, int T,
@@ -144,10 +286,26 @@ extern "C" int seqrec_history_features(const int32_t* items, const int64_t* offs
                                        void* stream) {
   SEQREC_ARG(items && offsets && c && n_seqs > 0 && T > 0 && V > 0, 1);
   SEQREC_ARG(!table || table_len > 1, 2);
-  int64_t blocks = (n_seqs * V + 255) / 256;
+  if (V <= 32) {
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (V > 16) rc = launch_history_small<32>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+    else if (V > 8) rc = launch_history_small<16>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+    else if (V > 4) rc = launch_history_small<8>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+    else rc = launch_history_small<4>(items, offsets, c, n_seqs, T, V, freq, table, table_len, err, st);
+    if (rc) return rc;
+    SEQREC_CHECK_LAUNCH();
+    return 0;
+  }
+  const bool vec = (V % 4 == 0) && (reinterpret_cast<uintptr_t>(c) % 16 == 0);
+  int64_t blocks = (n_seqs * (vec ? V / 4 : V) + 255) / 256;
   if (blocks > SEQREC_NUM_SMS * 8) blocks = SEQREC_NUM_SMS * 8;
-  history_features_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(items, offsets, c, n_seqs, T, V, freq, table,
-                                                                      table_len, err);
+  if (vec)
+    history_features_kernel<4><<<(int)blocks, 256, 0, as_stream(stream)>>>(items, offsets, c, n_seqs, T, V, freq, table,
+                                                                           table_len, err);
+  else
+    history_features_kernel<1><<<(int)blocks, 256, 0, as_stream(stream)>>>(items, offsets, c, n_seqs, T, V, freq, table,
+                                                                           table_len, err);
   SEQREC_CHECK_LAUNCH();
   return 0;
 }

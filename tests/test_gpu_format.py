@@ -86,6 +86,26 @@ def test_device_history_features_ragged_corpus_against_oracle():
         datasets.history_features_device([[1, 2, V, 3]], V, seq_length=4)
 
 
+@pytest.mark.parametrize("V,T", [(2, 37), (4, 37), (7, 37), (16, 37), (17, 37), (32, 37), (33, 37), (40, 37),
+                                 (17, 130), (5, 300)])
+def test_device_history_features_every_kernel_variant(V, T):
+    """Small catalogs (a group of 4 / 8 / 16 / 32 lanes per sequence, several sequences per warp with different
+    lengths; presence, counts and table modes), the scalar kernel (V = 33) and the float4 kernel (V = 40), with
+    truncation that drops counted rows."""
+    from oracle import history
+    from seq_recommendations_b200 import datasets
+    rng = np.random.default_rng(100 + V)
+    seqs = [rng.integers(0, V, size=int(L)).tolist() for L in rng.integers(0, 90, size=203)]
+    seqs[5], seqs[6], seqs[7] = [], [V - 1], [0] * 80
+    seqs[8] = rng.integers(0, V, size=T + 45).tolist()
+    for freq, log1p in ((True, True), (True, False), (False, False), (False, True)):
+        ref = history.history_block(seqs, V, seq_length=T, freq=freq, log1p=log1p)
+        c = datasets.history_features_device(seqs, V, seq_length=T, freq=freq, log1p=log1p)
+        assert np.array_equal(c.cpu().numpy(), ref.astype(np.float32)), (V, freq, log1p)
+    with pytest.raises(Exception):
+        datasets.history_features_device([[0, 1], [1, V, 0, 1]], V, seq_length=3)
+
+
 def test_device_history_features_feed_the_history_model_like_the_host_arrays():
     """x_to_y / x_to_z model (experiments_server.py:116-191 variants): the same losses whether the history features come
     from the host recipe (numpy, float64) or from the device kernel (a CUDA tensor passed as the `xs` input)."""
