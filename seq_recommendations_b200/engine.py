@@ -494,6 +494,10 @@ class HotPath:
             call("seqrec_gather_rows", ptr(self.W_in), ptr(self.b), ptr(w.ids), ptr(w.mask), ptr(w.in_scale),
                  ptr(w.xg), w.N, self.F, self.GH, st)
         else:
+            if training and self.dropout_in > 0:
+                # (RNNBaseline has no input dropout; a y_to_z_dropout model is fed one-hot / id batches, which take the
+                #  gather path above -- an element-wise mask over a dense (N, F) input is not built, so say so)
+                raise NotImplementedError("y_to_z_dropout on a dense (non one-hot) input batch")
             # K2: time-batched dense input projection (RNNBaseline with [onehot || xs]) -- tcgen05 GEMM when it fills tiles
             gemm(self, w.x_dense.view(w.N, self.F), self.W_in, w.xg.view(w.N, self.GH), "nn", bias=self.b)
         self._mark("rnn_fwd")
