@@ -554,6 +554,58 @@ def hbm_evidence(name, work, per_step, peaks):
             out["ncu"] = json.load(f)
     except Exception:
         out["ncu"] = None
+    try:
+        # the history-feature kernel (datasets.build_xs on the device) is not part of a training step: its committed
+        # probe (scripts/history_probe.py, CUDA events + ncu) rides along as evidence
+        with open(os.path.join(ROOT, "profiles", "r2_history_features.json")) as f:
+            h = json.load(f)
+        out["history_features"] = {k: {"ms": v["ms"], "frac_of_hbm_peak": v["frac_of_hbm_peak"],
+                                       "ncu_dram_throughput_pct": (v.get("ncu") or {}).get("dram_throughput_pct_of_peak")}
+                                   for k, v in h["shapes"].items()}
+    except Exception:
+        out["history_features"] = None
+    return out
+
+
+def history_features_live(peaks, iters=5):
+    """The history-feature kernel (seqrec_history_features: datasets.build_xs on the device) timed
+    live against the HBM roofline -- CUDA events on the launching stream, L2 flushed between launches; algorithmic
+    bytes = n_seqs*T*V*4 written + the ragged corpus read once.  Not part of a training step: a side line of the run."""
+    import ctypes
+    import torch
+    from seq_recommendations_b200._lib import call, ptr
+    dev = torch.device("cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(0)
+    out = {}
+    for name, (n, T, V, lo, hi) in {"msnbc_like_V17_T50_200k_seqs": (200000, 50, 17, 2, 52),
+                                     "cfg2_like_V10k_T50_512_seqs": (512, 50, 10000, 26, 52)}.items():
+        lens = rng.integers(lo, hi, size=n)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        items = torch.from_numpy(rng.integers(0, V, size=int(offs[-1])).astype(np.int32)).to(dev)
+        d_offs = torch.from_numpy(offs).to(dev)
+        table = torch.from_numpy(np.log(np.arange(hi + 1, dtype=np.float64) + 1.0).astype(np.float32)).to(dev)
+        c = torch.empty((n, T, V), dtype=torch.float32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        ms = []
+        for i in range(3 + iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call("seqrec_history_features", ptr(items), ptr(d_offs), ptr(c), n, T, V, 1, ptr(table), hi + 1, ptr(err), st)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms.append(e0.elapsed_time(e1))
+        alg = n * T * V * 4 + int(offs[-1]) * 4 + (n + 1) * 8
+        t = float(np.median(ms))
+        out[name] = {"ms": t, "algorithmic_bytes": alg, "achieved_gbs": alg / t / 1e6, "peak_gbs": peaks["hbm"],
+                     "frac": alg / t / 1e6 / peaks["hbm"]}
+        del items, d_offs, table, c
+    del flush
+    torch.cuda.empty_cache()
     return out
 
 
@@ -664,6 +716,11 @@ def main():
             sub["cfg5_score_gru256_100k"]["roofline"] = {k: sc["roofline"][k] for k in ("bound", "achieved", "peak",
                                                                                          "unit", "frac")}
         extra["configs"] = sub
+        if world == 1 and rank == 0:
+            try:
+                extra["history_features"] = history_features_live(load_peaks())
+            except Exception as e:                 # a side line must never take the bench line down
+                extra["history_features"] = {"error": repr(e)}
     if rank != 0:
         return
     line = {"metric": METRIC, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
