@@ -195,12 +195,15 @@ __global__ void __launch_bounds__(256)
 history_features_small_kernel(const int32_t* __restrict__ items, const int64_t* __restrict__ offs,
                               float* __restrict__ out, int64_t n_seqs, int T, int V, int freq,
                               const float* __restrict__ table, int table_len, int32_t* __restrict__ err) {
-  __shared__ float tab_s[HIST_TAB];
+  // (the entries past the table repeat its last one: MODE 2 walks a pointer through the table and clamps it once per
+  //  chunk of LPS steps instead of at every step)
+  __shared__ float tab_s[HIST_TAB + 32];
   constexpr int GPW = 32 / LPS;                                // sequences per warp
   constexpr int SPC = 8 * GPW;                                 // sequences per CTA
   const float* tab = table;
   if ((MODE == 2 || MODE == 3) && table && table_len <= HIST_TAB) {
-    for (int i = threadIdx.x; i < table_len; i += 256) tab_s[i] = __ldg(table + i);
+    for (int i = threadIdx.x; i < HIST_TAB + 32; i += 256)
+      tab_s[i] = __ldg(table + (i < table_len ? i : table_len - 1));
     __syncthreads();
     tab = tab_s;
   }
@@ -236,21 +239,35 @@ history_features_small_kernel(const int32_t* __restrict__ items, const int64_t* 
     const int other = __shfl_xor_sync(0xffffffffu, kmax, d);
     kmax = other > kmax ? other : kmax;
   }
+  // MODE 0 carries the output value itself (0 until the first match), MODE 2 the shared-memory address of the table
+  // entry of the running count (+4 bytes per match): a step is shuffle, compare, predicated update, load, store
+  float seen = cnt > 0 ? 1.f : 0.f;
+  const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(tab_s);
+  uint32_t va = tab_base + 4u * (uint32_t)(cnt < HIST_TAB - 1 ? cnt : HIST_TAB - 1);
   for (int j0 = 0; j0 < kmax; j0 += LPS, o += (size_t)LPS * V) {
     const int left = keep - j0;                                // steps of this chunk that exist for this sequence
-    const int32_t chunk = (v < left) ? __ldg(ip + j0 + v) : 0;
-    bad |= ((unsigned)chunk >= (unsigned)V) ? 1 : 0;           // every item is checked once, by the lane that loaded it
+    // (steps past the end of the sequence carry the item -1, which matches no lane)
+    const int32_t chunk = (v < left) ? __ldg(ip + j0 + v) : -1;
+    bad |= (v < left && (unsigned)chunk >= (unsigned)V) ? 1 : 0;   // every item is checked once, by the lane that loaded it
+    if (MODE == 2) va = va < tab_base + 4u * (HIST_TAB - 1) ? va : tab_base + 4u * (HIST_TAB - 1);
 #pragma unroll
     for (int jj = 0; jj < LPS; ++jj) {
       const int32_t it = __shfl_sync(0xffffffffu, chunk, jj, LPS);
-      cnt += (jj < left && it == v) ? 1 : 0;
+      const bool hit = it == v;
       float val;
-      if (MODE == 0) val = cnt > 0 ? 1.f : 0.f;
-      else if (MODE == 1) val = (float)cnt;
-      else if (MODE == 2) val = tab_s[cnt < last ? cnt : last];
-      else {
-        const int e = freq ? cnt : (cnt > 0 ? 1 : 0);
-        val = tab ? tab[e < last ? e : last] : (float)e;
+      if (MODE == 0) {
+        seen = hit ? 1.f : seen;
+        val = seen;
+      } else if (MODE == 2) {
+        va += hit ? 4u : 0u;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(va));
+      } else {
+        cnt += hit ? 1 : 0;
+        if (MODE == 1) val = (float)cnt;
+        else {
+          const int e = freq ? cnt : (cnt > 0 ? 1 : 0);
+          val = tab ? tab[e < last ? e : last] : (float)e;
+        }
       }
       if (writer && jj < left) __stcs(o + (size_t)jj * V, val);
     }
