@@ -163,3 +163,31 @@ def test_host_build_xs_matches_reference_fixture(golden_dir):
         assert False, "an id >= V must raise like the reference's list index"
     except IndexError:
         pass
+
+
+def test_host_build_xs_and_preprocessor_equal_the_history_oracle_on_random_corpora():
+    """Property test (hypothesis): for any ragged corpus, catalog width and truncation length, the package's host recipe
+    (datasets.build_xs -> optional log(x + 1) -> FullModelPreprocessor) equals oracle/history.py, which the fixture above
+    pins to the reference's own code."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import history
+    from seq_recommendations_b200 import datasets
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 9).flatmap(lambda V: st.tuples(
+        st.just(V), st.lists(st.lists(st.integers(0, V - 1), min_size=0, max_size=14), min_size=1, max_size=7),
+        st.one_of(st.none(), st.integers(1, 12)), st.booleans(), st.booleans())))
+    def check(case):
+        V, seqs, L, freq, log1p = case
+        if L is None and max(len(s) for s in seqs) < 2:
+            return                                             # (T = 0: the reference's pad_sequences has nothing to pad to)
+        vocab = dict(zip(range(V), range(V)))
+        xs = datasets.build_xs(seqs, vocab, freq=freq)
+        assert [np.asarray(x).reshape(-1, V).tolist() for x in xs] == [r for r in history.build_xs(seqs, V, freq)]
+        if log1p:
+            xs = [np.log(np.asarray(x, dtype=np.float64) + 1) for x in xs]
+        _, _, c = pp.FullModelPreprocessor(vocab=vocab, pad_value=0., seq_length=L).transform_data(seqs, xs=xs)
+        ref = history.history_block(seqs, V, seq_length=L, freq=freq, log1p=log1p)
+        assert c.shape == ref.shape and np.array_equal(c, ref)
+
+    check()
